@@ -1,0 +1,204 @@
+/*
+ * mwgpu.h -- C ABI of the B200-native hot path of keb721/mc_water_ls_mw.
+ *
+ * Drop-in boundary: the reference has no FFI layer; the seam is the Fortran
+ * module `energy` (molint.F90:22-37) plus the move loop of mc_moves.F90 that
+ * drives it.  Every entry point below names the reference interface it
+ * replaces.  All arrays use the reference's own (Fortran column-major) layouts
+ * and 1-based molecule / lattice / image numbers:
+ *
+ *   ljr(3,1,nwater,nlat), ref_ljr(...)   data_structures.f90:39,116
+ *   hmatrix(3,3,nlat)                    data_structures.f90:42
+ *   nn(nwater,nlat), jn(maxneigh,nwater,nlat), vn(maxneigh,nwater,nlat)   molint.F90:79-81
+ *   nivect(nlat), ivect(3,maxnivect,nlat)                                  molint.F90:44-45
+ *
+ * A context owns `nwalkers` independent walker boxes on one CUDA device (one
+ * walker == one MPI rank of the reference).  The fine-grained calls take a
+ * 0-based `walker` index; the batched calls act on all walkers at once.
+ * Every function returns 0 on success and a non-zero code on failure, with
+ * text available from mwgpu_last_error() (the reference `stop`s with a
+ * message; a Fortran shim does `if (ierr/=0) stop`).  A context is not
+ * thread-safe; distinct contexts may be driven from distinct host threads.
+ *
+ * There is NO CPU fallback: every call fails loudly when CUDA is unavailable.
+ */
+#ifndef MWGPU_H
+#define MWGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MWGPU_MAXNEIGH 50      /* molint.F90:79  leading dimension of jn/vn in the ABI */
+#define MWGPU_MAXIVECT 32      /* image vectors supported per lattice (27 in all reference decks) */
+#define MWGPU_LIST_SLOTS 32    /* neighbours per molecule held on the device (reference decks: 16..23) */
+
+typedef struct mwgpu_ctx mwgpu_ctx;
+
+/* run parameters: userparams.f90:14-79 in INTERNAL units (Bohr, Hartree, a.u.
+ * pressure) i.e. after the conversions of io.f90:165,185-186 */
+typedef struct mwgpu_mc_params {
+    double temperature;        /* K */
+    double pressure;           /* a.u. */
+    int    npt;                /* mc_ensemble == 'npt' */
+    double mc_max_trans;       /* Bohr */
+    double mc_dv_max;          /* Bohr */
+    double mc_target_ratio;
+    double wl_factor;
+    int    wl_swetnam;
+    double wl_alpha;
+    int    eta_interp;
+    int    samplerun;
+    int    leshift;
+    int    nbins;
+    double mu_min, mu_max;
+    int    allow_switch, allow_vol, allow_trans;
+    double mc_trans_prob, mc_vol_prob, mc_switch_prob;
+    int    mc_always_switch;
+    int    list_update_int;
+    int    eq_mc_cycles;
+    int    max_mc_cycles;
+    int    eq_adjust_mc;
+    int    monitor_int;
+    int    dd;                 /* parallel_strategy == 'dd' */
+    int    window_overlap;
+    double input_ref_enthalpy[2];
+    int    ls;                 /* initially active lattice (1-based) */
+} mwgpu_mc_params;
+
+/* per-walker observables (what main.f90:200-223 and mc_moves.F90:1722-1792 read) */
+typedef struct mwgpu_walker_state {
+    double model_energy[2];
+    double volume[2];
+    double ls_mu;
+    double mc_max_trans, mc_dv_max;
+    double wl_factor;
+    double my_mu_min, my_mu_max;
+    double average_energy[2];
+    double min_dmu, max_dmu;
+    double ref_enthalpy[2];
+    int64_t rng_index;         /* random numbers consumed so far (draw index) */
+    int    ls;
+    int    mc_cycle_num;
+    int    accepted[3];        /* translations, volume moves, switches   mc_moves.F90:45-47 */
+    int    attempted[3];       /*                                        mc_moves.F90:50-52 */
+    int    my_start_bin, my_end_bin;
+    int    walker_in_window;
+    int    error;              /* MWGPU_ERR_* bits */
+} mwgpu_walker_state;
+
+enum {
+    MWGPU_ERR_LIST_OVERFLOW  = 1,
+    MWGPU_ERR_IVECT_OVERFLOW = 2,
+    MWGPU_ERR_BOND_OVERFLOW  = 4,
+    MWGPU_ERR_ITEM_OVERFLOW  = 8,
+    MWGPU_ERR_SELF_IMAGE     = 16,
+    MWGPU_ERR_RNG_UNDERRUN   = 32,
+    MWGPU_ERR_WINDOW         = 64,
+    MWGPU_ERR_PROB           = 128
+};
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+/* replaces create_model / energy_init allocation (data_structures.f90:66-144, molint.F90:108-143) */
+int  mwgpu_create(int nwater, int nlat, int nwalkers, int device, mwgpu_ctx **out);
+/* replaces energy_deinit / destroy_model (molint.F90:155-171) */
+void mwgpu_destroy(mwgpu_ctx *ctx);
+const char *mwgpu_last_error(void);
+int  mwgpu_device_count(void);
+int  mwgpu_num_walkers(const mwgpu_ctx *ctx);
+
+/* ---- model state: upload after read_xmol / checkpoint load, download before output --- */
+/* walker >= 0: one walker; walker == -1: the same configuration is given to every walker */
+int  mwgpu_upload(mwgpu_ctx *ctx, int walker, const double *ljr, const double *ref_ljr, const double *hmatrix);
+int  mwgpu_download(mwgpu_ctx *ctx, int walker, double *ljr, double *ref_ljr, double *hmatrix);
+/* all walkers at once: arrays carry a leading walker dimension, e.g. ljr(3,1,nwater,nlat,nwalkers) */
+int  mwgpu_upload_all(mwgpu_ctx *ctx, const double *ljr, const double *ref_ljr, const double *hmatrix);
+int  mwgpu_download_all(mwgpu_ctx *ctx, double *ljr, double *ref_ljr, double *hmatrix);
+
+/* ---- module energy (molint.F90) --------------------------------------------------- */
+/* energy_init, molint.F90:91-153: volume, recip matrix, image vectors, lists, energies -- all walkers */
+int  mwgpu_energy_init(mwgpu_ctx *ctx);
+/* compute_ivects(ils), molint.F90:174-217; nivect/ivect(3,MWGPU_MAXIVECT) may be NULL */
+int  mwgpu_compute_ivects(mwgpu_ctx *ctx, int walker, int ils, int *nivect, double *ivect);
+/* compute_neighbours(ils), molint.F90:501-559; nn(nwater), jn/vn(MWGPU_MAXNEIGH,nwater) may be NULL */
+int  mwgpu_compute_neighbours(mwgpu_ctx *ctx, int walker, int ils, int *nn, int *jn, int *vn);
+/* compute_model_energy(ils), molint.F90:407-499; result also kept as model_energy(ils) */
+int  mwgpu_compute_model_energy(mwgpu_ctx *ctx, int walker, int ils, double *energy);
+/* compute_local_real_energy(imol,ils), molint.F90:220-404 */
+int  mwgpu_compute_local_real_energy(mwgpu_ctx *ctx, int walker, int imol, int ils, double *energy);
+/* the same for every molecule of a lattice in one launch: energy(nwater) */
+int  mwgpu_compute_local_real_energy_all(mwgpu_ctx *ctx, int walker, int ils, double *energy);
+/* batched: compute_neighbours / compute_model_energy for every lattice of every walker.
+ * energies(nlat,nwalkers) may be NULL */
+int  mwgpu_compute_neighbours_all(mwgpu_ctx *ctx);
+int  mwgpu_compute_model_energy_all(mwgpu_ctx *ctx, double *energies);
+/* read the current lists without rebuilding them */
+int  mwgpu_get_neighbours(mwgpu_ctx *ctx, int walker, int ils, int *nn, int *jn, int *vn);
+
+/* ---- mc_moves: initialisation (main.f90:146-175, mc_moves.F90:504-877) ------------ */
+/* walker w of this context is rank `first_rank + w` of `size` ranks (windows in dd mode,
+ * log_unbiased_norm).  file_weights = column 2 of eta_weights.dat (or NULL), file_wl_factor
+ * its header value.  Requires mwgpu_energy_init(). */
+int  mwgpu_mc_init(mwgpu_ctx *ctx, const mwgpu_mc_params *p, int first_rank, int size,
+                   const double *file_weights, int n_file_weights, double file_wl_factor);
+/* random stream (random.f90:87-102 draws from the compiler's generator, unpinned):
+ * Philox-4x32-10 keyed by seed, walker w uses stream first_stream + w, first draw = start_index
+ * (main.f90:79-81 burns 1 000 000 draws) ... */
+int  mwgpu_mc_set_rng_philox(mwgpu_ctx *ctx, uint64_t seed, uint32_t first_stream, uint64_t start_index);
+/* ... or a host FIFO of U[0,1) numbers for walker 0 of a 1-walker context: the device consumes
+ * them in the reference's draw order; mwgpu_mc_get_state().rng_index tells how many were used */
+int  mwgpu_mc_set_rng_fifo(mwgpu_ctx *ctx, const double *u, int64_t n);
+
+/* ---- mc_moves: the hot loop -------------------------------------------------------- */
+/* ncycles x mc_cycle (mc_moves.F90:117-255: list refresh, nwater trial moves incl.
+ * mc_water_translation :966, mc_volume :1216, mc_lattice_switch :1536, mc_update_wl_bins :1597,
+ * average-energy accumulation) for every walker.  The periodic bookkeeping of :257-316 is driven
+ * by the host between calls through the functions below. */
+int  mwgpu_mc_run(mwgpu_ctx *ctx, int ncycles);
+int  mwgpu_mc_run_async(mwgpu_ctx *ctx, int ncycles);     /* no host synchronisation */
+int  mwgpu_synchronize(mwgpu_ctx *ctx);
+
+int  mwgpu_mc_get_state(mwgpu_ctx *ctx, int walker, mwgpu_walker_state *out);
+int  mwgpu_mc_get_states(mwgpu_ctx *ctx, mwgpu_walker_state *out /* [nwalkers] */);
+int  mwgpu_mc_get_translations(mwgpu_ctx *ctx, int walker, int *mc_translations /* (nwater) */);
+/* weight / histogram / unbiased_hist (nbins) of one walker; any pointer may be NULL */
+int  mwgpu_mc_get_bins(mwgpu_ctx *ctx, int walker, double *weight, double *histogram, double *unbiased_hist);
+int  mwgpu_mc_set_bins(mwgpu_ctx *ctx, int walker, const double *weight, const double *histogram, const double *unbiased_hist);
+int  mwgpu_mc_get_grid(mwgpu_ctx *ctx, double *mu_bin, double *binwidth, double *scalars /* r_pos,r_neg,av_binwidth,log_unbiased_norm */);
+int  mwgpu_mc_set_wl_factor(mwgpu_ctx *ctx, int walker, double wl_factor, int wl_invt_active);  /* walker -1: all */
+int  mwgpu_mc_set_active_lattice(mwgpu_ctx *ctx, int walker, int ls);
+/* state effects of mc_monitor_stats (mc_moves.F90:1722-1732 step-size adjustment during
+ * equilibration, :1786-1792 energy re-synchronisation, :1797-1810 counter reset), all walkers */
+int  mwgpu_mc_monitor(mwgpu_ctx *ctx);
+/* mc_check_chain_synchronisation (mc_moves.F90:2217-2416), all walkers */
+int  mwgpu_mc_chain_sync(mwgpu_ctx *ctx);
+
+/* ---- comms (comms_mpi.f90:244-277, :461-530): delta-since-last-sync all-reduce ----- */
+/* Sums the increments of weight / histogram / (samplerun) unbiased_hist over all walkers of the
+ * context and, when mwgpu_comms_init() was called, over all ranks with one NCCL all-reduce on
+ * the context's stream; every walker ends with base + total and re-bases. */
+int  mwgpu_comms_allreduce_bins(mwgpu_ctx *ctx);
+/* comms_set_histogram / comms_set_uhistogram (comms_mpi.f90:533-565): re-base after a reset */
+int  mwgpu_comms_set_hist_base(mwgpu_ctx *ctx, const double *histogram, const double *unbiased_hist);
+/* NCCL bootstrap: rank 0 creates an id (128 bytes) and ships it to the other ranks out of band */
+int  mwgpu_comms_get_unique_id(void *id128);
+int  mwgpu_comms_init(mwgpu_ctx *ctx, int nranks, int rank, const void *id128);
+/* the staging buffer [3][nbins_padded] of summed increments, for an external all-reduce
+ * (e.g. torch.distributed): reduce_local -> all-reduce of `*count` doubles at `*dev_ptr` -> apply */
+int  mwgpu_comms_reduce_local(mwgpu_ctx *ctx, void **dev_ptr, int *count);
+int  mwgpu_comms_apply(mwgpu_ctx *ctx);
+
+/* ---- measurement helpers ------------------------------------------------------------ */
+/* elapsed milliseconds of the last mwgpu_mc_run / mwgpu_compute_model_energy_all kernel
+ * (CUDA events on the context's stream) */
+int  mwgpu_last_kernel_ms(mwgpu_ctx *ctx, float *ms);
+/* dependent-free DFMA throughput of the device in TFLOP/s (roofline denominator) */
+int  mwgpu_measure_fp64_peak(int device, double *tflops);
+int  mwgpu_kernel_launches(mwgpu_ctx *ctx, int64_t *count);   /* kernels launched by this context */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,686 @@
+// mw_device.cuh -- warp-cooperative device routines for the mW hot path (sm_100a).
+//
+// One warp owns one walker box.  A walker's positions, packed Verlet lists,
+// image vectors, cell matrices and "bond masks" live in shared memory; every
+// routine below is warp-synchronous (all 32 lanes call it).
+//
+// Two classes of arithmetic are kept strictly apart (DESIGN.md "Parity"):
+//   * STATE arithmetic (positions, cell, fractional transforms, image vectors,
+//     neighbour tests) uses the x*() helpers = explicit round-to-nearest
+//     mul/add/sub/div/sqrt intrinsics that the compiler never contracts into
+//     FMAs, in exactly the reference's operation order, so that it is
+//     bit-identical to the oracle (and to an uncontracted build of the reference).
+//   * ENERGY arithmetic is free-form fp64 (FMA allowed, pairwise shuffle-tree
+//     summation); parity tolerance 1e-11 relative.
+//
+// Reference lines cited as file:line are into keb721/mc_water_ls_mw.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mw {
+
+// ---------------------------------------------------------------- constants
+// constants.f90:23-24,39,43 ; molint.F90:64-74,255,516
+constexpr double PI          = 3.141592653589793238462643383279502884197;
+constexpr double INV_PI      = 1.0 / 3.141592653589793238462643383279502884197;
+constexpr double KB          = 1.0 / 3.1577465e5;
+constexpr double ANG_TO_BOHR = 1.0 / 0.5291772108;
+constexpr double SIGMA   = 2.3925 * ANG_TO_BOHR;
+constexpr double EPSILON = 6.189 / 627.509469;
+constexpr double LAMBDA  = 23.15;
+constexpr double BIGA    = 7.049556277;
+constexpr double BIGB    = 0.6022245584;
+constexpr double GAMMA   = 1.2;
+constexpr double SW_A    = 1.8;
+constexpr double COS0    = (double)(-0.33331324756f);   // single-precision literal, molint.F90:74
+constexpr double RC      = SIGMA * SW_A;
+constexpr double RCSQ    = SIGMA * SW_A * SIGMA * SW_A;
+constexpr double RN      = SW_A * SIGMA * 1.18;
+constexpr double RN2     = RN * RN;
+constexpr double GS      = GAMMA * SIGMA;
+constexpr double AEPS    = BIGA * EPSILON;
+constexpr double LEPS    = LAMBDA * EPSILON;
+constexpr double SS      = SIGMA * SIGMA;
+constexpr double F_HUGE  = 1.7976931348623157e308;
+
+// ---------------------------------------------------------------- capacities
+constexpr int LC  = 32;    // list slots per molecule held in shared memory (one lane per slot)
+constexpr int IVC = 32;    // image vectors per lattice (27 in every BASELINE config)
+constexpr int QC  = 128;   // bond records per batch: 4 evaluations x LC slots can never overflow it
+constexpr int CC  = 64;    // triplet centres per trial move: 2 lattices x LC slots
+constexpr int IC  = 128;   // j-centred triplet items buffered between flushes (any value >= 32 works)
+constexpr int NMAX = 1024; // molecules (10 bits of a packed list entry)
+constexpr unsigned FULL = 0xffffffffu;
+constexpr uint16_t NONE16 = 0xffffu;
+
+// error bits reported per walker
+enum : int {
+    ERR_LIST_OVERFLOW  = 1,    // a molecule has more than LC list neighbours
+    ERR_IVECT_OVERFLOW = 2,    // more than IVC image vectors (cell shrank below the cut-off)
+    ERR_BOND_OVERFLOW  = 4,    // more than QC in-range bonds in one batch
+    ERR_ITEM_OVERFLOW  = 8,    // more than CC centres / IC items in one trial move
+    ERR_SELF_IMAGE     = 16,   // a molecule is its own list neighbour (cell narrower than 1.18*a*sigma)
+    ERR_RNG_UNDERRUN   = 32,   // host FIFO ran dry
+    ERR_WINDOW         = 64,   // dd: walker not in its window at eq_mc_cycles (mc_moves.F90:191-201)
+    ERR_PROB           = 128,  // cumulative move probability error (mc_moves.F90:174)
+};
+
+// ---------------------------------------------------------------- exact (state) arithmetic
+__device__ __forceinline__ double xm(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xa(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xs(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xd(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double xsqrt(double a) { return __dsqrt_rn(a); }
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lt_mask() { return (1u << (threadIdx.x & 31)) - 1u; }
+
+// Fortran m(i,j), 1-based, column-major 3x3
+#define MW_H(m, i, j) ((m)[((j) - 1) * 3 + ((i) - 1)])
+
+// util.f90:16-41
+__device__ __forceinline__ double determinant3(const double* m)
+{
+    double det = xm(MW_H(m,1,1), xs(xm(MW_H(m,2,2), MW_H(m,3,3)), xm(MW_H(m,2,3), MW_H(m,3,2))));
+    det = xs(det, xm(MW_H(m,1,2), xs(xm(MW_H(m,2,1), MW_H(m,3,3)), xm(MW_H(m,2,3), MW_H(m,3,1)))));
+    det = xa(det, xm(MW_H(m,1,3), xs(xm(MW_H(m,2,1), MW_H(m,3,2)), xm(MW_H(m,2,2), MW_H(m,3,1)))));
+    return det;
+}
+
+// util.f90:43-77 (every lane computes the same 9 numbers)
+__device__ __forceinline__ void recipmatrix3(const double* h, double* r)
+{
+    MW_H(r,1,1) = xs(xm(MW_H(h,2,2), MW_H(h,3,3)), xm(MW_H(h,2,3), MW_H(h,3,2)));
+    MW_H(r,1,2) = xs(xm(MW_H(h,2,3), MW_H(h,3,1)), xm(MW_H(h,2,1), MW_H(h,3,3)));
+    MW_H(r,1,3) = xs(xm(MW_H(h,2,1), MW_H(h,3,2)), xm(MW_H(h,2,2), MW_H(h,3,1)));
+    MW_H(r,2,1) = xs(xm(MW_H(h,1,3), MW_H(h,3,2)), xm(MW_H(h,1,2), MW_H(h,3,3)));
+    MW_H(r,2,2) = xs(xm(MW_H(h,1,1), MW_H(h,3,3)), xm(MW_H(h,1,3), MW_H(h,3,1)));
+    MW_H(r,2,3) = xs(xm(MW_H(h,1,2), MW_H(h,3,1)), xm(MW_H(h,1,1), MW_H(h,3,2)));
+    MW_H(r,3,1) = xs(xm(MW_H(h,1,2), MW_H(h,2,3)), xm(MW_H(h,1,3), MW_H(h,2,2)));
+    MW_H(r,3,2) = xs(xm(MW_H(h,1,3), MW_H(h,2,1)), xm(MW_H(h,1,1), MW_H(h,2,3)));
+    MW_H(r,3,3) = xs(xm(MW_H(h,1,1), MW_H(h,2,2)), xm(MW_H(h,1,2), MW_H(h,2,1)));
+    const double vol = xa(xa(xm(MW_H(h,1,1), MW_H(r,1,1)), xm(MW_H(h,1,2), MW_H(r,1,2))), xm(MW_H(h,1,3), MW_H(r,1,3)));
+#pragma unroll
+    for (int k = 0; k < 9; ++k) r[k] = xd(xm(xm(r[k], 2.0), PI), vol);
+}
+
+// ---------------------------------------------------------------- Philox-4x32-10
+// counter = (block_lo, block_hi, stream, 0), key = (seed_lo, seed_hi); two
+// doubles per block (53 high bits of each 64-bit half).  Bit-identical to
+// oracle/mw_oracle.c:orc_philox_block.
+__device__ __forceinline__ void philox_block(uint64_t seed, uint32_t stream, uint64_t block, double& o0, double& o1)
+{
+    uint32_t c0 = (uint32_t)block, c1 = (uint32_t)(block >> 32), c2 = stream, c3 = 0u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const uint64_t a = ((uint64_t)c1 << 32) | c0;
+    const uint64_t b = ((uint64_t)c3 << 32) | c2;
+    o0 = (double)(a >> 11) * 0x1.0p-53;
+    o1 = (double)(b >> 11) * 0x1.0p-53;
+}
+
+// Per-walker stream of U[0,1) numbers (random.f90:87-102).  Each lane buffers
+// two draws; 64 draws per refill.  mode 0: Philox (draw n = half n&1 of block
+// n>>1).  mode 1: host FIFO (draw n = fifo[n]).
+struct WarpRng {
+    double v0, v1;
+    uint64_t base;     // draw index of lane 0's v0 (even)
+    int pos;           // next draw = base + pos, pos in [0,64]
+    int mode;
+    uint64_t seed; uint32_t stream;
+    const double* fifo; uint64_t fifo_len;
+    int underrun;
+
+    __device__ __forceinline__ void refill()
+    {
+        const int lane = lane_id();
+        if (mode == 0) {
+            philox_block(seed, stream, (base >> 1) + (uint64_t)lane, v0, v1);
+        } else {
+            const uint64_t i0 = base + 2u * (uint64_t)lane;
+            v0 = (i0 < fifo_len) ? fifo[i0] : 0.5;
+            v1 = (i0 + 1 < fifo_len) ? fifo[i0 + 1] : 0.5;
+        }
+    }
+    __device__ __forceinline__ void init(uint64_t index)
+    {
+        base = index & ~(uint64_t)1; pos = (int)(index - base); underrun = 0;
+        refill();
+    }
+    __device__ __forceinline__ uint64_t index() const { return base + (uint64_t)pos; }
+    __device__ __forceinline__ double draw()
+    {
+        if (pos == 64) { base += 64; pos = 0; refill(); }
+        if (mode == 1 && base + (uint64_t)pos >= fifo_len) underrun = 1;
+        const double mine = (pos & 1) ? v1 : v0;
+        const double x = __shfl_sync(FULL, mine, pos >> 1);
+        ++pos;
+        return x;
+    }
+};
+
+// ---------------------------------------------------------------- shared-memory view of one walker
+struct WalkerView {
+    int N, nlat;
+    double*   pos;     // [nlat][3][N]   SoA x|y|z
+    double*   iv;      // [nlat][3][IVC]
+    double*   cell;    // [nlat][9]      hmatrix, column-major
+    double*   recip;   // [nlat][9]
+    double*   q;       // [4][QC] scratch: tx,ty,tz,r2 -> ux,uy,uz,g
+    double*   save;    // [36]    old cell + recip during a volume move
+    uint32_t* qmeta;   // [QC]   call | slot<<2 | j<<8 | img<<18
+    uint32_t* cmeta;   // [CC]   lat | slot<<1 | j<<6 | img<<16
+    uint16_t* cq;      // [CC][2] bond record of the centre in the old / new variant
+    uint16_t* items;   // [IC]   centre<<5 | slot
+    uint32_t* bmask;   // [nlat][N] bit s: list slot s currently within the cut-off a*sigma
+    uint16_t* list;    // [nlat][N][LC] packed entries img<<10 | j   (0-based)
+    uint8_t*  nn;      // [nlat][N]
+    int*      niv;     // [2]
+};
+
+__host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+// Layout (every block 16-byte aligned): doubles | list | 32-bit words | 16-bit words | bytes
+__host__ __device__ inline size_t walker_smem_bytes(int N, int nlat)
+{
+    size_t b = 0;
+    b += align16(sizeof(double) * ((size_t)nlat * 3 * N + (size_t)nlat * 3 * IVC + (size_t)nlat * 18 + 4 * QC + 36));
+    b += align16(sizeof(uint16_t) * (size_t)nlat * N * LC);                       // list
+    b += align16(sizeof(uint32_t) * (QC + CC + (size_t)nlat * N + 2));            // qmeta, cmeta, bmask, niv
+    b += align16(sizeof(uint16_t) * (CC * 2 + IC));                               // cq, items
+    b += align16((size_t)nlat * N);                                               // nn
+    return b;
+}
+
+__device__ inline WalkerView carve_walker(unsigned char* base, int N, int nlat)
+{
+    WalkerView w; w.N = N; w.nlat = nlat;
+    unsigned char* p = base;
+    w.pos   = (double*)p;
+    w.iv    = w.pos + (size_t)nlat * 3 * N;
+    w.cell  = w.iv + (size_t)nlat * 3 * IVC;
+    w.recip = w.cell + (size_t)nlat * 9;
+    w.q     = w.recip + (size_t)nlat * 9;
+    w.save  = w.q + 4 * QC;
+    p += align16(sizeof(double) * ((size_t)nlat * 3 * N + (size_t)nlat * 3 * IVC + (size_t)nlat * 18 + 4 * QC + 36));
+    w.list  = (uint16_t*)p;
+    p += align16(sizeof(uint16_t) * (size_t)nlat * N * LC);
+    w.qmeta = (uint32_t*)p;
+    w.cmeta = w.qmeta + QC;
+    w.bmask = w.cmeta + CC;
+    w.niv   = (int*)(w.bmask + (size_t)nlat * N);
+    p += align16(sizeof(uint32_t) * (QC + CC + (size_t)nlat * N + 2));
+    w.cq    = (uint16_t*)p;
+    w.items = w.cq + CC * 2;
+    p += align16(sizeof(uint16_t) * (CC * 2 + IC));
+    w.nn    = (uint8_t*)p;
+    return w;
+}
+
+// ---------------------------------------------------------------- image vectors
+// molint.F90:174-217.  Lane k builds vector k.  Returns nivect (uniform); sets
+// ERR_IVECT_OVERFLOW in err when it exceeds IVC.
+__device__ inline int compute_ivects_warp(const WalkerView& w, int lat, int& err)
+{
+    const double* h = w.cell + 9 * lat;
+    const double l1 = xsqrt(xa(xa(xm(h[0], h[0]), xm(h[1], h[1])), xm(h[2], h[2])));
+    const double l2 = xsqrt(xa(xa(xm(h[3], h[3]), xm(h[4], h[4])), xm(h[5], h[5])));
+    const double l3 = xsqrt(xa(xa(xm(h[6], h[6]), xm(h[7], h[7])), xm(h[8], h[8])));
+    const int im = (int)floor(xd(RC, l1)) + 1;
+    const int jm = (int)floor(xd(RC, l2)) + 1;
+    const int km = (int)floor(xd(RC, l3)) + 1;
+    const int nj = 2 * jm + 1, nk = 2 * km + 1;
+    const int nv = (2 * im + 1) * nj * nk;
+    if (nv > IVC) { err |= ERR_IVECT_OVERFLOW; return nv; }
+    const int f0 = (nv - 1) / 2;           // full-grid index of the (0,0,0) cell
+    const int k = lane_id();
+    if (k < nv) {
+        double vx = 0.0, vy = 0.0, vz = 0.0;
+        if (k > 0) {
+            const int f = (k <= f0) ? k - 1 : k;       // entry 1 (k=0) is the zero vector, skipped in the loop nest
+            const int ic = f / (nj * nk) - im;
+            const int jc = (f / nk) % nj - jm;
+            const int kc = f % nk - km;
+            const double a = (double)ic, b = (double)jc, c = (double)kc;
+            vx = xa(xa(xm(a, h[0]), xm(b, h[3])), xm(c, h[6]));
+            vy = xa(xa(xm(a, h[1]), xm(b, h[4])), xm(c, h[7]));
+            vz = xa(xa(xm(a, h[2]), xm(b, h[5])), xm(c, h[8]));
+        }
+        double* V = w.iv + lat * 3 * IVC;
+        V[k] = vx; V[IVC + k] = vy; V[2 * IVC + k] = vz;
+    }
+    if (k == 0) w.niv[lat] = nv;
+    __syncwarp();
+    return nv;
+}
+
+// index of the image vector that is the negative of image `img`
+__device__ __forceinline__ int inverse_image(int img, int nv)
+{
+    if (img == 0) return 0;
+    const int f0 = (nv - 1) / 2;
+    const int f = (img <= f0) ? img - 1 : img;
+    const int g = nv - 1 - f;
+    return (g < f0) ? g + 1 : g;
+}
+
+// ---------------------------------------------------------------- Verlet list
+// molint.F90:501-559: brute force over (j, image k), emitted in j-ascending,
+// k-ascending order.  Lanes own molecules j; each lane walks the images and
+// keeps a bit mask; entries are then emitted in lane order.
+__device__ inline void compute_neighbours_warp(const WalkerView& w, int lat, int& err)
+{
+    const int N = w.N, lane = lane_id();
+    const int nv = compute_ivects_warp(w, lat, err);          // molint.F90:518
+    if (nv > IVC) return;
+    const double* P = w.pos + lat * 3 * N;
+    const double* V = w.iv + lat * 3 * IVC;
+    for (int i = 0; i < N; ++i) {
+        const double ix = P[i], iy = P[N + i], iz = P[2 * N + i];
+        int total = 0;
+        for (int jb = 0; jb < N; jb += 32) {
+            const int j = jb + lane;
+            uint32_t m = 0;
+            if (j < N) {
+                const double vx = xs(P[j], ix), vy = xs(P[N + j], iy), vz = xs(P[2 * N + j], iz);
+                for (int k = 0; k < nv; ++k) {
+                    const double tx = xa(vx, V[k]), ty = xa(vy, V[IVC + k]), tz = xa(vz, V[2 * IVC + k]);
+                    const double r2 = xa(xa(xm(tx, tx), xm(ty, ty)), xm(tz, tz));
+                    if (r2 < RN2) m |= 1u << k;
+                }
+                if (j == i) {
+                    m &= ~1u;                                   // (k==1).and.(jmol==imol) cycle
+                    if (m) err |= ERR_SELF_IMAGE;
+                }
+            }
+            const int cnt = __popc(m);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
+            }
+            int off = total + incl - cnt;
+            uint16_t* row = w.list + ((size_t)lat * N + i) * LC;
+            while (m) {
+                const int k = __ffs(m) - 1; m &= m - 1;
+                if (off < LC) row[off] = (uint16_t)((k << 10) | j);
+                ++off;
+            }
+            total += __shfl_sync(FULL, incl, 31);
+        }
+        if (total > LC) { err |= ERR_LIST_OVERFLOW; total = LC; }
+        if (lane == 0) w.nn[lat * N + i] = (uint8_t)total;
+    }
+    err = __reduce_or_sync(FULL, err);
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------- bond masks
+// bmask[lat][a] bit s <=> slot s of a's list is inside the cut-off (r^2 < rcsq,
+// molint.F90:276/454).  Lanes are the slots.
+__device__ __forceinline__ uint32_t bond_mask_of(const WalkerView& w, int lat, int a)
+{
+    const int N = w.N, lane = lane_id();
+    const double* P = w.pos + lat * 3 * N;
+    const double* V = w.iv + lat * 3 * IVC;
+    const int nna = w.nn[lat * N + a];
+    const bool has = lane < nna;
+    const uint32_t e = has ? w.list[((size_t)lat * N + a) * LC + lane] : 0u;
+    const int j = e & 1023, img = e >> 10;
+    const double tx = (P[j] + V[img]) - P[a];
+    const double ty = (P[N + j] + V[IVC + img]) - P[N + a];
+    const double tz = (P[2 * N + j] + V[2 * IVC + img]) - P[2 * N + a];
+    const double r2 = tx * tx + ty * ty + tz * tz;
+    return __ballot_sync(FULL, has && r2 < RCSQ);
+}
+
+__device__ inline void compute_bond_masks_warp(const WalkerView& w, int lat)
+{
+    for (int a = 0; a < w.N; ++a) {
+        const uint32_t m = bond_mask_of(w, lat, a);
+        if (lane_id() == 0) w.bmask[lat * w.N + a] = m;
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------- energy kernels (free-form fp64)
+// Pair record evaluation shared by the local and the full energy:
+//   in : q[0..2][r] = separation vector t, q[3][r] = r^2
+//   out: q[0..2][r] = unit vector u = t/r, q[3][r] = lambda*eps-free g = exp(gamma*sigma/(r - a*sigma))
+//   returns the pair energy A*eps*(B*(sigma/r)^4 - 1)*exp(sigma/(r - a*sigma))   (molint.F90:278-297 / :456-461)
+__device__ __forceinline__ double eval_bond(const WalkerView& w, int r)
+{
+    double* q = w.q;
+    const double tx = q[r], ty = q[QC + r], tz = q[2 * QC + r], r2 = q[3 * QC + r];
+    const double ir = rsqrt(r2);
+    const double r1 = ir * r2;
+    const double isr = 1.0 / (r1 - RC);
+    const double e2 = exp(SIGMA * isr);
+    const double g = exp(GS * isr);
+    const double s2 = SS * ir * ir;
+    q[r] = tx * ir; q[QC + r] = ty * ir; q[2 * QC + r] = tz * ir; q[3 * QC + r] = g;
+    return AEPS * (BIGB * (s2 * s2) - 1.0) * e2;
+}
+
+// (cos(theta) - cos0)^2 with the reference's k==i filter (molint.F90:367-371)
+__device__ __forceinline__ double hfun(double ct)
+{
+    const double d = ct - COS0;
+    return (ct < 0.99) ? d * d : 0.0;
+}
+
+// Sum 4 per-lane accumulators over the warp (pairwise shuffle tree) and
+// broadcast the 4 totals to every lane.
+__device__ __forceinline__ void reduce4(double& a0, double& a1, double& a2, double& a3)
+{
+    const int lane = lane_id();
+    // step 1 (xor 16): lanes 0-15 keep (a0,a1), lanes 16-31 keep (a2,a3)
+    {
+        const bool up = lane & 16;
+        const double s0 = up ? a0 : a2, s1 = up ? a1 : a3;
+        const double r0 = __shfl_xor_sync(FULL, s0, 16), r1 = __shfl_xor_sync(FULL, s1, 16);
+        a0 = (up ? a2 : a0) + r0;
+        a1 = (up ? a3 : a1) + r1;
+    }
+    // step 2 (xor 8): within each half, lanes with bit3 clear keep a0, others keep a1
+    {
+        const bool up = lane & 8;
+        const double s = up ? a0 : a1;
+        const double r = __shfl_xor_sync(FULL, s, 8);
+        a0 = (up ? a1 : a0) + r;
+    }
+    a0 += __shfl_xor_sync(FULL, a0, 4);
+    a0 += __shfl_xor_sync(FULL, a0, 2);
+    a0 += __shfl_xor_sync(FULL, a0, 1);
+    // value index held by a lane group: (lane>>4)*2 + ((lane>>3)&1)
+    const double t0 = __shfl_sync(FULL, a0, 0), t1 = __shfl_sync(FULL, a0, 8);
+    const double t2 = __shfl_sync(FULL, a0, 16), t3 = __shfl_sync(FULL, a0, 24);
+    a0 = t0; a1 = t1; a2 = t2; a3 = t3;
+}
+
+__device__ __forceinline__ double warp_sum(double a)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(FULL, a, d);
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Local energies of molecule imol in every lattice, for the current ("old")
+// position and -- when WITH_NEW -- for a trial position pnew[lat] as well
+// (4 evaluations of compute_local_real_energy, molint.F90:220-404, in one
+// flattened pass; mc_moves.F90:1010,1083).
+//
+// Formulation (equal to the reference's sum up to fp64 rounding):
+//   E(i) = sum_{b in bonds(i)} phi2(r_ib)
+//        + lam*eps * sum_{b<c in bonds(i)} g_ib g_ic h(u_ib.u_ic) * (j_b==j_c ? 3 : 1)
+//        + lam*eps * sum_{b in bonds(i)} g_ib sum_{k in bonds(j_b), k not an image of i} g_jk h(-u_ib.u_jk)
+// where bonds(x) are the list entries inside the cut-off.  The factor 3 covers
+// the two j-centred triplets whose third body is another periodic image of i
+// (reference: list-B entries with kmol==imol that survive the cos<0.99 filter).
+// Bonds of the neighbours j come from the cached bond masks; their geometry
+// does not depend on the position of i, so one item evaluation serves both
+// the old and the new variant.
+//
+// Outputs (uniform over the warp): eo[lat], en[lat]; mo[lat]/mn[lat] = in-range
+// slot masks of imol for the old / new position.
+template <int NLAT, bool WITH_NEW>
+__device__ inline void local_energies_warp(const WalkerView& w, int imol, const double (*pnew)[3],
+                                           double* eo, double* en, uint32_t* mo, uint32_t* mn, int& err)
+{
+    const int N = w.N, lane = lane_id();
+    constexpr int nlat = NLAT;
+    const unsigned lt = lt_mask();
+    double* q = w.q;
+    int nq = 0, nc = 0;
+    int seg_start[4] = {0, 0, 0, 0}, seg_n[4] = {0, 0, 0, 0};
+
+    // ---- stage 1: distance tests over imol's own list (lanes = slots), compaction into bond records
+#pragma unroll
+    for (int lat = 0; lat < nlat; ++lat) {
+        const double* P = w.pos + lat * 3 * N;
+        const double* V = w.iv + lat * 3 * IVC;
+        const int nni = w.nn[lat * N + imol];
+        const bool has = lane < nni;
+        const uint32_t e = has ? w.list[((size_t)lat * N + imol) * LC + lane] : 0u;
+        const int j = e & 1023, img = e >> 10;
+        const double pjx = P[j] + V[img], pjy = P[N + j] + V[IVC + img], pjz = P[2 * N + j] + V[2 * IVC + img];
+        const double tox = pjx - P[imol], toy = pjy - P[N + imol], toz = pjz - P[2 * N + imol];
+        const double r2o = tox * tox + toy * toy + toz * toz;
+        const bool fo = has && r2o < RCSQ;
+        const uint32_t bo = __ballot_sync(FULL, fo);
+        mo[lat] = bo;
+        const int io = nq + __popc(bo & lt);
+        seg_start[lat * 2] = nq; seg_n[lat * 2] = __popc(bo); nq += __popc(bo);
+        bool fn = false; int in_ = 0; uint32_t bn = 0;
+        double tnx = 0, tny = 0, tnz = 0, r2n = 0;
+        if (WITH_NEW) {
+            tnx = pjx - pnew[lat][0]; tny = pjy - pnew[lat][1]; tnz = pjz - pnew[lat][2];
+            r2n = tnx * tnx + tny * tny + tnz * tnz;
+            fn = has && r2n < RCSQ;
+            bn = __ballot_sync(FULL, fn);
+            mn[lat] = bn;
+            in_ = nq + __popc(bn & lt);
+            seg_start[lat * 2 + 1] = nq; seg_n[lat * 2 + 1] = __popc(bn); nq += __popc(bn);
+        }
+        const uint32_t bu = bo | bn;
+        const int ic = nc + __popc(bu & lt);
+        nc += __popc(bu);
+        {   // nq <= 4*LC == QC and nc <= 2*LC == CC by construction
+            if (fo) {
+                q[io] = tox; q[QC + io] = toy; q[2 * QC + io] = toz; q[3 * QC + io] = r2o;
+                w.qmeta[io] = (uint32_t)(lat * 2) | ((uint32_t)j << 8);
+            }
+            if (WITH_NEW && fn) {
+                q[in_] = tnx; q[QC + in_] = tny; q[2 * QC + in_] = tnz; q[3 * QC + in_] = r2n;
+                w.qmeta[in_] = (uint32_t)(lat * 2 + 1) | ((uint32_t)j << 8);
+            }
+            if (fo || fn) {
+                w.cmeta[ic] = (uint32_t)lat | ((uint32_t)j << 6);
+                w.cq[ic * 2] = fo ? (uint16_t)io : NONE16;
+                w.cq[ic * 2 + 1] = fn ? (uint16_t)in_ : NONE16;
+            }
+        }
+    }
+    __syncwarp();
+
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;     // per-lane partial sums of the 4 evaluations
+
+    // ---- stage 2: bond evaluation (pair energy, g, unit vector)
+    for (int b = 0; b < nq; b += 32) {
+        const int r = b + lane;
+        if (r < nq) {
+            const double pe = eval_bond(w, r);
+            const int c = w.qmeta[r] & 3;
+            a0 += (c == 0) ? pe : 0.0; a1 += (c == 1) ? pe : 0.0;
+            a2 += (c == 2) ? pe : 0.0; a3 += (c == 3) ? pe : 0.0;
+        }
+    }
+    __syncwarp();
+
+    // ---- stage 3: triplets centred on imol (lanes = bond records, loop over later records of the same call)
+    {
+        int maxn = max(max(seg_n[0], seg_n[1]), max(seg_n[2], seg_n[3]));
+        for (int b = 0; b < nq; b += 32) {
+            const int r = b + lane;
+            const bool act = r < nq;
+            const uint32_t meta = act ? w.qmeta[r] : 0u;
+            const int c = meta & 3;
+            const int send = (c == 0) ? seg_start[0] + seg_n[0] : (c == 1) ? seg_start[1] + seg_n[1]
+                           : (c == 2) ? seg_start[2] + seg_n[2] : seg_start[3] + seg_n[3];
+            const double ux = act ? q[r] : 0.0, uy = act ? q[QC + r] : 0.0, uz = act ? q[2 * QC + r] : 0.0;
+            const double g = act ? q[3 * QC + r] : 0.0;
+            double tb = 0.0;
+            for (int d = 1; d < maxn; ++d) {
+                const int r2i = r + d;
+                if (act && r2i < send) {
+                    const double ct = ux * q[r2i] + uy * q[QC + r2i] + uz * q[2 * QC + r2i];
+                    const double mult = ((w.qmeta[r2i] >> 8) == (meta >> 8)) ? 3.0 : 1.0;
+                    tb += g * q[3 * QC + r2i] * hfun(ct) * mult;
+                }
+            }
+            tb *= LEPS;
+            a0 += (c == 0) ? tb : 0.0; a1 += (c == 1) ? tb : 0.0;
+            a2 += (c == 2) ? tb : 0.0; a3 += (c == 3) ? tb : 0.0;
+        }
+    }
+
+    // ---- stages 4+5: j-centred triplets.  Lanes = centres enumerate the bonds of their j from the
+    // cached bond mask (skipping images of imol) into an item buffer; the buffer is evaluated
+    // (lanes = items) whenever it could overflow and at the end.  One evaluation of (j,k) serves
+    // both variants.
+    auto flush_items = [&](int ni) {
+        for (int b = 0; b < ni; b += 32) {
+            const int t = b + lane;
+            if (t < ni) {
+                const uint32_t it = w.items[t];
+                const int c = it >> 5, s2 = it & 31;
+                const uint32_t cm = w.cmeta[c];
+                const int lat = cm & 1, j = (cm >> 6) & 1023;
+                const double* P = w.pos + lat * 3 * N;
+                const double* V = w.iv + lat * 3 * IVC;
+                const uint32_t e2 = w.list[((size_t)lat * N + j) * LC + s2];
+                const int k = e2 & 1023, img = e2 >> 10;
+                const double tx = (P[k] + V[img]) - P[j];
+                const double ty = (P[N + k] + V[IVC + img]) - P[N + j];
+                const double tz = (P[2 * N + k] + V[2 * IVC + img]) - P[2 * N + j];
+                const double sq = tx * tx + ty * ty + tz * tz;
+                if (sq < RCSQ) {
+                    const double vi = rsqrt(sq);
+                    const double ex = LEPS * exp(GS / (sq * vi - RC));
+                    const double ux = tx * vi, uy = ty * vi, uz = tz * vi;
+                    const uint16_t qo = w.cq[c * 2], qn = w.cq[c * 2 + 1];
+                    double vo = 0.0, vn = 0.0;
+                    if (qo != NONE16) {
+                        const double ct = -(q[qo] * ux + q[QC + qo] * uy + q[2 * QC + qo] * uz);
+                        vo = q[3 * QC + qo] * ex * hfun(ct);
+                    }
+                    if (WITH_NEW && qn != NONE16) {
+                        const double ct = -(q[qn] * ux + q[QC + qn] * uy + q[2 * QC + qn] * uz);
+                        vn = q[3 * QC + qn] * ex * hfun(ct);
+                    }
+                    if (lat == 0) { a0 += vo; a1 += vn; } else { a2 += vo; a3 += vn; }
+                }
+            }
+        }
+    };
+    {
+        int ni = 0;
+        for (int cb = 0; cb < nc; cb += 32) {
+            const int c = cb + lane;
+            const bool act = c < nc;
+            const uint32_t cm = act ? w.cmeta[c] : 0u;
+            const int lat = cm & 1, j = (cm >> 6) & 1023;
+            uint32_t m = act ? w.bmask[lat * N + j] : 0u;
+            const uint16_t* row = w.list + ((size_t)lat * N + j) * LC;
+            while (__any_sync(FULL, m != 0)) {
+                if (ni + 32 > IC) { __syncwarp(); flush_items(ni); __syncwarp(); ni = 0; }
+                bool valid = false; int s2 = 0;
+                if (m) {
+                    s2 = __ffs(m) - 1; m &= m - 1;
+                    valid = (row[s2] & 1023) != imol;
+                }
+                const uint32_t bv = __ballot_sync(FULL, valid);
+                if (valid) w.items[ni + __popc(bv & lt)] = (uint16_t)((c << 5) | s2);
+                ni += __popc(bv);
+            }
+        }
+        __syncwarp();
+        flush_items(ni);
+    }
+
+    reduce4(a0, a1, a2, a3);
+    eo[0] = a0; en[0] = a1;
+    if (nlat == 2) { eo[1] = a2; en[1] = a3; }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Full energy of one lattice (compute_model_energy, molint.F90:407-499), molecule-
+// chunked: bonds of a chunk of molecules are compacted (stage 1), evaluated
+// (stage 2) and combined into i-centred triplets (stage 3).  Also refreshes the
+// bond masks of the lattice.  Returns E (uniform).
+__device__ inline double full_energy_warp(const WalkerView& w, int lat, int& err)
+{
+    const int N = w.N, lane = lane_id();
+    const unsigned lt = lt_mask();
+    const double* P = w.pos + lat * 3 * N;
+    const double* V = w.iv + lat * 3 * IVC;
+    double* q = w.q;
+    double acc = 0.0;
+    int a = 0;
+    while (a < N) {
+        // ---- gather bonds of molecules a.. while they fit in the record buffer
+        int nq = 0;
+        int a1 = a;
+        for (; a1 < N; ++a1) {
+            const int nna = w.nn[lat * N + a1];
+            const bool has = lane < nna;
+            const uint32_t e = has ? w.list[((size_t)lat * N + a1) * LC + lane] : 0u;
+            const int j = e & 1023, img = e >> 10;
+            const double tx = (P[j] + V[img]) - P[a1];
+            const double ty = (P[N + j] + V[IVC + img]) - P[N + a1];
+            const double tz = (P[2 * N + j] + V[2 * IVC + img]) - P[2 * N + a1];
+            const double r2 = tx * tx + ty * ty + tz * tz;
+            const bool f = has && r2 < RCSQ;
+            const uint32_t bm = __ballot_sync(FULL, f);
+            const int cnt = __popc(bm);
+            if (nq + cnt > QC) {
+                if (nq == 0) { err |= ERR_BOND_OVERFLOW; if (lane == 0) w.bmask[lat * N + a1] = bm; ++a1; }
+                break;
+            }
+            if (lane == 0) w.bmask[lat * N + a1] = bm;
+            if (f) {
+                const int io = nq + __popc(bm & lt);
+                q[io] = tx; q[QC + io] = ty; q[2 * QC + io] = tz; q[3 * QC + io] = r2;
+                // meta: molecule (segment id) in the high bits, index of the segment end filled below
+                w.qmeta[io] = (uint32_t)a1 << 8 | (uint32_t)(nq + cnt);
+            }
+            nq += cnt;
+        }
+        __syncwarp();
+        // ---- bond evaluation: 0.5 * pair energy (molint.F90:464)
+        for (int b = 0; b < nq; b += 32) {
+            const int r = b + lane;
+            if (r < nq) acc += 0.5 * eval_bond(w, r);
+        }
+        __syncwarp();
+        // ---- triplets centred on each molecule of the chunk
+        for (int b = 0; b < nq; b += 32) {
+            const int r = b + lane;
+            const bool act = r < nq;
+            const uint32_t meta = act ? w.qmeta[r] : 0u;
+            const int send = meta & 255;
+            const double ux = act ? q[r] : 0.0, uy = act ? q[QC + r] : 0.0, uz = act ? q[2 * QC + r] : 0.0;
+            const double g = act ? q[3 * QC + r] : 0.0;
+            double tb = 0.0;
+            int more = act ? send - r - 1 : 0;
+            const int maxd = __reduce_max_sync(FULL, more);
+            for (int d = 1; d <= maxd; ++d) {
+                const int r2i = r + d;
+                if (act && r2i < send) {
+                    const double ct = ux * q[r2i] + uy * q[QC + r2i] + uz * q[2 * QC + r2i];
+                    // no k==i filter here: compute_model_energy has none (molint.F90:480-483)
+                    const double dd = ct - COS0;
+                    tb += g * q[3 * QC + r2i] * dd * dd;
+                }
+            }
+            acc += LEPS * tb;
+        }
+        __syncwarp();
+        a = a1;
+    }
+    return warp_sum(acc);
+}
+
+}  // namespace mw

@@ -1,0 +1,1271 @@
+// mwgpu.cu -- host side of the C ABI (include/mwgpu.h) and the small service kernels.
+//
+// The two hot kernels are k_mc_run (mw_mc.cuh) and k_model_energy_all (below);
+// everything else here is start-up / bookkeeping plumbing around them.
+#include "../../include/mwgpu.h"
+#include "mw_mc.cuh"
+
+#include <cmath>
+#include <cfloat>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <dlfcn.h>
+
+using namespace mw;
+
+// ------------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(const std::string& msg, int code = 1)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(std::string(#expr) + ": " + cudaGetErrorString(e_), 100 + (int)e_);          \
+    } while (0)
+
+extern "C" const char* mwgpu_last_error(void) { return g_last_error.c_str(); }
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct NcclApi;
+struct mwgpu_ctx {
+    int device = 0;
+    int N = 0, nlat = 0, W = 0, NB = 0, NBP = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DeviceState S{};
+    McParams P{};
+    mwgpu_mc_params user{};
+    bool mc_ready = false, energy_ready = false;
+    int first_rank = 0, size = 1;
+    double* stage = nullptr;       // device staging for layout conversion: [W][nlat][N][3] x2 + cells
+    size_t stage_doubles = 0;
+    double* out = nullptr;         // device scratch for results
+    size_t out_doubles = 0;
+    int* iout = nullptr;
+    size_t iout_ints = 0;
+    double* delta = nullptr;       // [3][NBP] summed increments
+    double* fifo = nullptr;
+    int64_t launches = 0;
+    float last_ms = 0.f;
+    std::vector<double> h_mubin, h_binwidth;
+    // NCCL
+    void* nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+template <typename T>
+static int dalloc(T** p, size_t n)
+{
+    CUDA_TRY(cudaMalloc((void**)p, sizeof(T) * (n ? n : 1)));
+    CUDA_TRY(cudaMemset(*p, 0, sizeof(T) * (n ? n : 1)));
+    return 0;
+}
+
+extern "C" int mwgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int mwgpu_num_walkers(const mwgpu_ctx* c) { return c ? c->W : 0; }
+
+extern "C" int mwgpu_create(int nwater, int nlat, int nwalkers, int device, mwgpu_ctx** out)
+{
+    if (!out) return fail("mwgpu_create: out is NULL");
+    *out = nullptr;
+    if (nwater < 1 || nwater > NMAX) return fail("mwgpu_create: nwater must be in 1..1024");
+    if (nlat != 1 && nlat != 2) return fail("Error num_lattices must equal 1 or 2!");
+    if (nwalkers < 1) return fail("mwgpu_create: nwalkers must be >= 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1)
+        return fail(std::string("mwgpu_create: no CUDA device available (") + cudaGetErrorString(e) +
+                    "); this library has no CPU fallback", 2);
+    if (device < 0 || device >= ndev) return fail("mwgpu_create: invalid device ordinal");
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t smem = walker_smem_bytes(nwater, nlat);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (smem > prop.sharedMemPerBlockOptin)
+        return fail("mwgpu_create: a walker of this size does not fit in shared memory");
+
+    mwgpu_ctx* c = new mwgpu_ctx();
+    c->device = device; c->N = nwater; c->nlat = nlat; c->W = nwalkers;
+    const size_t W = nwalkers, N = nwater, L = nlat;
+    DeviceState& S = c->S;
+    S.N = nwater; S.nlat = nlat; S.W = nwalkers; S.NB = 0;
+    int rc = 0;
+    rc |= dalloc(&S.pos, W * L * 3 * N);
+    rc |= dalloc(&S.ref, W * L * 3 * N);
+    rc |= dalloc(&S.cell, W * L * 9);
+    rc |= dalloc(&S.recip, W * L * 9);
+    rc |= dalloc(&S.refcell, W * L * 9);
+    rc |= dalloc(&S.iv, W * L * 3 * IVC);
+    rc |= dalloc(&S.niv, W * 2);
+    rc |= dalloc(&S.list, W * L * N * LC);
+    rc |= dalloc(&S.nn, W * L * N);
+    rc |= dalloc(&S.scal, W);
+    rc |= dalloc(&S.transcount, W * N);
+    c->stage_doubles = W * L * (2 * 3 * N + 9);
+    rc |= dalloc(&c->stage, c->stage_doubles);
+    c->out_doubles = W * 2 > N ? W * 2 : N;
+    if (c->out_doubles < (size_t)3 * MWGPU_MAXIVECT) c->out_doubles = 3 * MWGPU_MAXIVECT;
+    rc |= dalloc(&c->out, c->out_doubles);
+    c->iout_ints = N * (2 * MWGPU_MAXNEIGH + 1) + 4;
+    rc |= dalloc(&c->iout, c->iout_ints);
+    if (rc) { mwgpu_destroy(c); return rc; }
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+    *out = c;
+    return 0;
+}
+
+static void nccl_destroy(mwgpu_ctx* c);
+
+extern "C" void mwgpu_destroy(mwgpu_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    nccl_destroy(c);
+    DeviceState& S = c->S;
+    void* ptrs[] = {S.pos, S.ref, S.cell, S.recip, S.refcell, S.iv, S.niv, S.list, S.nn, S.scal,
+                    S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.transcount, S.mubin,
+                    S.binwidth, c->stage, c->out, c->iout, c->delta, c->fifo};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int check_ctx(mwgpu_ctx* c, int walker, bool allow_all)
+{
+    if (!c) return fail("mwgpu: NULL context");
+    if (walker < (allow_all ? -1 : 0) || walker >= c->W) return fail("mwgpu: walker index out of range");
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+static int check_ils(mwgpu_ctx* c, int ils)
+{
+    if (ils < 1 || ils > c->nlat) return fail("mwgpu: lattice index ils out of range (1-based)");
+    return 0;
+}
+
+static int finish(mwgpu_ctx* c, bool sync)
+{
+    CUDA_TRY(cudaGetLastError());
+    if (sync) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int mwgpu_synchronize(mwgpu_ctx* c)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int mwgpu_kernel_launches(mwgpu_ctx* c, int64_t* n)
+{
+    if (!c || !n) return fail("mwgpu_kernel_launches: NULL argument");
+    *n = c->launches;
+    return 0;
+}
+
+extern "C" int mwgpu_last_kernel_ms(mwgpu_ctx* c, float* ms)
+{
+    if (!c || !ms) return fail("mwgpu_last_kernel_ms: NULL argument");
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    *ms = c->last_ms;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion kernels: reference AoS ljr(3,1,N,nlat[,W])  <->  device SoA [W][nlat][3][N]
+// ------------------------------------------------------------------------------------------------
+__global__ void k_unpack(DeviceState S, const double* __restrict__ ljr, const double* __restrict__ ref,
+                         const double* __restrict__ hm, int w0, int nw, int bcast)
+{
+    const int N = S.N, L = S.nlat;
+    const size_t per = (size_t)L * N;
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t < (size_t)nw * per) {
+        const int w = (int)(t / per);
+        const int rem = (int)(t % per);
+        const int lat = rem / N, i = rem % N;
+        const size_t src = ((bcast ? 0 : (size_t)w * per) + (size_t)lat * N + i) * 3;
+        const size_t dst = ((size_t)(w0 + w) * L + lat) * 3 * N + i;
+        S.pos[dst] = ljr[src]; S.pos[dst + N] = ljr[src + 1]; S.pos[dst + 2 * N] = ljr[src + 2];
+        S.ref[dst] = ref[src]; S.ref[dst + N] = ref[src + 1]; S.ref[dst + 2 * N] = ref[src + 2];
+    }
+    if (t < (size_t)nw * L * 9) {
+        const int w = (int)(t / (L * 9));
+        const int rem = (int)(t % (L * 9));
+        const double v = hm[(bcast ? 0 : (size_t)w * L * 9) + rem];
+        S.cell[(size_t)(w0 + w) * L * 9 + rem] = v;
+        S.refcell[(size_t)(w0 + w) * L * 9 + rem] = v;
+    }
+}
+
+__global__ void k_pack(DeviceState S, double* __restrict__ ljr, double* __restrict__ ref,
+                       double* __restrict__ hm, int w0, int nw)
+{
+    const int N = S.N, L = S.nlat;
+    const size_t per = (size_t)L * N;
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t < (size_t)nw * per) {
+        const int w = (int)(t / per);
+        const int rem = (int)(t % per);
+        const int lat = rem / N, i = rem % N;
+        const size_t dst = ((size_t)w * per + (size_t)lat * N + i) * 3;
+        const size_t src = ((size_t)(w0 + w) * L + lat) * 3 * N + i;
+        ljr[dst] = S.pos[src]; ljr[dst + 1] = S.pos[src + N]; ljr[dst + 2] = S.pos[src + 2 * N];
+        ref[dst] = S.ref[src]; ref[dst + 1] = S.ref[src + N]; ref[dst + 2] = S.ref[src + 2 * N];
+    }
+    if (t < (size_t)nw * L * 9) {
+        const int w = (int)(t / (L * 9));
+        const int rem = (int)(t % (L * 9));
+        hm[(size_t)w * L * 9 + rem] = S.cell[(size_t)(w0 + w) * L * 9 + rem];
+    }
+}
+
+static int upload_impl(mwgpu_ctx* c, int w0, int nw, int bcast, const double* ljr, const double* ref, const double* hm)
+{
+    if (!ljr || !hm) return fail("mwgpu_upload: ljr and hmatrix must not be NULL");
+    if (!ref) ref = ljr;                               // init.f90:103: ref_ljr = ljr
+    const size_t nsrc = bcast ? 1 : (size_t)nw;
+    const size_t np = nsrc * c->nlat * c->N * 3, nh = nsrc * c->nlat * 9;
+    double* d_ljr = c->stage;
+    double* d_ref = d_ljr + (size_t)c->W * c->nlat * c->N * 3;
+    double* d_hm = d_ref + (size_t)c->W * c->nlat * c->N * 3;
+    CUDA_TRY(cudaMemcpyAsync(d_ljr, ljr, np * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_ref, ref, np * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_hm, hm, nh * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const size_t threads = (size_t)nw * c->nlat * c->N;
+    const int blk = 256;
+    k_unpack<<<(unsigned)((threads + blk - 1) / blk), blk, 0, c->stream>>>(c->S, d_ljr, d_ref, d_hm, w0, nw, bcast);
+    c->launches++;
+    c->energy_ready = false;
+    return finish(c, true);
+}
+
+extern "C" int mwgpu_upload(mwgpu_ctx* c, int walker, const double* ljr, const double* ref, const double* hm)
+{
+    if (int rc = check_ctx(c, walker, true)) return rc;
+    if (walker < 0) return upload_impl(c, 0, c->W, 1, ljr, ref, hm);
+    return upload_impl(c, walker, 1, 0, ljr, ref, hm);
+}
+
+extern "C" int mwgpu_upload_all(mwgpu_ctx* c, const double* ljr, const double* ref, const double* hm)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    return upload_impl(c, 0, c->W, 0, ljr, ref, hm);
+}
+
+static int download_impl(mwgpu_ctx* c, int w0, int nw, double* ljr, double* ref, double* hm)
+{
+    const size_t np = (size_t)nw * c->nlat * c->N * 3, nh = (size_t)nw * c->nlat * 9;
+    double* d_ljr = c->stage;
+    double* d_ref = d_ljr + (size_t)c->W * c->nlat * c->N * 3;
+    double* d_hm = d_ref + (size_t)c->W * c->nlat * c->N * 3;
+    const size_t threads = (size_t)nw * c->nlat * c->N;
+    const int blk = 256;
+    k_pack<<<(unsigned)((threads + blk - 1) / blk), blk, 0, c->stream>>>(c->S, d_ljr, d_ref, d_hm, w0, nw);
+    c->launches++;
+    if (ljr) CUDA_TRY(cudaMemcpyAsync(ljr, d_ljr, np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (ref) CUDA_TRY(cudaMemcpyAsync(ref, d_ref, np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (hm) CUDA_TRY(cudaMemcpyAsync(hm, d_hm, nh * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return finish(c, true);
+}
+
+extern "C" int mwgpu_download(mwgpu_ctx* c, int walker, double* ljr, double* ref, double* hm)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    return download_impl(c, walker, 1, ljr, ref, hm);
+}
+
+extern "C" int mwgpu_download_all(mwgpu_ctx* c, double* ljr, double* ref, double* hm)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    return download_impl(c, 0, c->W, ljr, ref, hm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// service kernel: one warp per walker, op selected at run time
+// ------------------------------------------------------------------------------------------------
+enum WalkerOp : int {
+    OP_ENERGY_INIT = 0,   // molint.F90:91-153
+    OP_IVECTS,            // compute_ivects(lat)
+    OP_NEIGHBOURS,        // compute_neighbours(lat); lat < 0: all lattices
+    OP_MODEL_ENERGY,      // compute_model_energy(lat); lat < 0: all lattices
+    OP_LOCAL_ONE,         // compute_local_real_energy(imol, lat)
+    OP_LOCAL_ALL,         // for every molecule
+    OP_MONITOR,           // state effects of mc_monitor_stats
+    OP_CHAIN_SYNC,        // mc_check_chain_synchronisation
+};
+
+struct OpArgs {
+    int op, w0, lat, imol;
+    double* out;          // per-op result buffer
+    int eq_adjust, eq_mc_cycles;
+    double target_ratio;
+    double beta, pressure; int leshift;
+};
+
+template <int NLAT>
+__global__ void __launch_bounds__(32) k_walker_op(DeviceState S, OpArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int wi = a.w0 + blockIdx.x;
+    if (wi >= S.W) return;
+    const int lane = lane_id(), N = S.N;
+    const WalkerView w = carve_walker(smem, N, NLAT);
+    load_walker(S, wi, w);
+    WalkerScalars sc = S.scal[wi];
+    int err = sc.error;
+    bool store_lists = false;
+
+    switch (a.op) {
+    case OP_ENERGY_INIT: {
+#pragma unroll
+        for (int lat = 0; lat < NLAT; ++lat) {
+            double hm[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) hm[k] = w.cell[lat * 9 + k];
+            sc.vol[lat] = fabs(determinant3(hm));                       // molint.F90:125
+            double rm[9];
+            recipmatrix3(hm, rm);                                       // init.f90:90
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) w.recip[lat * 9 + k] = rm[k];
+            }
+            __syncwarp();
+        }
+        err = 0;
+#pragma unroll
+        for (int lat = 0; lat < NLAT; ++lat) {
+            compute_neighbours_warp(w, lat, err);                       // includes compute_ivects
+            sc.E[lat] = full_energy_warp(w, lat, err);
+        }
+        store_lists = true;
+        break;
+    }
+    case OP_IVECTS:
+        compute_ivects_warp(w, a.lat, err);
+        break;
+    case OP_NEIGHBOURS:
+#pragma unroll
+        for (int lat = 0; lat < NLAT; ++lat)
+            if (a.lat < 0 || a.lat == lat) compute_neighbours_warp(w, lat, err);
+        store_lists = true;
+        break;
+    case OP_MODEL_ENERGY:
+#pragma unroll
+        for (int lat = 0; lat < NLAT; ++lat)
+            if (a.lat < 0 || a.lat == lat) {
+                sc.E[lat] = full_energy_warp(w, lat, err);
+                if (a.out && lane == 0) a.out[(size_t)(wi - a.w0) * NLAT + lat] = sc.E[lat];
+            }
+        break;
+    case OP_LOCAL_ONE:
+    case OP_LOCAL_ALL: {
+#pragma unroll
+        for (int lat = 0; lat < NLAT; ++lat) compute_bond_masks_warp(w, lat);
+        const int i0 = (a.op == OP_LOCAL_ONE) ? a.imol : 0;
+        const int i1 = (a.op == OP_LOCAL_ONE) ? a.imol + 1 : N;
+        for (int i = i0; i < i1; ++i) {
+            double eo[2] = {0, 0}, en[2] = {0, 0};
+            uint32_t mo[2], mn[2];
+            local_energies_warp<NLAT, false>(w, i, nullptr, eo, en, mo, mn, err);
+            if (lane == 0) a.out[i - i0] = (a.lat == 0) ? eo[0] : eo[1];
+        }
+        break;
+    }
+    case OP_MONITOR: {
+        // mc_moves.F90:1722-1732 (exact arithmetic: the step sizes feed the state arithmetic)
+        const double atr = xd((double)sc.acc_r, (double)sc.att_r);
+        const double avr = xd((double)sc.acc_v, (double)sc.att_v);
+        if (a.eq_adjust && sc.cycle < a.eq_mc_cycles) {
+            sc.max_trans = fmax(xd(xm(sc.max_trans, atr), a.target_ratio), 0.1);
+            sc.dv_max = fmax(xd(xm(sc.dv_max, avr), a.target_ratio), 0.0001);
+        }
+#pragma unroll
+        for (int lat = 0; lat < NLAT; ++lat) sc.E[lat] = full_energy_warp(w, lat, err);   // :1786-1792
+        sc.acc_r = sc.acc_v = sc.acc_s = sc.att_r = sc.att_v = sc.att_s = 0;              // :1797-1810
+        for (int i = lane; i < N; i += 32) S.transcount[(size_t)wi * N + i] = 0;
+        sc.avgE[0] = sc.avgE[1] = 0.0;
+        sc.max_dmu = 0.0; sc.min_dmu = F_HUGE;
+        break;
+    }
+    case OP_CHAIN_SYNC: {
+        // mc_moves.F90:2217-2416 (two lattices only)
+        if (NLAT == 2) {
+            sc.E[0] = full_energy_warp(w, 0, err);
+            sc.E[1] = full_energy_warp(w, 1, err);
+            const double* rh = S.refcell + (size_t)wi * NLAT * 9;
+            if (lane < 9) w.cell[9 + lane] = xa(rh[9 + lane], xs(w.cell[lane], rh[lane]));     // :2262,2277
+            __syncwarp();
+            double dummy;
+#pragma unroll
+            for (int lat = 0; lat < 2; ++lat) {
+                double hm[9], rm[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) hm[k] = w.cell[lat * 9 + k];
+                recipmatrix3(hm, rm);
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) w.recip[lat * 9 + k] = rm[k];
+                }
+                __syncwarp();
+            }
+            (void)dummy;
+            const double* R = S.ref + (size_t)wi * NLAT * 3 * N;
+            for (int i = lane; i < N; i += 32) {
+                double sv[2][3], rsv[2][3];
+#pragma unroll
+                for (int lat = 0; lat < 2; ++lat) {
+                    const double* rm = w.recip + 9 * lat;
+                    const double* P = w.pos + lat * 3 * N;
+                    const double* Q = R + lat * 3 * N;
+                    const double a0 = P[i], a1 = P[N + i], a2 = P[2 * N + i];
+                    const double b0 = Q[i], b1 = Q[N + i], b2 = Q[2 * N + i];
+                    sv[lat][0] = xa(xa(xm(MW_H(rm,1,1), a0), xm(MW_H(rm,2,1), a1)), xm(MW_H(rm,3,1), a2));
+                    sv[lat][1] = xa(xa(xm(MW_H(rm,1,2), a0), xm(MW_H(rm,2,2), a1)), xm(MW_H(rm,3,2), a2));
+                    sv[lat][2] = xa(xa(xm(MW_H(rm,1,3), a0), xm(MW_H(rm,2,3), a1)), xm(MW_H(rm,3,3), a2));
+                    rsv[lat][0] = xa(xa(xm(MW_H(rm,1,1), b0), xm(MW_H(rm,2,1), b1)), xm(MW_H(rm,3,1), b2));
+                    rsv[lat][1] = xa(xa(xm(MW_H(rm,1,2), b0), xm(MW_H(rm,2,2), b1)), xm(MW_H(rm,3,2), b2));
+                    rsv[lat][2] = xa(xa(xm(MW_H(rm,1,3), b0), xm(MW_H(rm,2,3), b1)), xm(MW_H(rm,3,3), b2));
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        sv[lat][d] = xm(xm(sv[lat][d], 0.5), INV_PI);
+                        rsv[lat][d] = xm(xm(rsv[lat][d], 0.5), INV_PI);
+                    }
+                }
+                double s2[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) s2[d] = xa(rsv[1][d], xs(sv[0][d], rsv[0][d]));
+                const double* hm = w.cell + 9;
+                double* P2 = w.pos + 3 * N;
+                P2[i]         = xa(xa(xm(MW_H(hm,1,1), s2[0]), xm(MW_H(hm,1,2), s2[1])), xm(MW_H(hm,1,3), s2[2]));
+                P2[N + i]     = xa(xa(xm(MW_H(hm,2,1), s2[0]), xm(MW_H(hm,2,2), s2[1])), xm(MW_H(hm,2,3), s2[2]));
+                P2[2 * N + i] = xa(xa(xm(MW_H(hm,3,1), s2[0]), xm(MW_H(hm,3,2), s2[1])), xm(MW_H(hm,3,3), s2[2]));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int lat = 0; lat < 2; ++lat) {
+                double hm[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) hm[k] = w.cell[lat * 9 + k];
+                sc.vol[lat] = fabs(determinant3(hm));
+                compute_ivects_warp(w, lat, err);
+            }
+            sc.E[0] = full_energy_warp(w, 0, err);
+            sc.E[1] = full_energy_warp(w, 1, err);
+            // left-to-right association (:2400-2402)
+            double mu = sc.E[0] + a.pressure * sc.vol[0] - sc.E[1] - a.pressure * sc.vol[1];
+            if (a.leshift) mu = mu - sc.refH[0] + sc.refH[1];
+            sc.mu = mu * a.beta - (double)N * log(sc.vol[0] / sc.vol[1]);
+        }
+        break;
+    }
+    default: break;
+    }
+    sc.error = err;
+    store_walker(S, wi, w, store_lists);
+    if (lane == 0) S.scal[wi] = sc;
+}
+
+static int launch_op(mwgpu_ctx* c, OpArgs a, int nw, bool sync = true)
+{
+    const size_t smem = walker_smem_bytes(c->N, c->nlat);
+    if (c->nlat == 2) {
+        CUDA_TRY(cudaFuncSetAttribute(k_walker_op<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_walker_op<2><<<nw, 32, smem, c->stream>>>(c->S, a);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_walker_op<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_walker_op<1><<<nw, 32, smem, c->stream>>>(c->S, a);
+    }
+    c->launches++;
+    return finish(c, sync);
+}
+
+static OpArgs make_args(mwgpu_ctx* c, int op, int w0, int lat, int imol, double* out)
+{
+    OpArgs a{};
+    a.op = op; a.w0 = w0; a.lat = lat; a.imol = imol; a.out = out;
+    a.eq_adjust = c->user.eq_adjust_mc; a.eq_mc_cycles = c->user.eq_mc_cycles;
+    a.target_ratio = c->user.mc_target_ratio;
+    a.beta = c->P.beta; a.pressure = c->P.pressure; a.leshift = c->P.leshift;
+    return a;
+}
+
+static int collect_errors(mwgpu_ctx* c, const char* what)
+{
+    std::vector<WalkerScalars> h(c->W);
+    CUDA_TRY(cudaMemcpy(h.data(), c->S.scal, sizeof(WalkerScalars) * c->W, cudaMemcpyDeviceToHost));
+    int all = 0, first = -1;
+    for (int w = 0; w < c->W; ++w) if (h[w].error) { all |= h[w].error; if (first < 0) first = w; }
+    if (!all) return 0;
+    std::string msg = std::string(what) + ": device error bits " + std::to_string(all) + " (first walker " +
+                      std::to_string(first) + "):";
+    if (all & ERR_LIST_OVERFLOW) msg += " a molecule has more than 32 list neighbours;";
+    if (all & ERR_IVECT_OVERFLOW) msg += " more than 32 image vectors (cell narrower than the cut-off);";
+    if (all & ERR_BOND_OVERFLOW) msg += " too many in-range bonds in one batch;";
+    if (all & ERR_ITEM_OVERFLOW) msg += " too many triplet centres/items in one trial move;";
+    if (all & ERR_SELF_IMAGE) msg += " a molecule neighbours its own periodic image (cell too small);";
+    if (all & ERR_RNG_UNDERRUN) msg += " random-number FIFO ran dry;";
+    if (all & ERR_WINDOW) msg += " Error : Not all walkers have reached their designated window;";
+    if (all & ERR_PROB) msg += " Cumulative move type probability error;";
+    return fail(msg, 3);
+}
+
+extern "C" int mwgpu_energy_init(mwgpu_ctx* c)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (int rc = launch_op(c, make_args(c, OP_ENERGY_INIT, 0, -1, 0, nullptr), c->W)) return rc;
+    c->energy_ready = true;
+    return collect_errors(c, "mwgpu_energy_init");
+}
+
+extern "C" int mwgpu_compute_ivects(mwgpu_ctx* c, int walker, int ils, int* nivect, double* ivect)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    if (int rc = check_ils(c, ils)) return rc;
+    if (int rc = launch_op(c, make_args(c, OP_IVECTS, walker, ils - 1, 0, nullptr), 1)) return rc;
+    int niv[2];
+    CUDA_TRY(cudaMemcpy(niv, c->S.niv + walker * 2, sizeof(niv), cudaMemcpyDeviceToHost));
+    if (nivect) *nivect = niv[ils - 1];
+    if (niv[ils - 1] > IVC) return fail("mwgpu_compute_ivects: more than 32 image vectors", 3);
+    if (ivect) {
+        std::vector<double> h(3 * IVC);
+        CUDA_TRY(cudaMemcpy(h.data(), c->S.iv + ((size_t)walker * c->nlat + (ils - 1)) * 3 * IVC,
+                            sizeof(double) * 3 * IVC, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < IVC; ++k)
+            for (int d = 0; d < 3; ++d) ivect[k * 3 + d] = (k < niv[ils - 1]) ? h[d * IVC + k] : 0.0;
+    }
+    return 0;
+}
+
+static int fetch_lists(mwgpu_ctx* c, int walker, int ils, int* nn, int* jn, int* vn)
+{
+    const int N = c->N;
+    std::vector<uint16_t> hl((size_t)N * LC);
+    std::vector<uint8_t> hn(N);
+    CUDA_TRY(cudaMemcpy(hl.data(), c->S.list + ((size_t)walker * c->nlat + (ils - 1)) * N * LC,
+                        sizeof(uint16_t) * N * LC, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(hn.data(), c->S.nn + ((size_t)walker * c->nlat + (ils - 1)) * N, N, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < N; ++i) {
+        if (nn) nn[i] = hn[i];
+        for (int s = 0; s < MWGPU_MAXNEIGH; ++s) {
+            const bool used = s < hn[i] && s < LC;
+            if (jn) jn[i * MWGPU_MAXNEIGH + s] = used ? (hl[(size_t)i * LC + s] & 1023) + 1 : 0;
+            if (vn) vn[i * MWGPU_MAXNEIGH + s] = used ? (hl[(size_t)i * LC + s] >> 10) + 1 : 0;
+        }
+    }
+    return 0;
+}
+
+extern "C" int mwgpu_compute_neighbours(mwgpu_ctx* c, int walker, int ils, int* nn, int* jn, int* vn)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    if (int rc = check_ils(c, ils)) return rc;
+    if (int rc = launch_op(c, make_args(c, OP_NEIGHBOURS, walker, ils - 1, 0, nullptr), 1)) return rc;
+    if (int rc = collect_errors(c, "mwgpu_compute_neighbours")) return rc;
+    return fetch_lists(c, walker, ils, nn, jn, vn);
+}
+
+extern "C" int mwgpu_get_neighbours(mwgpu_ctx* c, int walker, int ils, int* nn, int* jn, int* vn)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    if (int rc = check_ils(c, ils)) return rc;
+    return fetch_lists(c, walker, ils, nn, jn, vn);
+}
+
+extern "C" int mwgpu_compute_neighbours_all(mwgpu_ctx* c)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (int rc = launch_op(c, make_args(c, OP_NEIGHBOURS, 0, -1, 0, nullptr), c->W)) return rc;
+    return collect_errors(c, "mwgpu_compute_neighbours_all");
+}
+
+extern "C" int mwgpu_compute_model_energy(mwgpu_ctx* c, int walker, int ils, double* energy)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    if (int rc = check_ils(c, ils)) return rc;
+    if (int rc = launch_op(c, make_args(c, OP_MODEL_ENERGY, walker, ils - 1, 0, c->out), 1)) return rc;
+    if (energy) CUDA_TRY(cudaMemcpy(energy, c->out + (ils - 1), sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int mwgpu_compute_local_real_energy(mwgpu_ctx* c, int walker, int imol, int ils, double* energy)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    if (int rc = check_ils(c, ils)) return rc;
+    if (imol < 1 || imol > c->N) return fail("mwgpu_compute_local_real_energy: imol out of range (1-based)");
+    if (!energy) return fail("mwgpu_compute_local_real_energy: energy is NULL");
+    if (int rc = launch_op(c, make_args(c, OP_LOCAL_ONE, walker, ils - 1, imol - 1, c->out), 1)) return rc;
+    CUDA_TRY(cudaMemcpy(energy, c->out, sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int mwgpu_compute_local_real_energy_all(mwgpu_ctx* c, int walker, int ils, double* energy)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    if (int rc = check_ils(c, ils)) return rc;
+    if (!energy) return fail("mwgpu_compute_local_real_energy_all: energy is NULL");
+    if (int rc = launch_op(c, make_args(c, OP_LOCAL_ALL, walker, ils - 1, 0, c->out), 1)) return rc;
+    CUDA_TRY(cudaMemcpy(energy, c->out, sizeof(double) * c->N, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched full energy: "full mW energy evals/s" kernel.  One warp per (walker, lattice);
+// needs only positions, lists and image vectors of that lattice.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_model_energy_all(DeviceState S, double* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int unit = blockIdx.x;                 // walker * nlat + lat
+    if (unit >= S.W * S.nlat) return;
+    const int wi = unit / S.nlat, lat = unit % S.nlat;
+    const int lane = lane_id(), N = S.N;
+    // a one-lattice view: lattice `lat` of the walker is staged as lattice 0
+    const WalkerView w = carve_walker(smem, N, 1);
+    const double* gp = S.pos + ((size_t)wi * S.nlat + lat) * 3 * N;
+    for (int t = lane; t < 3 * N; t += 32) w.pos[t] = gp[t];
+    const double* gi = S.iv + ((size_t)wi * S.nlat + lat) * 3 * IVC;
+    for (int t = lane; t < 3 * IVC; t += 32) w.iv[t] = gi[t];
+    const uint4* gl = (const uint4*)(S.list + ((size_t)wi * S.nlat + lat) * N * LC);
+    uint4* sl = (uint4*)w.list;
+    for (int t = lane; t < N * LC / 8; t += 32) sl[t] = gl[t];
+    const uint8_t* gn = S.nn + ((size_t)wi * S.nlat + lat) * N;
+    for (int t = lane; t < N; t += 32) w.nn[t] = gn[t];
+    __syncwarp();
+    int err = 0;
+    const double e = full_energy_warp(w, 0, err);
+    if (lane == 0) {
+        S.scal[wi].E[lat] = e;
+        if (err) atomicOr(&S.scal[wi].error, err);
+        if (out) out[unit] = e;
+    }
+}
+
+extern "C" int mwgpu_compute_model_energy_all(mwgpu_ctx* c, double* energies)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    const size_t smem = walker_smem_bytes(c->N, 1);
+    CUDA_TRY(cudaFuncSetAttribute(k_model_energy_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    k_model_energy_all<<<c->W * c->nlat, 32, smem, c->stream>>>(c->S, c->out);
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->launches++;
+    if (int rc = finish(c, false)) return rc;
+    if (energies)
+        CUDA_TRY(cudaMemcpyAsync(energies, c->out, sizeof(double) * c->W * c->nlat, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mc_init (host): bin grid, windows, weights, log_unbiased_norm, initial order parameter
+// ------------------------------------------------------------------------------------------------
+static double powi(double x, int n)     // x**n, integer n (mc_moves.F90:588,626,642)
+{
+    unsigned m = (n < 0) ? (unsigned)(-n) : (unsigned)n;
+    double y = (m & 1) ? x : 1.0;
+    while (m >>= 1) { x = x * x; if (m & 1) y = y * x; }
+    return (n < 0) ? 1.0 / y : y;
+}
+
+static double gp_ratio(double a, double ssum, int Ns)     // mc_moves.F90:584-594, :604-613
+{
+    double r = 1.1, r_new;
+    int k = 0;
+    for (;;) {
+        ++k;
+        const double tmpsum = a * (1.0 - powi(r, Ns)) / (1.0 - r);
+        r_new = r * std::pow(ssum / tmpsum, 1.0 / (double)Ns);
+        if (std::fabs(r_new - r) <= 2.0 * DBL_EPSILON) break;
+        if (k > 1000000) break;
+        r = r_new;
+    }
+    return r;
+}
+
+extern "C" int mwgpu_mc_init(mwgpu_ctx* c, const mwgpu_mc_params* up, int first_rank, int size,
+                             const double* file_weights, int n_file_weights, double file_wl_factor)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!up) return fail("mwgpu_mc_init: params is NULL");
+    if (!c->energy_ready) return fail("mwgpu_mc_init: call mwgpu_energy_init first");
+    if (size < 1 || first_rank < 0 || first_rank + c->W > size)
+        return fail("mwgpu_mc_init: walkers [first_rank, first_rank+nwalkers) must lie inside [0,size)");
+    c->user = *up;
+    mwgpu_mc_params& u = c->user;
+    c->first_rank = first_rank; c->size = size;
+    const int N = c->N, W = c->W;
+    if (u.nbins % 2 == 0) u.nbins += 1;                                     // :557
+    const int nb = u.nbins;
+    c->NB = nb; c->NBP = (nb + 31) / 32 * 32;
+
+    // ---- grid (:570-656)
+    const double s_pos = std::fabs(u.mu_max) - 0.5, s_neg = std::fabs(u.mu_min) - 0.5;
+    const double a_pos = 1.0, a_neg = 1.0;
+    const int Ns = nb / 2;
+    const double r_pos = gp_ratio(a_pos, s_pos, Ns), r_neg = gp_ratio(a_neg, s_neg, Ns);
+    std::vector<double> mu_bin(nb), bw(nb);
+    {
+        double mu_u = -0.5, mu_l;
+        int k = 0;
+        for (int ibin = nb / 2; ibin >= 1; --ibin) {
+            mu_l = mu_u - a_neg * powi(r_neg, k);
+            mu_bin[ibin - 1] = 0.5 * (mu_u + mu_l);
+            bw[ibin - 1] = mu_u - mu_l;
+            mu_u = mu_l; ++k;
+        }
+        mu_bin[nb / 2] = 0.0; bw[nb / 2] = 1.0;
+        mu_l = 0.5; k = 0;
+        for (int ibin = nb / 2 + 2; ibin <= nb; ++ibin) {
+            mu_u = mu_l + a_pos * powi(r_pos, k);
+            mu_bin[ibin - 1] = 0.5 * (mu_u + mu_l);
+            bw[ibin - 1] = mu_u - mu_l;
+            mu_l = mu_u; ++k;
+        }
+    }
+    double av_bw = 0.0;
+    for (int i = 0; i < nb; ++i) av_bw = av_bw + bw[i];
+    av_bw = av_bw / (double)nb;
+    c->h_mubin = mu_bin; c->h_binwidth = bw;
+
+    // ---- weights (:734-776) and log_unbiased_norm (:781-806)
+    std::vector<double> weight(nb, 0.0);
+    double wl_factor = u.wl_factor;
+    const double orig_wl_factor = u.wl_factor;
+    double lun = 0.0;
+    if (c->nlat == 2) {
+        if (file_weights) {
+            if (file_wl_factor > (double)1e-10f) {
+                wl_factor = std::fmin(wl_factor, file_wl_factor);
+                if (u.samplerun) wl_factor = 0.0;
+            }
+            for (int i = 0; i < n_file_weights && i < nb; ++i) weight[i] = file_weights[i];
+        }
+        double hits = (double)u.max_mc_cycles - (double)u.eq_mc_cycles;
+        hits = hits * (double)(size * N) / (double)nb;
+        double incr = hits * av_bw;
+        lun = std::log(incr) + weight[0];
+        for (int k = 1; k < nb; ++k) {
+            incr = hits * av_bw;
+            if (lun > weight[k] + std::log(incr)) lun = lun + std::log(1.0 + incr * std::exp(weight[k] - lun));
+            else lun = std::log(incr) + weight[k] + std::log(1.0 + std::exp(lun - weight[k]) / incr);
+        }
+    }
+
+    // ---- (re)allocate per-walker bin arrays
+    DeviceState& S = c->S;
+    void* old[] = {S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.mubin, S.binwidth, c->delta};
+    for (void* p : old) if (p) cudaFree(p);
+    S.NB = nb;
+    int rc = 0;
+    rc |= dalloc(&S.weight, (size_t)W * nb); rc |= dalloc(&S.hist, (size_t)W * nb); rc |= dalloc(&S.uhist, (size_t)W * nb);
+    rc |= dalloc(&S.wbase, (size_t)W * nb); rc |= dalloc(&S.hbase, (size_t)W * nb); rc |= dalloc(&S.ubase, (size_t)W * nb);
+    rc |= dalloc(&S.mubin, nb); rc |= dalloc(&S.binwidth, nb);
+    rc |= dalloc(&c->delta, (size_t)3 * c->NBP);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(S.mubin, mu_bin.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(S.binwidth, bw.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
+
+    // ---- per-walker scalars: windows (:659-722), ref_enthalpy (main.f90:146-150), mu (:857-862)
+    std::vector<WalkerScalars> h(W);
+    CUDA_TRY(cudaMemcpy(h.data(), S.scal, sizeof(WalkerScalars) * W, cudaMemcpyDeviceToHost));
+    std::vector<double> hw((size_t)W * nb), hb((size_t)W * nb);
+    const double beta = 1.0 / (KB * u.temperature);
+    for (int w = 0; w < W; ++w) {
+        WalkerScalars& sc = h[w];
+        const int rank = first_rank + w;
+        sc.ls = u.ls;
+        if (u.dd) {
+            const int bpw = nb / size;
+            const int ov = (size == 1) ? 0 : u.window_overlap;             // io.f90:249
+            auto sumw = [&](int n) { double s = 0.0; for (int i = 0; i < n; ++i) s += bw[i]; return s; };
+            if (rank == 0) {
+                sc.start_bin = 1; sc.end_bin = bpw + ov;
+                sc.mu_lo = u.mu_min; sc.mu_hi = u.mu_min + sumw(sc.end_bin);
+            }
+            if (size > 1) {
+                if (rank >= 1 && rank <= size - 2) {
+                    sc.start_bin = rank * bpw - ov; sc.end_bin = (rank + 1) * bpw + ov;
+                    sc.mu_lo = u.mu_min + sumw(sc.start_bin - 1); sc.mu_hi = u.mu_min + sumw(sc.end_bin);
+                }
+                if (rank == size - 1) {
+                    sc.start_bin = rank * bpw - ov; sc.end_bin = nb;
+                    sc.mu_lo = u.mu_min + sumw(sc.start_bin - 1); sc.mu_hi = u.mu_max;
+                }
+            }
+            if (sc.mu_hi < 0.0) sc.ls = 1;
+            if (sc.mu_lo > 0.0) sc.ls = 2;
+        } else {
+            sc.start_bin = 1; sc.end_bin = nb; sc.mu_lo = u.mu_min; sc.mu_hi = u.mu_max;
+        }
+        for (int l = 0; l < c->nlat; ++l) {
+            sc.refH[l] = sc.E[l];
+            if (u.npt) sc.refH[l] = sc.refH[l] + u.pressure * sc.vol[l];
+        }
+        if (std::fabs(u.input_ref_enthalpy[0]) > DBL_MIN || std::fabs(u.input_ref_enthalpy[1]) > DBL_MIN) {
+            sc.refH[0] = u.input_ref_enthalpy[0]; sc.refH[1] = u.input_ref_enthalpy[1];
+        }
+        if (c->nlat == 2) {
+            double mu = sc.E[0] + u.pressure * sc.vol[0] - sc.E[1] - u.pressure * sc.vol[1];
+            if (u.leshift) mu = mu - sc.refH[0] + sc.refH[1];
+            sc.mu = mu * beta - (double)N * std::log(sc.vol[0] / sc.vol[1]);
+        } else {
+            sc.mu = 0.0;
+        }
+        sc.max_trans = u.mc_max_trans; sc.dv_max = u.mc_dv_max; sc.wl_factor = wl_factor;
+        sc.avgE[0] = sc.avgE[1] = 0.0; sc.min_dmu = DBL_MAX; sc.max_dmu = 0.0; sc.sumhist = 0.0;
+        sc.rng_index = 0; sc.cycle = 0;
+        sc.acc_r = sc.acc_v = sc.acc_s = sc.att_r = sc.att_v = sc.att_s = 0;
+        sc.in_window = u.dd ? 0 : 1;
+        sc.wl_invt_active = 0; sc.wmin_zero = 0; sc.error = 0;
+        for (int i = 0; i < nb; ++i) {
+            hb[(size_t)w * nb + i] = weight[i];                            // eta_last_sync = weight (:776)
+            double v = weight[i];
+            if (u.dd && (i + 1 < sc.start_bin || i + 1 > sc.end_bin)) v = 0.0;   // :808-814
+            hw[(size_t)w * nb + i] = v;
+        }
+    }
+    CUDA_TRY(cudaMemcpy(S.scal, h.data(), sizeof(WalkerScalars) * W, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(S.weight, hw.data(), sizeof(double) * W * nb, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(S.wbase, hb.data(), sizeof(double) * W * nb, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(S.transcount, 0, sizeof(int) * W * N));
+
+    // ---- shared run parameters; move-type probabilities (mc_moves.F90:153-176)
+    McParams& P = c->P;
+    P = McParams{};
+    P.beta = beta; P.pressure = u.pressure;
+    double sw = u.mc_switch_prob, vp = u.mc_vol_prob, tp = u.mc_trans_prob;
+    if (u.mc_always_switch) sw = 0.0;
+    if (!u.allow_switch) sw = 0.0;
+    if (!u.npt) vp = 0.0;
+    if (!u.allow_vol) vp = 0.0;
+    if (!u.allow_trans) tp = 0.0;
+    const double sum_prob = tp + vp + sw;
+    P.transP = tp / sum_prob; P.volP = vp / sum_prob; P.swP = sw / sum_prob;
+    P.volP = P.volP + P.transP; P.swP = P.swP + P.volP;
+    P.prob_error = (P.swP < 0.999) ? 1 : 0;
+    P.r_pos = r_pos; P.r_neg = r_neg; P.a_pos = a_pos; P.a_neg = a_neg;
+    P.log_r_pos = std::log(r_pos); P.log_r_neg = std::log(r_neg);
+    P.av_binwidth = av_bw; P.log_unbiased_norm = lun;
+    P.mu_min = u.mu_min; P.mu_max = u.mu_max;
+    P.orig_wl_factor = orig_wl_factor; P.wl_alpha = u.wl_alpha;
+    P.seed = 20141211ull; P.stream0 = (unsigned)first_rank; P.rng_mode = 0;
+    P.nbins = nb;
+    P.npt = u.npt; P.eta_interp = u.eta_interp; P.samplerun = u.samplerun; P.leshift = u.leshift;
+    P.always_switch = (c->nlat == 2) ? u.mc_always_switch : 0; P.dd = u.dd; P.wl_swetnam = u.wl_swetnam;
+    P.list_update_int = u.list_update_int; P.eq_mc_cycles = u.eq_mc_cycles;
+    c->mc_ready = true;
+    return 0;
+}
+
+extern "C" int mwgpu_mc_set_rng_philox(mwgpu_ctx* c, uint64_t seed, uint32_t first_stream, uint64_t start_index)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_mc_set_rng_philox: call mwgpu_mc_init first");
+    c->P.seed = seed; c->P.stream0 = first_stream; c->P.rng_mode = 0;
+    std::vector<WalkerScalars> h(c->W);
+    CUDA_TRY(cudaMemcpy(h.data(), c->S.scal, sizeof(WalkerScalars) * c->W, cudaMemcpyDeviceToHost));
+    for (auto& s : h) s.rng_index = start_index;
+    CUDA_TRY(cudaMemcpy(c->S.scal, h.data(), sizeof(WalkerScalars) * c->W, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int mwgpu_mc_set_rng_fifo(mwgpu_ctx* c, const double* u, int64_t n)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_mc_set_rng_fifo: call mwgpu_mc_init first");
+    if (c->W != 1) return fail("mwgpu_mc_set_rng_fifo: the host FIFO serves single-walker contexts only");
+    if (!u || n < 1) return fail("mwgpu_mc_set_rng_fifo: empty FIFO");
+    if (c->fifo) { cudaFree(c->fifo); c->fifo = nullptr; }
+    CUDA_TRY(cudaMalloc((void**)&c->fifo, sizeof(double) * n));
+    CUDA_TRY(cudaMemcpy(c->fifo, u, sizeof(double) * n, cudaMemcpyHostToDevice));
+    c->S.fifo = c->fifo; c->S.fifo_len = (unsigned long long)n;
+    c->P.rng_mode = 1;
+    WalkerScalars s;
+    CUDA_TRY(cudaMemcpy(&s, c->S.scal, sizeof(s), cudaMemcpyDeviceToHost));
+    s.rng_index = 0;
+    CUDA_TRY(cudaMemcpy(c->S.scal, &s, sizeof(s), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the hot loop
+// ------------------------------------------------------------------------------------------------
+static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_mc_run: call mwgpu_mc_init first");
+    if (ncycles < 0) return fail("mwgpu_mc_run: ncycles must be >= 0");
+    const size_t smem = walker_smem_bytes(c->N, c->nlat);
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    if (c->nlat == 2) {
+        CUDA_TRY(cudaFuncSetAttribute(k_mc_run<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_mc_run<2><<<c->W, 32, smem, c->stream>>>(c->S, c->P, ncycles);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_mc_run<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_mc_run<1><<<c->W, 32, smem, c->stream>>>(c->S, c->P, ncycles);
+    }
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->launches++;
+    if (int rc = finish(c, sync)) return rc;
+    if (sync) return collect_errors(c, "mwgpu_mc_run");
+    return 0;
+}
+
+extern "C" int mwgpu_mc_run(mwgpu_ctx* c, int ncycles) { return mc_run_impl(c, ncycles, true); }
+extern "C" int mwgpu_mc_run_async(mwgpu_ctx* c, int ncycles) { return mc_run_impl(c, ncycles, false); }
+
+static void fill_state(const WalkerScalars& s, mwgpu_walker_state* o)
+{
+    o->model_energy[0] = s.E[0]; o->model_energy[1] = s.E[1];
+    o->volume[0] = s.vol[0]; o->volume[1] = s.vol[1];
+    o->ls_mu = s.mu; o->mc_max_trans = s.max_trans; o->mc_dv_max = s.dv_max; o->wl_factor = s.wl_factor;
+    o->my_mu_min = s.mu_lo; o->my_mu_max = s.mu_hi;
+    o->average_energy[0] = s.avgE[0]; o->average_energy[1] = s.avgE[1];
+    o->min_dmu = s.min_dmu; o->max_dmu = s.max_dmu;
+    o->ref_enthalpy[0] = s.refH[0]; o->ref_enthalpy[1] = s.refH[1];
+    o->rng_index = (int64_t)s.rng_index;
+    o->ls = s.ls; o->mc_cycle_num = s.cycle;
+    o->accepted[0] = s.acc_r; o->accepted[1] = s.acc_v; o->accepted[2] = s.acc_s;
+    o->attempted[0] = s.att_r; o->attempted[1] = s.att_v; o->attempted[2] = s.att_s;
+    o->my_start_bin = s.start_bin; o->my_end_bin = s.end_bin;
+    o->walker_in_window = s.in_window; o->error = s.error;
+}
+
+extern "C" int mwgpu_mc_get_state(mwgpu_ctx* c, int walker, mwgpu_walker_state* out)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    if (!out) return fail("mwgpu_mc_get_state: out is NULL");
+    WalkerScalars s;
+    CUDA_TRY(cudaMemcpyAsync(&s, c->S.scal + walker, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    fill_state(s, out);
+    return 0;
+}
+
+extern "C" int mwgpu_mc_get_states(mwgpu_ctx* c, mwgpu_walker_state* out)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!out) return fail("mwgpu_mc_get_states: out is NULL");
+    std::vector<WalkerScalars> h(c->W);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), c->S.scal, sizeof(WalkerScalars) * c->W, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int w = 0; w < c->W; ++w) fill_state(h[w], out + w);
+    return 0;
+}
+
+extern "C" int mwgpu_mc_get_translations(mwgpu_ctx* c, int walker, int* t)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    if (!t) return fail("mwgpu_mc_get_translations: NULL");
+    CUDA_TRY(cudaMemcpy(t, c->S.transcount + (size_t)walker * c->N, sizeof(int) * c->N, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int mwgpu_mc_get_bins(mwgpu_ctx* c, int walker, double* weight, double* hist, double* uhist)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_mc_get_bins: call mwgpu_mc_init first");
+    const size_t off = (size_t)walker * c->NB, nbytes = sizeof(double) * c->NB;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (weight) CUDA_TRY(cudaMemcpy(weight, c->S.weight + off, nbytes, cudaMemcpyDeviceToHost));
+    if (hist) CUDA_TRY(cudaMemcpy(hist, c->S.hist + off, nbytes, cudaMemcpyDeviceToHost));
+    if (uhist) CUDA_TRY(cudaMemcpy(uhist, c->S.uhist + off, nbytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int mwgpu_mc_set_bins(mwgpu_ctx* c, int walker, const double* weight, const double* hist, const double* uhist)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_mc_set_bins: call mwgpu_mc_init first");
+    const size_t off = (size_t)walker * c->NB, nbytes = sizeof(double) * c->NB;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (weight) CUDA_TRY(cudaMemcpy(c->S.weight + off, weight, nbytes, cudaMemcpyHostToDevice));
+    if (hist) CUDA_TRY(cudaMemcpy(c->S.hist + off, hist, nbytes, cudaMemcpyHostToDevice));
+    if (uhist) CUDA_TRY(cudaMemcpy(c->S.uhist + off, uhist, nbytes, cudaMemcpyHostToDevice));
+    if (weight) {           // the wl-bin update may no longer assume min(weight) == 0
+        WalkerScalars s;
+        CUDA_TRY(cudaMemcpy(&s, c->S.scal + walker, sizeof(s), cudaMemcpyDeviceToHost));
+        s.wmin_zero = 0;
+        CUDA_TRY(cudaMemcpy(c->S.scal + walker, &s, sizeof(s), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+extern "C" int mwgpu_mc_get_grid(mwgpu_ctx* c, double* mu_bin, double* binwidth, double* scalars)
+{
+    if (!c || !c->mc_ready) return fail("mwgpu_mc_get_grid: call mwgpu_mc_init first");
+    if (mu_bin) memcpy(mu_bin, c->h_mubin.data(), sizeof(double) * c->NB);
+    if (binwidth) memcpy(binwidth, c->h_binwidth.data(), sizeof(double) * c->NB);
+    if (scalars) {
+        scalars[0] = c->P.r_pos; scalars[1] = c->P.r_neg; scalars[2] = c->P.av_binwidth;
+        scalars[3] = c->P.log_unbiased_norm;
+    }
+    return 0;
+}
+
+extern "C" int mwgpu_mc_set_wl_factor(mwgpu_ctx* c, int walker, double wl_factor, int wl_invt_active)
+{
+    if (int rc = check_ctx(c, walker, true)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<WalkerScalars> h(c->W);
+    CUDA_TRY(cudaMemcpy(h.data(), c->S.scal, sizeof(WalkerScalars) * c->W, cudaMemcpyDeviceToHost));
+    for (int w = 0; w < c->W; ++w)
+        if (walker < 0 || walker == w) { h[w].wl_factor = wl_factor; h[w].wl_invt_active = wl_invt_active; }
+    CUDA_TRY(cudaMemcpy(c->S.scal, h.data(), sizeof(WalkerScalars) * c->W, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int mwgpu_mc_set_active_lattice(mwgpu_ctx* c, int walker, int ls)
+{
+    if (int rc = check_ctx(c, walker, true)) return rc;
+    if (int rc = check_ils(c, ls)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<WalkerScalars> h(c->W);
+    CUDA_TRY(cudaMemcpy(h.data(), c->S.scal, sizeof(WalkerScalars) * c->W, cudaMemcpyDeviceToHost));
+    for (int w = 0; w < c->W; ++w) if (walker < 0 || walker == w) h[w].ls = ls;
+    CUDA_TRY(cudaMemcpy(c->S.scal, h.data(), sizeof(WalkerScalars) * c->W, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int mwgpu_mc_monitor(mwgpu_ctx* c)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_mc_monitor: call mwgpu_mc_init first");
+    if (int rc = launch_op(c, make_args(c, OP_MONITOR, 0, -1, 0, nullptr), c->W)) return rc;
+    return collect_errors(c, "mwgpu_mc_monitor");
+}
+
+extern "C" int mwgpu_mc_chain_sync(mwgpu_ctx* c)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_mc_chain_sync: call mwgpu_mc_init first");
+    if (c->nlat != 2) return 0;
+    if (int rc = launch_op(c, make_args(c, OP_CHAIN_SYNC, 0, -1, 0, nullptr), c->W)) return rc;
+    return collect_errors(c, "mwgpu_mc_chain_sync");
+}
+
+// ------------------------------------------------------------------------------------------------
+// comms: delta-since-last-sync all-reduce of weight / histogram / unbiased_hist
+// (comms_mpi.f90:244-277, :461-530)
+// ------------------------------------------------------------------------------------------------
+// delta[a][k] = sum over walkers (in walker order) of arr_a[w][k] - base_a[w][k]
+__global__ void k_reduce_bins(DeviceState S, double* __restrict__ delta, int NBP, int narr)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= narr * NBP) return;
+    const int a = t / NBP, k = t % NBP;
+    double s = 0.0;
+    if (k < S.NB) {
+        const double* arr = (a == 0) ? S.weight : (a == 1) ? S.hist : S.uhist;
+        const double* base = (a == 0) ? S.wbase : (a == 1) ? S.hbase : S.ubase;
+        for (int w = 0; w < S.W; ++w) s = s + (arr[(size_t)w * S.NB + k] - base[(size_t)w * S.NB + k]);
+    }
+    delta[t] = s;
+}
+
+// arr = total + base ; base = arr
+__global__ void k_apply_bins(DeviceState S, const double* __restrict__ delta, int NBP, int narr)
+{
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t per = (size_t)S.W * S.NB;
+    if (t >= per * narr) return;
+    const int a = (int)(t / per);
+    const size_t r = t % per;
+    const int k = (int)(r % S.NB);
+    double* arr = (a == 0) ? S.weight : (a == 1) ? S.hist : S.uhist;
+    double* base = (a == 0) ? S.wbase : (a == 1) ? S.hbase : S.ubase;
+    const double v = delta[a * NBP + k] + base[r];
+    arr[r] = v; base[r] = v;
+}
+
+__global__ void k_clear_wmin(DeviceState S)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < S.W) S.scal[w].wmin_zero = 0;
+}
+
+static int narr_of(const mwgpu_ctx* c) { return c->user.samplerun ? 3 : 2; }
+
+extern "C" int mwgpu_comms_reduce_local(mwgpu_ctx* c, void** dev_ptr, int* count)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_comms_reduce_local: call mwgpu_mc_init first");
+    const int narr = narr_of(c), n = narr * c->NBP;
+    k_reduce_bins<<<(n + 127) / 128, 128, 0, c->stream>>>(c->S, c->delta, c->NBP, narr);
+    c->launches++;
+    if (dev_ptr) *dev_ptr = c->delta;
+    if (count) *count = n;
+    return finish(c, dev_ptr != nullptr);
+}
+
+extern "C" int mwgpu_comms_apply(mwgpu_ctx* c)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_comms_apply: call mwgpu_mc_init first");
+    const int narr = narr_of(c);
+    const size_t n = (size_t)c->W * c->NB * narr;
+    k_apply_bins<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->S, c->delta, c->NBP, narr);
+    k_clear_wmin<<<(c->W + 127) / 128, 128, 0, c->stream>>>(c->S);
+    c->launches += 2;
+    return finish(c, true);
+}
+
+extern "C" int mwgpu_comms_set_hist_base(mwgpu_ctx* c, const double* hist, const double* uhist)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_comms_set_hist_base: call mwgpu_mc_init first");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int w = 0; w < c->W; ++w) {
+        if (hist) CUDA_TRY(cudaMemcpy(c->S.hbase + (size_t)w * c->NB, hist, sizeof(double) * c->NB, cudaMemcpyHostToDevice));
+        if (uhist) CUDA_TRY(cudaMemcpy(c->S.ubase + (size_t)w * c->NB, uhist, sizeof(double) * c->NB, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// ---- NCCL, loaded lazily so that the library has no link-time dependency on it -------------------
+typedef struct { char internal[128]; } nccl_unique_id;
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(nccl_unique_id*) = nullptr;
+    int (*CommInitRank)(void**, int, nccl_unique_id, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load()
+{
+    if (g_nccl.handle) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.handle) break; }
+    if (!g_nccl.handle) return fail(std::string("mwgpu_comms: cannot load NCCL: ") + dlerror());
+    g_nccl.GetUniqueId = (int (*)(nccl_unique_id*))dlsym(g_nccl.handle, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, nccl_unique_id, int))dlsym(g_nccl.handle, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.handle, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.handle, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.handle, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail("mwgpu_comms: NCCL symbols missing");
+    return 0;
+}
+
+static int nccl_fail(const char* what, int r)
+{
+    return fail(std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "NCCL error"), 200 + r);
+}
+
+extern "C" int mwgpu_comms_get_unique_id(void* id128)
+{
+    if (!id128) return fail("mwgpu_comms_get_unique_id: NULL");
+    if (int rc = nccl_load()) return rc;
+    nccl_unique_id id;
+    const int r = g_nccl.GetUniqueId(&id);
+    if (r) return nccl_fail("ncclGetUniqueId", r);
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+extern "C" int mwgpu_comms_init(mwgpu_ctx* c, int nranks, int rank, const void* id128)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail("mwgpu_comms_init: bad arguments");
+    if (int rc = nccl_load()) return rc;
+    nccl_unique_id id;
+    memcpy(&id, id128, 128);
+    const int r = g_nccl.CommInitRank(&c->nccl_comm, nranks, id, rank);
+    if (r) return nccl_fail("ncclCommInitRank", r);
+    c->nranks = nranks; c->rank = rank;
+    return 0;
+}
+
+static void nccl_destroy(mwgpu_ctx* c)
+{
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    c->nccl_comm = nullptr;
+}
+
+extern "C" int mwgpu_comms_allreduce_bins(mwgpu_ctx* c)
+{
+    if (int rc = mwgpu_comms_reduce_local(c, nullptr, nullptr)) return rc;
+    if (c->nccl_comm && c->nranks > 1) {
+        const int n = narr_of(c) * c->NBP;
+        // ncclDouble = 8, ncclSum = 0
+        const int r = g_nccl.AllReduce(c->delta, c->delta, (size_t)n, 8, 0, c->nccl_comm, c->stream);
+        if (r) return nccl_fail("ncclAllReduce", r);
+    }
+    return mwgpu_comms_apply(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 peak micro-benchmark: 8 independent DFMA chains per thread
+// ------------------------------------------------------------------------------------------------
+__global__ void k_dfma_peak(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int mwgpu_measure_fp64_peak(int device, double* tflops)
+{
+    if (!tflops) return fail("mwgpu_measure_fp64_peak: NULL");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return fail("mwgpu_measure_fp64_peak: no CUDA device", 2);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0));
+        k_dfma_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
+    return 0;
+}
