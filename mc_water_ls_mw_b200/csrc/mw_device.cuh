@@ -107,8 +107,7 @@ __device__ __forceinline__ void recipmatrix3(const double* h, double* r)
 
 // ---------------------------------------------------------------- Philox-4x32-10
 // counter = (block_lo, block_hi, stream, 0), key = (seed_lo, seed_hi); two
-// doubles per block (53 high bits of each 64-bit half).  Bit-identical to
-// oracle/mw_oracle.c:orc_philox_block.
+// doubles per block (53 high bits of each 64-bit half) -- the stream documented in DESIGN.md "RNG".
 __device__ __forceinline__ void philox_block(uint64_t seed, uint32_t stream, uint64_t block, double& o0, double& o1)
 {
     uint32_t c0 = (uint32_t)block, c1 = (uint32_t)(block >> 32), c2 = stream, c3 = 0u;

@@ -90,17 +90,28 @@ static inline void philox_round(uint32_t c[4], const uint32_t k[2])
     c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
 }
 
-/* Philox-4x32-10.  counter = (block_lo, block_hi, stream, 0), key = (seed_lo, seed_hi).
- * Two doubles per block: 53 high bits of (w1:w0) and of (w3:w2), times 2^-53. */
-void orc_philox_block(uint64_t seed, uint32_t stream, uint64_t block, double out[2])
+/* Philox-4x32-10 (Salmon et al., SC'11), raw form: pinned by the published
+ * known-answer vectors in tests/test_oracle_golden.py. */
+void orc_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {
-    uint32_t c[4] = { (uint32_t)block, (uint32_t)(block >> 32), stream, 0u };
-    uint32_t k[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint32_t c[4] = { ctr[0], ctr[1], ctr[2], ctr[3] };
+    uint32_t k[2] = { key[0], key[1] };
     for (int r = 0; r < 10; ++r) {
         philox_round(c, k);
         k[0] += 0x9E3779B9u;
         k[1] += 0xBB67AE85u;
     }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+/* counter = (block_lo, block_hi, stream, 0), key = (seed_lo, seed_hi).
+ * Two doubles per block: 53 high bits of (w1:w0) and of (w3:w2), times 2^-53. */
+void orc_philox_block(uint64_t seed, uint32_t stream, uint64_t block, double out[2])
+{
+    const uint32_t ctr[4] = { (uint32_t)block, (uint32_t)(block >> 32), stream, 0u };
+    const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint32_t c[4];
+    orc_philox_raw(ctr, key, c);
     const uint64_t a = ((uint64_t)c[1] << 32) | c[0];
     const uint64_t b = ((uint64_t)c[3] << 32) | c[2];
     out[0] = (double)(a >> 11) * 0x1.0p-53;
@@ -1247,7 +1258,7 @@ int64_t orc_get_i(const orc_system *s, const char *name)
     if (!strcmp(name, "nbins")) return s->p.nbins;
     if (!strcmp(name, "error")) return s->error;
     if (!strcmp(name, "nn_warnings")) return s->nn_warnings;
-    if (!strcmp(name, "rng_index")) return (int64_t)s->rng.index;
+    if (!strcmp(name, "rng_index")) return (s->rng.mode == 1) ? s->rng.fifo_pos : (int64_t)s->rng.index;
     if (!strcmp(name, "rng_fifo_pos")) return s->rng.fifo_pos;
     if (!strcmp(name, "wl_invt_active")) return s->wl_invt_active;
     return -1;

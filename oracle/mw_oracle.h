@@ -156,6 +156,7 @@ void   orc_rng_philox(orc_rng *r, uint64_t seed, uint32_t stream, uint64_t start
 void   orc_rng_fifo(orc_rng *r, const double *u, int64_t n);
 double orc_rng_draw(orc_rng *r);
 void   orc_philox_block(uint64_t seed, uint32_t stream, uint64_t block, double out[2]);
+void   orc_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
 /* batch helpers for the CPU baseline (OpenMP over independent walkers) */
 int    orc_mc_run_many(orc_system **walkers, int nwalkers, int ncycles, int nthreads);

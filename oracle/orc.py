@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
     L.orc_mc_run.restype = i; L.orc_mc_run.argtypes = [vp, i]
     L.orc_allreduce_bins.argtypes = [C.POINTER(vp), i]
     L.orc_philox_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, dp]
+    L.orc_philox_raw.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.orc_mc_run_many.restype = i; L.orc_mc_run_many.argtypes = [C.POINTER(vp), i, i, i]
     L.orc_model_energy_many.argtypes = [C.POINTER(vp), i, i, dp]
     L.orc_max_threads.restype = i
@@ -263,3 +264,9 @@ def philox_block(seed: int, stream: int, block: int) -> np.ndarray:
     out = np.zeros(2, dtype=np.float64)
     lib().orc_philox_block(seed, stream, block, _dp(out))
     return out
+
+
+def philox_raw(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr); k = (C.c_uint32 * 2)(*key); o = (C.c_uint32 * 4)()
+    lib().orc_philox_raw(c, k, o)
+    return [int(x) for x in o]

@@ -41,3 +41,38 @@ def make_oracle_walker(name: str, rank: int = 0, size: int = 1, overrides: dict 
     rc = s.mc_init(orc.params_from_user(up), rank=rank, size=size, weights=w, file_wl_factor=wl)
     assert rc == 0
     return s, up
+
+
+def make_gpu_walkers(name: str, nwalkers: int = 1, first_rank: int = 0, size: int | None = None,
+                     overrides: dict | None = None, mc: bool = True):
+    """A WalkerBatch initialised like the reference's start-up sequence (main.f90:98-175)."""
+    from mc_water_ls_mw_b200 import walkers as W
+    size = nwalkers if size is None else size
+    up, h, r, w, wl = load_example(name, size=size)
+    for k, v in (overrides or {}).items():
+        setattr(up, k, v)
+    g = W.WalkerBatch(up.nwater, up.num_lattices, nwalkers)
+    g.upload(r, h)                      # the same xmol configuration for every walker
+    g.energy_init()
+    if mc:
+        g.mc_init(W.params_from_user(up), first_rank, size, w, wl)
+    return g, up
+
+
+def make_oracle_walkers(name: str, nwalkers: int, first_rank: int = 0, size: int | None = None,
+                        overrides: dict | None = None):
+    size = nwalkers if size is None else size
+    return [make_oracle_walker(name, rank=first_rank + w, size=size, overrides=overrides)[0] for w in range(nwalkers)]
+
+
+def used_lists(nn, jn, vn):
+    """Zero the unused tail of jn/vn rows (the reference leaves stale entries beyond nn)."""
+    jn = np.array(jn, copy=True); vn = np.array(vn, copy=True)
+    for i, n in enumerate(np.asarray(nn)):
+        jn[i, n:] = 0; vn[i, n:] = 0
+    return np.asarray(nn), jn, vn
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
