@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: attempted MC moves/s (whole box) and full mW energy evals/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[4], "synthetic scale-out"): 4096 independent
+lattice-switch walkers PER GPU of the ice1 size (48 mW molecules per lattice,
+cubic <-> hexagonal ice, deck + weights of examples/ice1_sample: 200 K, 1 atm,
+samplerun, nbins 101, list_update_int 10).  Weak scaling: every rank owns 4096
+walkers; the only exchange is the delta all-reduce of weights / histograms every
+mpi_sync_int = 250 cycles (NCCL).
+
+A *step* = one call of the hot path over the whole batch: `mc_run(10 cycles)` =
+4096 x 48 x 10 attempted moves per GPU, including the in-kernel neighbour-list
+rebuild that falls into every 10th cycle.  `value` is device-timed with inputs
+resident in HBM; `e2e` is the same step through the C ABI with HOST buffers
+(pinned host -> device upload of every walker's positions / reference positions /
+cells, list + energy re-initialisation as after a checkpoint load, the 10 cycles,
+and the device -> host read of positions and observables) inside the timed region.
+
+`--impl reference`: the reference cannot be compiled here (no Fortran compiler, no
+MPI in this image or on the GPU box); the arm times the CPU oracle (C restatement of
+the same algorithm, oracle/mw_oracle.c) on all host cores, same config and metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WALKERS_PER_GPU = 4096
+CYCLES_PER_STEP = 10
+FLOP_PER_MOVE = 10730.0          # BASELINE.md section 3 / SURVEY.md 8(d): average attempted LS move
+FLOP_PER_EVAL = 35424.0          # one lattice full energy (mean of 34560 / 36288)
+BYTES_PER_EVAL = 8336.0          # one lattice, reference int32 list layout (mean of 8144 / 8528)
+EXAMPLE = "ice1_sample"
+SEED = 20141211
+
+
+def _example():
+    from mc_water_ls_mw_b200 import decks
+    d = os.path.join(ROOT, "tests", "golden", "examples", EXAMPLE)
+    up = decks.read_input(os.path.join(d, "ice.input"))
+    h, r = decks.read_config(d, up)
+    wl, _, w = decks.read_eta_weights(os.path.join(d, "eta_weights.dat"))
+    return up, h, r, w, wl
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons during the timed region (pynvml)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def finish(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU oracle on the host cores
+# --------------------------------------------------------------------------------------------------
+def _oracle_walkers(n, up, h, r, w, wl, first_stream=0):
+    from oracle import orc
+    ws = []
+    for i in range(n):
+        s = orc.System(up.nwater, up.num_lattices)
+        s.set_config(r, h)
+        s.energy_init()
+        s.mc_init(orc.params_from_user(up), rank=i, size=max(n, 1), weights=w, file_wl_factor=wl)
+        s.set_rng_philox(SEED, first_stream + i, 1000000)
+        ws.append(s)
+    return ws
+
+
+def _decorrelate_oracle(ws, nthreads):
+    """Same untimed preparation as the GPU arm: 4 x (25 cycles + monitor with eq_adjust_mc)."""
+    from oracle import orc
+    for _ in range(4):
+        assert orc.mc_run_many(ws, 25, nthreads) == 0
+        for s in ws:
+            s.mc_monitor()
+
+
+def cpu_baseline(target_seconds: float = 12.0):
+    """Oracle timed on all host cores on a bounded sample of the same workload."""
+    from oracle import orc
+    up, h, r, w, wl = _example()
+    nthreads = orc.max_threads()
+    ws = _oracle_walkers(nthreads * 2, up, h, r, w, wl)
+    _decorrelate_oracle(ws, nthreads)
+    t0 = time.perf_counter(); assert orc.mc_run_many(ws, CYCLES_PER_STEP, nthreads) == 0; dt = time.perf_counter() - t0
+    ncyc = max(CYCLES_PER_STEP, int(target_seconds / max(dt, 1e-6)) * CYCLES_PER_STEP)
+    t0 = time.perf_counter(); assert orc.mc_run_many(ws, ncyc, nthreads) == 0; dt = time.perf_counter() - t0
+    moves = len(ws) * up.nwater * ncyc
+    # energy evaluations (single lattice evals / s)
+    t0 = time.perf_counter(); reps = 0
+    while time.perf_counter() - t0 < 2.0:
+        orc.model_energy_many(ws, nthreads); reps += 1
+    evals = reps * len(ws) * 2 / (time.perf_counter() - t0)
+    return {
+        "value": moves / dt, "unit": "attempted MC moves/s", "cores": nthreads, "kind": "port",
+        "sample": f"{len(ws)} walkers x {ncyc} cycles of {EXAMPLE} (oracle restatement, not the Fortran binary; "
+                  f"{dt:.1f} s on {nthreads} threads)",
+        "energy_evals_per_s": evals,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import orc
+    up, h, r, w, wl = _example()
+    nthreads = orc.max_threads()
+    ws = _oracle_walkers(nthreads * 2, up, h, r, w, wl)
+    _decorrelate_oracle(ws, nthreads)
+    # size one step to ~3 s so that K+W steps end within minutes
+    t0 = time.perf_counter(); assert orc.mc_run_many(ws, CYCLES_PER_STEP, nthreads) == 0; dt = time.perf_counter() - t0
+    per_step = max(1, int(3.0 / max(dt, 1e-6))) * CYCLES_PER_STEP
+    for _ in range(args.warmup):
+        assert orc.mc_run_many(ws, per_step, nthreads) == 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        assert orc.mc_run_many(ws, per_step, nthreads) == 0
+    dt = time.perf_counter() - t0
+    moves = len(ws) * up.nwater * per_step * args.steps
+    val = moves / dt
+    unit = "attempted MC moves/s"
+    sample = f"{len(ws)} walkers x {per_step} cycles per step of {EXAMPLE} on {nthreads} host threads (CPU oracle)"
+    print(json.dumps({
+        "impl": "reference", "metric": "attempted MC moves/sec (whole box)", "value": val, "unit": unit,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{EXAMPLE}: lattice-switch walkers, 48 mW molecules per lattice, samplerun "
+                               "(the reference's own CPU algorithm restated in C; Fortran toolchain absent)",
+                   "walkers": len(ws), "cycles_per_step": per_step},
+        "cpu_baseline": {"value": val, "unit": unit, "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mc_water_ls_mw_b200 import comms, walkers as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nw = args.walkers
+    total = nw * world
+    up, h, r, w, wl = _example()
+
+    g = W.WalkerBatch(up.nwater, up.num_lattices, nw, device=local)
+    g.upload(r, h)
+    g.energy_init()
+    g.mc_init(W.params_from_user(up), first_rank=rank * nw, size=total, weights=w, file_wl_factor=wl)
+    g.set_rng_philox(SEED, rank * nw, 1000000)
+    if world > 1:
+        comms.init_nccl(g, rank, world)
+    # untimed decorrelation: 100 cycles with the reference's equilibration step-size adjustment
+    for _ in range(4):
+        g.mc_run(25)
+        g.mc_monitor()
+
+    C = args.cycles
+    sync_every = max(1, up.mpi_sync_int // C)
+
+    def barrier():
+        g.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def step(i):
+        g.mc_run_async(C)
+        if (i + 1) % sync_every == 0:
+            g.comms_allreduce_bins()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = g.kernel_launches()
+    g.timer_start()
+    for i in range(args.steps):
+        step(i)
+    ms = g.timer_stop()
+    barrier()
+    launches = g.kernel_launches() - l0
+    clocks = sampler.finish()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    moves_per_step = total * up.nwater * C
+    value = moves_per_step * args.steps / (ms * 1e-3)
+
+    # ---- dominant kernel (k_mc_run) timed live with CUDA events on its own stream
+    kms = []
+    for i in range(min(args.steps, 10)):
+        g.mc_run(C)
+        kms.append(g.last_kernel_ms())
+    k_ms = float(np.mean(kms))
+    fp64_peak = W.measure_fp64_peak(local)
+    achieved_tf = nw * up.nwater * C * FLOP_PER_MOVE / (k_ms * 1e-3) / 1e12
+    peaks, peak_kind = _peaks()
+
+    # ---- full mW energy evals / s (second half of the metric): batched kernel, device resident
+    e_out = np.empty((nw, up.num_lattices))
+    for _ in range(3):
+        g.compute_model_energy_all(e_out)
+    ems = []
+    for _ in range(20):
+        g.compute_model_energy_all(e_out)
+        ems.append(g.last_kernel_ms())
+    e_ms = float(np.mean(ems))
+    evals_per_s = nw * up.num_lattices / (e_ms * 1e-3) * world
+    hbm_gbs = nw * up.num_lattices * BYTES_PER_EVAL / (e_ms * 1e-3) / 1e9
+
+    # ---- end to end through the C ABI with host buffers (pinned), every step
+    ljr, ref, hm = g.download_all()
+    pin = [torch.from_numpy(a.copy()).pin_memory() for a in (ljr, ref, hm)]
+    hl, hr, hh = [p.numpy() for p in pin]
+    out_l = torch.empty_like(pin[0]).pin_memory(); out_r = torch.empty_like(pin[1]).pin_memory()
+    out_h = torch.empty_like(pin[2]).pin_memory()
+    import ctypes as Ct
+    states = (W.WalkerState * nw)()
+
+    def e2e_step():
+        g.upload_all(hl, hh, hr)                        # H2D: positions, reference positions, cells
+        g.energy_init()                                 # lists + energies + mu, as after a checkpoint load
+        g.mc_run(C)
+        W.check(g.L.mwgpu_download_all(g.h, W._dp(out_l.numpy()), W._dp(out_r.numpy()), W._dp(out_h.numpy())))
+        W.check(g.L.mwgpu_mc_get_states(g.h, states))   # D2H: energies, mu, volumes, counters
+        hl[...] = out_l.numpy(); hr[...] = out_r.numpy(); hh[...] = out_h.numpy()
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(3, min(args.steps, 10))
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = moves_per_step * n_e2e / e2e_s
+    h2d = hl.nbytes + hr.nbytes + hh.nbytes
+    d2h = h2d + Ct.sizeof(states)
+    bad = [s.error for s in states if s.error]
+    if bad:
+        raise SystemExit(f"bench.py: device error bits {bad[:4]}")
+
+    if rank == 0:
+        line = {
+            "metric": "attempted MC moves/sec (whole box)",
+            "value": value, "unit": "attempted MC moves/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"synthetic scale-out (BASELINE configs[4]): {nw} independent lattice-switch walkers per GPU, "
+                            f"{EXAMPLE} deck (48 mW molecules per lattice, cubic<->hexagonal ice, 200 K, 1 atm, fixed weights)",
+                "walkers_per_gpu": nw, "walkers_total": total, "cycles_per_step": C, "moves_per_step": moves_per_step,
+                "l2_policy": "walker state (~19 MB) is re-read from HBM once per step; the hot loop runs out of shared memory",
+                "rng": "Philox-4x32-10, one stream per walker",
+            },
+            "energy_evals_per_s": evals_per_s,
+            "energy_evals": {"value": evals_per_s, "unit": "single-lattice full mW energy evals/s (dual-lattice = /2)",
+                             "ms_per_batch": e_ms, "hbm_gbs_algorithmic": hbm_gbs,
+                             "hbm_frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "hbm_peak": peak_kind,
+                             "fp64_tflops_algorithmic": nw * up.num_lattices * FLOP_PER_EVAL / (e_ms * 1e-3) / 1e12},
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                         "kernel": "k_mc_run<2>", "kernel_ms": k_ms,
+                         "note": "algorithmic flop (10730 per attempted move, BASELINE.md) / measured DFMA peak of this GPU "
+                                 "(mwgpu_measure_fp64_peak; MEASURED_PEAKS.json has no fp64 entry)"},
+            "e2e": {"value": e2e_value, "unit": "attempted MC moves/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--walkers", type=int, default=WALKERS_PER_GPU, help="walkers per GPU")
+    ap.add_argument("--cycles", type=int, default=CYCLES_PER_STEP, help="MC cycles per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -118,7 +118,9 @@ int  mwgpu_upload_all(mwgpu_ctx *ctx, const double *ljr, const double *ref_ljr, 
 int  mwgpu_download_all(mwgpu_ctx *ctx, double *ljr, double *ref_ljr, double *hmatrix);
 
 /* ---- module energy (molint.F90) --------------------------------------------------- */
-/* energy_init, molint.F90:91-153: volume, recip matrix, image vectors, lists, energies -- all walkers */
+/* energy_init, molint.F90:91-153: volume, recip matrix, image vectors, lists, energies -- all walkers.
+ * When mwgpu_mc_init() has been called before (restart path, mc_moves.F90:842-862) the order
+ * parameter ls_mu is recomputed from the fresh energies as well. */
 int  mwgpu_energy_init(mwgpu_ctx *ctx);
 /* compute_ivects(ils), molint.F90:174-217; nivect/ivect(3,MWGPU_MAXIVECT) may be NULL */
 int  mwgpu_compute_ivects(mwgpu_ctx *ctx, int walker, int ils, int *nivect, double *ivect);
@@ -194,6 +196,10 @@ int  mwgpu_comms_apply(mwgpu_ctx *ctx);
 /* elapsed milliseconds of the last mwgpu_mc_run / mwgpu_compute_model_energy_all kernel
  * (CUDA events on the context's stream) */
 int  mwgpu_last_kernel_ms(mwgpu_ctx *ctx, float *ms);
+/* CUDA-event stopwatch on the context's stream: start, enqueue work (e.g. mwgpu_mc_run_async),
+ * stop (synchronises) -> elapsed device milliseconds */
+int  mwgpu_timer_start(mwgpu_ctx *ctx);
+int  mwgpu_timer_stop(mwgpu_ctx *ctx, float *ms);
 /* dependent-free DFMA throughput of the device in TFLOP/s (roofline denominator) */
 int  mwgpu_measure_fp64_peak(int device, double *tflops);
 int  mwgpu_kernel_launches(mwgpu_ctx *ctx, int64_t *count);   /* kernels launched by this context */

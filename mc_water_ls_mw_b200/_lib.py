@@ -98,6 +98,8 @@ SYMBOLS = {
     "mwgpu_comms_init": (_i, [_vp, _i, _i, _vp]),
     "mwgpu_comms_reduce_local": (_i, [_vp, C.POINTER(_vp), _ip]),
     "mwgpu_comms_apply": (_i, [_vp]),
+    "mwgpu_timer_start": (_i, [_vp]),
+    "mwgpu_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
     "mwgpu_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),
     "mwgpu_measure_fp64_peak": (_i, [_i, _dp]),
     "mwgpu_kernel_launches": (_i, [_vp, C.POINTER(C.c_int64)]),

@@ -44,7 +44,7 @@ struct mwgpu_ctx {
     int device = 0;
     int N = 0, nlat = 0, W = 0, NB = 0, NBP = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, tv0 = nullptr, tv1 = nullptr;
     DeviceState S{};
     McParams P{};
     mwgpu_mc_params user{};
@@ -131,6 +131,8 @@ extern "C" int mwgpu_create(int nwater, int nlat, int nwalkers, int device, mwgp
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
+    CUDA_TRY(cudaEventCreate(&c->tv0));
+    CUDA_TRY(cudaEventCreate(&c->tv1));
     *out = c;
     return 0;
 }
@@ -149,6 +151,8 @@ extern "C" void mwgpu_destroy(mwgpu_ctx* c)
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->tv0) cudaEventDestroy(c->tv0);
+    if (c->tv1) cudaEventDestroy(c->tv1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -186,6 +190,23 @@ extern "C" int mwgpu_kernel_launches(mwgpu_ctx* c, int64_t* n)
 {
     if (!c || !n) return fail("mwgpu_kernel_launches: NULL argument");
     *n = c->launches;
+    return 0;
+}
+
+extern "C" int mwgpu_timer_start(mwgpu_ctx* c)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    CUDA_TRY(cudaEventRecord(c->tv0, c->stream));
+    return 0;
+}
+
+extern "C" int mwgpu_timer_stop(mwgpu_ctx* c, float* ms)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!ms) return fail("mwgpu_timer_stop: NULL");
+    CUDA_TRY(cudaEventRecord(c->tv1, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->tv1));
+    CUDA_TRY(cudaEventElapsedTime(ms, c->tv0, c->tv1));
     return 0;
 }
 
@@ -328,6 +349,7 @@ struct OpArgs {
     int eq_adjust, eq_mc_cycles;
     double target_ratio;
     double beta, pressure; int leshift;
+    int refresh_mu;
 };
 
 template <int NLAT>
@@ -365,6 +387,11 @@ __global__ void __launch_bounds__(32) k_walker_op(DeviceState S, OpArgs a)
         for (int lat = 0; lat < NLAT; ++lat) {
             compute_neighbours_warp(w, lat, err);                       // includes compute_ivects
             sc.E[lat] = full_energy_warp(w, lat, err);
+        }
+        if (NLAT == 2 && a.refresh_mu) {      // mc_moves.F90:857-862 (left-to-right association)
+            double mu = sc.E[0] + a.pressure * sc.vol[0] - sc.E[1] - a.pressure * sc.vol[1];
+            if (a.leshift) mu = mu - sc.refH[0] + sc.refH[1];
+            sc.mu = mu * a.beta - (double)N * log(sc.vol[0] / sc.vol[1]);
         }
         store_lists = true;
         break;
@@ -516,6 +543,7 @@ static OpArgs make_args(mwgpu_ctx* c, int op, int w0, int lat, int imol, double*
     a.eq_adjust = c->user.eq_adjust_mc; a.eq_mc_cycles = c->user.eq_mc_cycles;
     a.target_ratio = c->user.mc_target_ratio;
     a.beta = c->P.beta; a.pressure = c->P.pressure; a.leshift = c->P.leshift;
+    a.refresh_mu = c->mc_ready ? 1 : 0;
     return a;
 }
 

@@ -236,6 +236,14 @@ class WalkerBatch:
         check(self.L.mwgpu_comms_init(self.h, nranks, rank, C.cast(buf, C.c_void_p)))
 
     # ------------------------------------------------------------------ measurement
+    def timer_start(self) -> None:
+        check(self.L.mwgpu_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0.0)
+        check(self.L.mwgpu_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
     def last_kernel_ms(self) -> float:
         ms = C.c_float(0.0)
         check(self.L.mwgpu_last_kernel_ms(self.h, C.byref(ms)))
