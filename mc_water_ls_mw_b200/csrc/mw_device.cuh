@@ -1,8 +1,9 @@
 // mw_device.cuh -- warp-cooperative device routines for the mW hot path (sm_100a).
 //
 // One warp owns one walker box.  A walker's positions, packed Verlet lists,
-// image vectors, cell matrices and "bond masks" live in shared memory; every
-// routine below is warp-synchronous (all 32 lanes call it).
+// image vectors, cell matrices, "bond masks", scalar state and random-number
+// buffer live in shared memory; every routine below is warp-synchronous (all
+// 32 lanes call it).
 //
 // Two classes of arithmetic are kept strictly apart (DESIGN.md "Parity"):
 //   * STATE arithmetic (positions, cell, fractional transforms, image vectors,
@@ -10,8 +11,8 @@
 //     mul/add/sub/div/sqrt intrinsics that the compiler never contracts into
 //     FMAs, in exactly the reference's operation order, so that it is
 //     bit-identical to the oracle (and to an uncontracted build of the reference).
-//   * ENERGY arithmetic is free-form fp64 (FMA allowed, pairwise shuffle-tree
-//     summation); parity tolerance 1e-11 relative.
+//   * ENERGY arithmetic is free-form fp64 (FMA, MUFU-seeded Newton reciprocals,
+//     pairwise shuffle-tree summation); parity tolerance 1e-11 relative.
 //
 // Reference lines cited as file:line are into keb721/mc_water_ls_mw.
 #pragma once
@@ -49,7 +50,7 @@ constexpr int LC  = 32;    // list slots per molecule held in shared memory (one
 constexpr int IVC = 32;    // image vectors per lattice (27 in every BASELINE config)
 constexpr int QC  = 128;   // bond records per batch: 4 evaluations x LC slots can never overflow it
 constexpr int CC  = 64;    // triplet centres per trial move: 2 lattices x LC slots
-constexpr int IC  = 128;   // j-centred triplet items buffered between flushes (any value >= 32 works)
+constexpr int RB  = 64;    // random numbers buffered per refill
 constexpr int NMAX = 1024; // molecules (10 bits of a packed list entry)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint16_t NONE16 = 0xffffu;
@@ -58,8 +59,8 @@ constexpr uint16_t NONE16 = 0xffffu;
 enum : int {
     ERR_LIST_OVERFLOW  = 1,    // a molecule has more than LC list neighbours
     ERR_IVECT_OVERFLOW = 2,    // more than IVC image vectors (cell shrank below the cut-off)
-    ERR_BOND_OVERFLOW  = 4,    // more than QC in-range bonds in one batch
-    ERR_ITEM_OVERFLOW  = 8,    // more than CC centres / IC items in one trial move
+    ERR_BOND_OVERFLOW  = 4,    // (unused: the bond-record buffer cannot overflow)
+    ERR_ITEM_OVERFLOW  = 8,    // (unused)
     ERR_SELF_IMAGE     = 16,   // a molecule is its own list neighbour (cell narrower than 1.18*a*sigma)
     ERR_RNG_UNDERRUN   = 32,   // host FIFO ran dry
     ERR_WINDOW         = 64,   // dd: walker not in its window at eq_mc_cycles (mc_moves.F90:191-201)
@@ -105,6 +106,59 @@ __device__ __forceinline__ void recipmatrix3(const double* h, double* r)
     for (int k = 0; k < 9; ++k) r[k] = xd(xm(xm(r[k], 2.0), PI), vol);
 }
 
+// ---------------------------------------------------------------- fast fp64 math for the ENERGY arithmetic
+// The library routines (division, rsqrt, exp) carry special-case handling that costs 40-60 SASS
+// instructions each; the energy terms only see normal, positive, moderate arguments, so a MUFU
+// seed + Newton steps / a plain range reduction is enough.  Accuracy ~2e-16 relative.
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));       // MUFU.RCP64H seed
+    double e = fma(-x, y, 1.0);                                  // 2 Newton steps: 2^-23 -> 2^-46 -> 2^-92
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+__device__ __forceinline__ double rsqrt_fast(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));     // MUFU.RSQ64H seed
+    double e = fma(-(x * y), y, 1.0);                            // 3 Newton steps (second-order each)
+    y = fma(0.5 * y, e, y);
+    e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-(x * y), y, 1.0);
+    return fma(0.5 * y, e, y);
+}
+
+// exp(x) for x <= ~700; returns 0 below -708 (the SW terms vanish at the cut-off: x -> -inf)
+__device__ __forceinline__ double exp_fast(double x)
+{
+    const double xc = fmax(x, -708.0);
+    const double t = fma(xc, 1.4426950408889634, 6755399441055744.0);    // round(x*log2 e) in the low word
+    const int n = __double2loint(t);
+    const double fn = t - 6755399441055744.0;
+    double r = fma(-fn, 6.93147180369123816490e-01, xc);
+    r = fma(-fn, 1.90821492927058770002e-10, r);                           // |r| <= ln2/2
+    double p = 1.6059043836821613e-10;                                     // Taylor, 1/13! ... 1
+    p = fma(p, r, 2.08767569878681e-09);
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.755731922398589e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 1.984126984126984e-04);
+    p = fma(p, r, 1.388888888888889e-03);
+    p = fma(p, r, 8.333333333333333e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double s = __hiloint2double((n + 1023) << 20, 0);               // 2^n, n in [-1022, 1023]
+    return (x < -708.0) ? 0.0 : p * s;
+}
+
 // ---------------------------------------------------------------- Philox-4x32-10
 // counter = (block_lo, block_hi, stream, 0), key = (seed_lo, seed_hi); two
 // doubles per block (53 high bits of each 64-bit half) -- the stream documented in DESIGN.md "RNG".
@@ -127,44 +181,31 @@ __device__ __forceinline__ void philox_block(uint64_t seed, uint32_t stream, uin
     o1 = (double)(b >> 11) * 0x1.0p-53;
 }
 
-// Per-walker stream of U[0,1) numbers (random.f90:87-102).  Each lane buffers
-// two draws; 64 draws per refill.  mode 0: Philox (draw n = half n&1 of block
-// n>>1).  mode 1: host FIFO (draw n = fifo[n]).
-struct WarpRng {
-    double v0, v1;
-    uint64_t base;     // draw index of lane 0's v0 (even)
-    int pos;           // next draw = base + pos, pos in [0,64]
-    int mode;
-    uint64_t seed; uint32_t stream;
-    const double* fifo; uint64_t fifo_len;
-    int underrun;
-
-    __device__ __forceinline__ void refill()
-    {
-        const int lane = lane_id();
-        if (mode == 0) {
-            philox_block(seed, stream, (base >> 1) + (uint64_t)lane, v0, v1);
-        } else {
-            const uint64_t i0 = base + 2u * (uint64_t)lane;
-            v0 = (i0 < fifo_len) ? fifo[i0] : 0.5;
-            v1 = (i0 + 1 < fifo_len) ? fifo[i0 + 1] : 0.5;
-        }
-    }
-    __device__ __forceinline__ void init(uint64_t index)
-    {
-        base = index & ~(uint64_t)1; pos = (int)(index - base); underrun = 0;
-        refill();
-    }
-    __device__ __forceinline__ uint64_t index() const { return base + (uint64_t)pos; }
-    __device__ __forceinline__ double draw()
-    {
-        if (pos == 64) { base += 64; pos = 0; refill(); }
-        if (mode == 1 && base + (uint64_t)pos >= fifo_len) underrun = 1;
-        const double mine = (pos & 1) ? v1 : v0;
-        const double x = __shfl_sync(FULL, mine, pos >> 1);
-        ++pos;
-        return x;
-    }
+// ---------------------------------------------------------------- per-walker state
+// Scalars that persist between launches (global memory) and live in shared memory inside a
+// kernel.  Inside a kernel they are "uniform registers in shared memory": every lane stores the
+// same value and reads back what it wrote itself, so no synchronisation is needed for them.
+struct WalkerScalars {
+    double E[2];            // model_energy(1:2)                        molint.F90:41
+    double vol[2];          // volume(1:2)                              data_structures.f90:48
+    double mu;              // ls_mu                                    mc_moves.F90:63
+    double max_trans;       // mc_max_trans (Bohr) -- per walker: eq_adjust_mc tunes it per rank
+    double dv_max;          // mc_dv_max (Bohr)
+    double wl_factor;
+    double mu_lo, mu_hi;    // my_mu_min, my_mu_max                     mc_moves.F90:108
+    double avgE[2];         // average_energy                           mc_moves.F90:88
+    double min_dmu, max_dmu;
+    double refH[2];         // ref_enthalpy                             mc_moves.F90:88
+    double sumhist;
+    unsigned long long rng_index;   // next draw index (Philox) / FIFO position
+    int ls;                 // active lattice, 1-based                  data_structures.f90:51
+    int cycle;              // mc_cycle_num
+    int acc_r, acc_v, acc_s, att_r, att_v, att_s;
+    int start_bin, end_bin; // my_start_bin, my_end_bin (1-based)
+    int in_window;          // walker_in_window
+    int wl_invt_active;
+    int wmin_zero;          // invariant "min(weight(window)) == 0" established
+    int error;
 };
 
 // ---------------------------------------------------------------- shared-memory view of one walker
@@ -176,41 +217,55 @@ struct WalkerView {
     double*   recip;   // [nlat][9]
     double*   q;       // [4][QC] scratch: tx,ty,tz,r2 -> ux,uy,uz,g
     double*   save;    // [36]    old cell + recip during a volume move
-    uint32_t* qmeta;   // [QC]   call | slot<<2 | j<<8 | img<<18
-    uint32_t* cmeta;   // [CC]   lat | slot<<1 | j<<6 | img<<16
-    uint16_t* cq;      // [CC][2] bond record of the centre in the old / new variant
-    uint16_t* items;   // [IC]   centre<<5 | slot
+    double*   rngbuf;  // [RB]    buffered U[0,1) numbers
+    double*   lv;      // [2]     log(V1/V2), log(V2/V1)
+    WalkerScalars* sc;
+    uint64_t* rngbase; // draw index of rngbuf[0]
+    uint32_t* qmeta;   // [QC]   call | j<<8
+    uint32_t* cmeta;   // [CC]   lat | j<<6
     uint32_t* bmask;   // [nlat][N] bit s: list slot s currently within the cut-off a*sigma
+    int*      niv;     // [2]
+    uint16_t* cq;      // [CC][2] bond record of the centre in the old / new variant
+    uint16_t* cpre;    // [CC+2]  exclusive prefix of the per-centre bond counts
     uint16_t* list;    // [nlat][N][LC] packed entries img<<10 | j   (0-based)
     uint8_t*  nn;      // [nlat][N]
-    int*      niv;     // [2]
 };
 
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t smem_doubles(int N, int nlat)
+{
+    return (size_t)nlat * 3 * N + (size_t)nlat * 3 * IVC + (size_t)nlat * 18 + 4 * QC + 36 + RB + 2;
+}
 
-// Layout (every block 16-byte aligned): doubles | list | 32-bit words | 16-bit words | bytes
+// Layout (every block 16-byte aligned): doubles | scalars | list | 32-bit words | 16-bit words | bytes
 __host__ __device__ inline size_t walker_smem_bytes(int N, int nlat)
 {
     size_t b = 0;
-    b += align16(sizeof(double) * ((size_t)nlat * 3 * N + (size_t)nlat * 3 * IVC + (size_t)nlat * 18 + 4 * QC + 36));
+    b += align16(sizeof(double) * smem_doubles(N, nlat));
+    b += align16(sizeof(WalkerScalars) + sizeof(uint64_t));
     b += align16(sizeof(uint16_t) * (size_t)nlat * N * LC);                       // list
     b += align16(sizeof(uint32_t) * (QC + CC + (size_t)nlat * N + 2));            // qmeta, cmeta, bmask, niv
-    b += align16(sizeof(uint16_t) * (CC * 2 + IC));                               // cq, items
+    b += align16(sizeof(uint16_t) * (CC * 2 + CC + 2));                           // cq, cpre
     b += align16((size_t)nlat * N);                                               // nn
     return b;
 }
 
-__device__ inline WalkerView carve_walker(unsigned char* base, int N, int nlat)
+__device__ __forceinline__ WalkerView carve_walker(unsigned char* base, int N, int nlat)
 {
     WalkerView w; w.N = N; w.nlat = nlat;
     unsigned char* p = base;
-    w.pos   = (double*)p;
-    w.iv    = w.pos + (size_t)nlat * 3 * N;
-    w.cell  = w.iv + (size_t)nlat * 3 * IVC;
-    w.recip = w.cell + (size_t)nlat * 9;
-    w.q     = w.recip + (size_t)nlat * 9;
-    w.save  = w.q + 4 * QC;
-    p += align16(sizeof(double) * ((size_t)nlat * 3 * N + (size_t)nlat * 3 * IVC + (size_t)nlat * 18 + 4 * QC + 36));
+    w.pos    = (double*)p;
+    w.iv     = w.pos + (size_t)nlat * 3 * N;
+    w.cell   = w.iv + (size_t)nlat * 3 * IVC;
+    w.recip  = w.cell + (size_t)nlat * 9;
+    w.q      = w.recip + (size_t)nlat * 9;
+    w.save   = w.q + 4 * QC;
+    w.rngbuf = w.save + 36;
+    w.lv     = w.rngbuf + RB;
+    p += align16(sizeof(double) * smem_doubles(N, nlat));
+    w.sc      = (WalkerScalars*)p;
+    w.rngbase = (uint64_t*)(p + sizeof(WalkerScalars));
+    p += align16(sizeof(WalkerScalars) + sizeof(uint64_t));
     w.list  = (uint16_t*)p;
     p += align16(sizeof(uint16_t) * (size_t)nlat * N * LC);
     w.qmeta = (uint32_t*)p;
@@ -219,17 +274,17 @@ __device__ inline WalkerView carve_walker(unsigned char* base, int N, int nlat)
     w.niv   = (int*)(w.bmask + (size_t)nlat * N);
     p += align16(sizeof(uint32_t) * (QC + CC + (size_t)nlat * N + 2));
     w.cq    = (uint16_t*)p;
-    w.items = w.cq + CC * 2;
-    p += align16(sizeof(uint16_t) * (CC * 2 + IC));
+    w.cpre  = w.cq + CC * 2;
+    p += align16(sizeof(uint16_t) * (CC * 2 + CC + 2));
     w.nn    = (uint8_t*)p;
     return w;
 }
 
 // ---------------------------------------------------------------- image vectors
-// molint.F90:174-217.  Lane k builds vector k.  Returns nivect (uniform); sets
-// ERR_IVECT_OVERFLOW in err when it exceeds IVC.
-__device__ inline int compute_ivects_warp(const WalkerView& w, int lat, int& err)
+// molint.F90:174-217.  Lane k builds vector k.  Returns error bits.
+__device__ __noinline__ int compute_ivects_warp(unsigned char* smem, int N, int nlat, int lat)
 {
+    const WalkerView w = carve_walker(smem, N, nlat);
     const double* h = w.cell + 9 * lat;
     const double l1 = xsqrt(xa(xa(xm(h[0], h[0]), xm(h[1], h[1])), xm(h[2], h[2])));
     const double l2 = xsqrt(xa(xa(xm(h[3], h[3]), xm(h[4], h[4])), xm(h[5], h[5])));
@@ -239,9 +294,10 @@ __device__ inline int compute_ivects_warp(const WalkerView& w, int lat, int& err
     const int km = (int)floor(xd(RC, l3)) + 1;
     const int nj = 2 * jm + 1, nk = 2 * km + 1;
     const int nv = (2 * im + 1) * nj * nk;
-    if (nv > IVC) { err |= ERR_IVECT_OVERFLOW; return nv; }
-    const int f0 = (nv - 1) / 2;           // full-grid index of the (0,0,0) cell
     const int k = lane_id();
+    if (k == 0) w.niv[lat] = nv;
+    if (nv > IVC) { __syncwarp(); return ERR_IVECT_OVERFLOW; }
+    const int f0 = (nv - 1) / 2;           // full-grid index of the (0,0,0) cell
     if (k < nv) {
         double vx = 0.0, vy = 0.0, vz = 0.0;
         if (k > 0) {
@@ -257,9 +313,8 @@ __device__ inline int compute_ivects_warp(const WalkerView& w, int lat, int& err
         double* V = w.iv + lat * 3 * IVC;
         V[k] = vx; V[IVC + k] = vy; V[2 * IVC + k] = vz;
     }
-    if (k == 0) w.niv[lat] = nv;
     __syncwarp();
-    return nv;
+    return 0;
 }
 
 // index of the image vector that is the negative of image `img`
@@ -275,12 +330,16 @@ __device__ __forceinline__ int inverse_image(int img, int nv)
 // ---------------------------------------------------------------- Verlet list
 // molint.F90:501-559: brute force over (j, image k), emitted in j-ascending,
 // k-ascending order.  Lanes own molecules j; each lane walks the images and
-// keeps a bit mask; entries are then emitted in lane order.
-__device__ inline void compute_neighbours_warp(const WalkerView& w, int lat, int& err)
+// keeps a bit mask; entries are then emitted in lane order.  The exact test
+// (tx^2 + ty^2) + tz^2 < rn^2 is monotone in each term, so an image whose
+// tx^2 alone reaches rn^2 is skipped without changing any decision.
+__device__ __noinline__ int compute_neighbours_warp(unsigned char* smem, int N, int nlat, int lat)
 {
-    const int N = w.N, lane = lane_id();
-    const int nv = compute_ivects_warp(w, lat, err);          // molint.F90:518
-    if (nv > IVC) return;
+    int err = compute_ivects_warp(smem, N, nlat, lat);          // molint.F90:518
+    if (err) return err;
+    const WalkerView w = carve_walker(smem, N, nlat);
+    const int lane = lane_id();
+    const int nv = w.niv[lat];
     const double* P = w.pos + lat * 3 * N;
     const double* V = w.iv + lat * 3 * IVC;
     for (int i = 0; i < N; ++i) {
@@ -292,9 +351,13 @@ __device__ inline void compute_neighbours_warp(const WalkerView& w, int lat, int
             if (j < N) {
                 const double vx = xs(P[j], ix), vy = xs(P[N + j], iy), vz = xs(P[2 * N + j], iz);
                 for (int k = 0; k < nv; ++k) {
-                    const double tx = xa(vx, V[k]), ty = xa(vy, V[IVC + k]), tz = xa(vz, V[2 * IVC + k]);
-                    const double r2 = xa(xa(xm(tx, tx), xm(ty, ty)), xm(tz, tz));
-                    if (r2 < RN2) m |= 1u << k;
+                    const double tx = xa(vx, V[k]);
+                    const double xx = xm(tx, tx);
+                    if (xx < RN2) {
+                        const double ty = xa(vy, V[IVC + k]), tz = xa(vz, V[2 * IVC + k]);
+                        const double r2 = xa(xa(xx, xm(ty, ty)), xm(tz, tz));
+                        if (r2 < RN2) m |= 1u << k;
+                    }
                 }
                 if (j == i) {
                     m &= ~1u;                                   // (k==1).and.(jmol==imol) cycle
@@ -320,34 +383,31 @@ __device__ inline void compute_neighbours_warp(const WalkerView& w, int lat, int
         if (total > LC) { err |= ERR_LIST_OVERFLOW; total = LC; }
         if (lane == 0) w.nn[lat * N + i] = (uint8_t)total;
     }
-    err = __reduce_or_sync(FULL, err);
+    err = (int)__reduce_or_sync(FULL, (unsigned)err);
     __syncwarp();
+    return err;
 }
 
 // ---------------------------------------------------------------- bond masks
 // bmask[lat][a] bit s <=> slot s of a's list is inside the cut-off (r^2 < rcsq,
 // molint.F90:276/454).  Lanes are the slots.
-__device__ __forceinline__ uint32_t bond_mask_of(const WalkerView& w, int lat, int a)
+__device__ __noinline__ void compute_bond_masks_warp(unsigned char* smem, int N, int nlat, int lat)
 {
-    const int N = w.N, lane = lane_id();
+    const WalkerView w = carve_walker(smem, N, nlat);
+    const int lane = lane_id();
     const double* P = w.pos + lat * 3 * N;
     const double* V = w.iv + lat * 3 * IVC;
-    const int nna = w.nn[lat * N + a];
-    const bool has = lane < nna;
-    const uint32_t e = has ? w.list[((size_t)lat * N + a) * LC + lane] : 0u;
-    const int j = e & 1023, img = e >> 10;
-    const double tx = (P[j] + V[img]) - P[a];
-    const double ty = (P[N + j] + V[IVC + img]) - P[N + a];
-    const double tz = (P[2 * N + j] + V[2 * IVC + img]) - P[2 * N + a];
-    const double r2 = tx * tx + ty * ty + tz * tz;
-    return __ballot_sync(FULL, has && r2 < RCSQ);
-}
-
-__device__ inline void compute_bond_masks_warp(const WalkerView& w, int lat)
-{
-    for (int a = 0; a < w.N; ++a) {
-        const uint32_t m = bond_mask_of(w, lat, a);
-        if (lane_id() == 0) w.bmask[lat * w.N + a] = m;
+    for (int a = 0; a < N; ++a) {
+        const int nna = w.nn[lat * N + a];
+        const bool has = lane < nna;
+        const uint32_t e = has ? w.list[((size_t)lat * N + a) * LC + lane] : 0u;
+        const int j = e & 1023, img = e >> 10;
+        const double tx = (P[j] + V[img]) - P[a];
+        const double ty = (P[N + j] + V[IVC + img]) - P[N + a];
+        const double tz = (P[2 * N + j] + V[2 * IVC + img]) - P[2 * N + a];
+        const double r2 = tx * tx + ty * ty + tz * tz;
+        const uint32_t m = __ballot_sync(FULL, has && r2 < RCSQ);
+        if (lane == 0) w.bmask[lat * N + a] = m;
     }
     __syncwarp();
 }
@@ -355,17 +415,16 @@ __device__ inline void compute_bond_masks_warp(const WalkerView& w, int lat)
 // ---------------------------------------------------------------- energy kernels (free-form fp64)
 // Pair record evaluation shared by the local and the full energy:
 //   in : q[0..2][r] = separation vector t, q[3][r] = r^2
-//   out: q[0..2][r] = unit vector u = t/r, q[3][r] = lambda*eps-free g = exp(gamma*sigma/(r - a*sigma))
+//   out: q[0..2][r] = unit vector u = t/r, q[3][r] = g = exp(gamma*sigma/(r - a*sigma))
 //   returns the pair energy A*eps*(B*(sigma/r)^4 - 1)*exp(sigma/(r - a*sigma))   (molint.F90:278-297 / :456-461)
-__device__ __forceinline__ double eval_bond(const WalkerView& w, int r)
+__device__ __forceinline__ double eval_bond(double* q, int r)
 {
-    double* q = w.q;
     const double tx = q[r], ty = q[QC + r], tz = q[2 * QC + r], r2 = q[3 * QC + r];
-    const double ir = rsqrt(r2);
+    const double ir = rsqrt_fast(r2);
     const double r1 = ir * r2;
-    const double isr = 1.0 / (r1 - RC);
-    const double e2 = exp(SIGMA * isr);
-    const double g = exp(GS * isr);
+    const double isr = rcp_fast(r1 - RC);
+    const double e2 = exp_fast(SIGMA * isr);
+    const double g = exp_fast(GS * isr);
     const double s2 = SS * ir * ir;
     q[r] = tx * ir; q[QC + r] = ty * ir; q[2 * QC + r] = tz * ir; q[3 * QC + r] = g;
     return AEPS * (BIGB * (s2 * s2) - 1.0) * e2;
@@ -383,16 +442,14 @@ __device__ __forceinline__ double hfun(double ct)
 __device__ __forceinline__ void reduce4(double& a0, double& a1, double& a2, double& a3)
 {
     const int lane = lane_id();
-    // step 1 (xor 16): lanes 0-15 keep (a0,a1), lanes 16-31 keep (a2,a3)
-    {
+    {   // xor 16: lanes 0-15 keep (a0,a1), lanes 16-31 keep (a2,a3)
         const bool up = lane & 16;
         const double s0 = up ? a0 : a2, s1 = up ? a1 : a3;
         const double r0 = __shfl_xor_sync(FULL, s0, 16), r1 = __shfl_xor_sync(FULL, s1, 16);
         a0 = (up ? a2 : a0) + r0;
         a1 = (up ? a3 : a1) + r1;
     }
-    // step 2 (xor 8): within each half, lanes with bit3 clear keep a0, others keep a1
-    {
+    {   // xor 8: within each half, lanes with bit 3 clear keep a0, the others keep a1
         const bool up = lane & 8;
         const double s = up ? a0 : a1;
         const double r = __shfl_xor_sync(FULL, s, 8);
@@ -401,7 +458,6 @@ __device__ __forceinline__ void reduce4(double& a0, double& a1, double& a2, doub
     a0 += __shfl_xor_sync(FULL, a0, 4);
     a0 += __shfl_xor_sync(FULL, a0, 2);
     a0 += __shfl_xor_sync(FULL, a0, 1);
-    // value index held by a lane group: (lane>>4)*2 + ((lane>>3)&1)
     const double t0 = __shfl_sync(FULL, a0, 0), t1 = __shfl_sync(FULL, a0, 8);
     const double t2 = __shfl_sync(FULL, a0, 16), t3 = __shfl_sync(FULL, a0, 24);
     a0 = t0; a1 = t1; a2 = t2; a3 = t3;
@@ -412,6 +468,22 @@ __device__ __forceinline__ double warp_sum(double a)
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(FULL, a, d);
     return a;
+}
+
+// position of the (rank+1)-th set bit of m (rank < popc(m))
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int rank)
+{
+    int pos = 0;
+    int c = __popc(m & 0xffffu);
+    if (rank >= c) { rank -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xffu);
+    if (rank >= c) { rank -= c; pos += 8; m >>= 8; }
+    c = __popc(m & 0xfu);
+    if (rank >= c) { rank -= c; pos += 4; m >>= 4; }
+    c = __popc(m & 0x3u);
+    if (rank >= c) { rank -= c; pos += 2; m >>= 2; }
+    if (rank >= (int)(m & 1u)) pos += 1;
+    return pos;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -434,11 +506,10 @@ __device__ __forceinline__ double warp_sum(double a)
 // Outputs (uniform over the warp): eo[lat], en[lat]; mo[lat]/mn[lat] = in-range
 // slot masks of imol for the old / new position.
 template <int NLAT, bool WITH_NEW>
-__device__ inline void local_energies_warp(const WalkerView& w, int imol, const double (*pnew)[3],
-                                           double* eo, double* en, uint32_t* mo, uint32_t* mn, int& err)
+__device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imol, const double (*pnew)[3],
+                                                    double* eo, double* en, uint32_t* mo, uint32_t* mn)
 {
     const int N = w.N, lane = lane_id();
-    constexpr int nlat = NLAT;
     const unsigned lt = lt_mask();
     double* q = w.q;
     int nq = 0, nc = 0;
@@ -446,7 +517,7 @@ __device__ inline void local_energies_warp(const WalkerView& w, int imol, const 
 
     // ---- stage 1: distance tests over imol's own list (lanes = slots), compaction into bond records
 #pragma unroll
-    for (int lat = 0; lat < nlat; ++lat) {
+    for (int lat = 0; lat < NLAT; ++lat) {
         const double* P = w.pos + lat * 3 * N;
         const double* V = w.iv + lat * 3 * IVC;
         const int nni = w.nn[lat * N + imol];
@@ -475,20 +546,19 @@ __device__ inline void local_energies_warp(const WalkerView& w, int imol, const 
         const uint32_t bu = bo | bn;
         const int ic = nc + __popc(bu & lt);
         nc += __popc(bu);
-        {   // nq <= 4*LC == QC and nc <= 2*LC == CC by construction
-            if (fo) {
-                q[io] = tox; q[QC + io] = toy; q[2 * QC + io] = toz; q[3 * QC + io] = r2o;
-                w.qmeta[io] = (uint32_t)(lat * 2) | ((uint32_t)j << 8);
-            }
-            if (WITH_NEW && fn) {
-                q[in_] = tnx; q[QC + in_] = tny; q[2 * QC + in_] = tnz; q[3 * QC + in_] = r2n;
-                w.qmeta[in_] = (uint32_t)(lat * 2 + 1) | ((uint32_t)j << 8);
-            }
-            if (fo || fn) {
-                w.cmeta[ic] = (uint32_t)lat | ((uint32_t)j << 6);
-                w.cq[ic * 2] = fo ? (uint16_t)io : NONE16;
-                w.cq[ic * 2 + 1] = fn ? (uint16_t)in_ : NONE16;
-            }
+        // nq <= 4*LC == QC and nc <= 2*LC == CC by construction
+        if (fo) {
+            q[io] = tox; q[QC + io] = toy; q[2 * QC + io] = toz; q[3 * QC + io] = r2o;
+            w.qmeta[io] = (uint32_t)(lat * 2) | ((uint32_t)j << 8);
+        }
+        if (WITH_NEW && fn) {
+            q[in_] = tnx; q[QC + in_] = tny; q[2 * QC + in_] = tnz; q[3 * QC + in_] = r2n;
+            w.qmeta[in_] = (uint32_t)(lat * 2 + 1) | ((uint32_t)j << 8);
+        }
+        if (fo || fn) {
+            w.cmeta[ic] = (uint32_t)lat | ((uint32_t)j << 6);
+            w.cq[ic * 2] = fo ? (uint16_t)io : NONE16;
+            w.cq[ic * 2 + 1] = fn ? (uint16_t)in_ : NONE16;
         }
     }
     __syncwarp();
@@ -499,64 +569,87 @@ __device__ inline void local_energies_warp(const WalkerView& w, int imol, const 
     for (int b = 0; b < nq; b += 32) {
         const int r = b + lane;
         if (r < nq) {
-            const double pe = eval_bond(w, r);
+            const double pe = eval_bond(q, r);
             const int c = w.qmeta[r] & 3;
             a0 += (c == 0) ? pe : 0.0; a1 += (c == 1) ? pe : 0.0;
             a2 += (c == 2) ? pe : 0.0; a3 += (c == 3) ? pe : 0.0;
         }
     }
+
+    // ---- per-centre bond counts (lanes = centres) -> exclusive prefix in shared memory
+    int ncand = 0;
+    for (int cb = 0; cb < nc; cb += 32) {
+        const int c = cb + lane;
+        int cnt = 0;
+        if (c < nc) {
+            const uint32_t cm = w.cmeta[c];
+            cnt = __popc(w.bmask[(cm & 1) * N + ((cm >> 6) & 1023)]);
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (c < nc) w.cpre[c] = (uint16_t)(ncand + incl - cnt);
+        ncand += __shfl_sync(FULL, incl, 31);
+    }
+    if (lane == 0) w.cpre[nc] = (uint16_t)ncand;
     __syncwarp();
 
-    // ---- stage 3: triplets centred on imol (lanes = bond records, loop over later records of the same call)
+    // ---- stage 3: triplets centred on imol: all pairs (a<b) of bond records of the same evaluation,
+    // flattened over the 4 evaluations (lanes = pairs)
     {
-        int maxn = max(max(seg_n[0], seg_n[1]), max(seg_n[2], seg_n[3]));
-        for (int b = 0; b < nq; b += 32) {
-            const int r = b + lane;
-            const bool act = r < nq;
-            const uint32_t meta = act ? w.qmeta[r] : 0u;
-            const int c = meta & 3;
-            const int send = (c == 0) ? seg_start[0] + seg_n[0] : (c == 1) ? seg_start[1] + seg_n[1]
-                           : (c == 2) ? seg_start[2] + seg_n[2] : seg_start[3] + seg_n[3];
-            const double ux = act ? q[r] : 0.0, uy = act ? q[QC + r] : 0.0, uz = act ? q[2 * QC + r] : 0.0;
-            const double g = act ? q[3 * QC + r] : 0.0;
-            double tb = 0.0;
-            for (int d = 1; d < maxn; ++d) {
-                const int r2i = r + d;
-                if (act && r2i < send) {
-                    const double ct = ux * q[r2i] + uy * q[QC + r2i] + uz * q[2 * QC + r2i];
-                    const double mult = ((w.qmeta[r2i] >> 8) == (meta >> 8)) ? 3.0 : 1.0;
-                    tb += g * q[3 * QC + r2i] * hfun(ct) * mult;
-                }
+        const int p0 = seg_n[0] * (seg_n[0] - 1) / 2, p1 = p0 + seg_n[1] * (seg_n[1] - 1) / 2;
+        const int p2 = p1 + seg_n[2] * (seg_n[2] - 1) / 2, p3 = p2 + seg_n[3] * (seg_n[3] - 1) / 2;
+        for (int pb = 0; pb < p3; pb += 32) {
+            const int p = pb + lane;
+            if (p < p3) {
+                const int c = (p >= p2) ? 3 : (p >= p1) ? 2 : (p >= p0) ? 1 : 0;
+                const int m = p - ((c == 3) ? p2 : (c == 2) ? p1 : (c == 1) ? p0 : 0);
+                const int s0 = (c == 3) ? seg_start[3] : (c == 2) ? seg_start[2] : (c == 1) ? seg_start[1] : seg_start[0];
+                // m = b(b-1)/2 + a with a < b
+                int bb = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)m)) * 0.5f);
+                if (bb * (bb - 1) / 2 > m) --bb;
+                if ((bb + 1) * bb / 2 <= m) ++bb;
+                const int ra = s0 + (m - bb * (bb - 1) / 2), rb = s0 + bb;
+                const double ct = q[ra] * q[rb] + q[QC + ra] * q[QC + rb] + q[2 * QC + ra] * q[2 * QC + rb];
+                const double mult = ((w.qmeta[ra] >> 8) == (w.qmeta[rb] >> 8)) ? 3.0 * LEPS : LEPS;
+                const double tb = q[3 * QC + ra] * q[3 * QC + rb] * hfun(ct) * mult;
+                a0 += (c == 0) ? tb : 0.0; a1 += (c == 1) ? tb : 0.0;
+                a2 += (c == 2) ? tb : 0.0; a3 += (c == 3) ? tb : 0.0;
             }
-            tb *= LEPS;
-            a0 += (c == 0) ? tb : 0.0; a1 += (c == 1) ? tb : 0.0;
-            a2 += (c == 2) ? tb : 0.0; a3 += (c == 3) ? tb : 0.0;
         }
     }
 
-    // ---- stages 4+5: j-centred triplets.  Lanes = centres enumerate the bonds of their j from the
-    // cached bond mask (skipping images of imol) into an item buffer; the buffer is evaluated
-    // (lanes = items) whenever it could overflow and at the end.  One evaluation of (j,k) serves
-    // both variants.
-    auto flush_items = [&](int ni) {
-        for (int b = 0; b < ni; b += 32) {
-            const int t = b + lane;
-            if (t < ni) {
-                const uint32_t it = w.items[t];
-                const int c = it >> 5, s2 = it & 31;
-                const uint32_t cm = w.cmeta[c];
-                const int lat = cm & 1, j = (cm >> 6) & 1023;
+    // ---- stages 4+5: j-centred triplets, lanes = (centre, bond of the centre) candidates.  The
+    // centre of a candidate is found by binary search in the prefix table, its list slot as the
+    // rank-th set bit of the centre's bond mask.  Images of imol are skipped (see above).  One
+    // evaluation of (j,k) serves both variants.
+    for (int tb0 = 0; tb0 < ncand; tb0 += 32) {
+        const int t = tb0 + lane;
+        if (t < ncand) {
+            int lo = 0, hi = nc;                       // largest c with cpre[c] <= t
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if ((int)w.cpre[mid] <= t) lo = mid; else hi = mid;
+            }
+            const int c = lo;
+            const uint32_t cm = w.cmeta[c];
+            const int lat = cm & 1, j = (cm >> 6) & 1023;
+            const int s2 = nth_set_bit(w.bmask[lat * N + j], t - (int)w.cpre[c]);
+            const uint32_t e2 = w.list[((size_t)lat * N + j) * LC + s2];
+            const int k = e2 & 1023, img = e2 >> 10;
+            if (k != imol) {
                 const double* P = w.pos + lat * 3 * N;
                 const double* V = w.iv + lat * 3 * IVC;
-                const uint32_t e2 = w.list[((size_t)lat * N + j) * LC + s2];
-                const int k = e2 & 1023, img = e2 >> 10;
                 const double tx = (P[k] + V[img]) - P[j];
                 const double ty = (P[N + k] + V[IVC + img]) - P[N + j];
                 const double tz = (P[2 * N + k] + V[2 * IVC + img]) - P[2 * N + j];
                 const double sq = tx * tx + ty * ty + tz * tz;
                 if (sq < RCSQ) {
-                    const double vi = rsqrt(sq);
-                    const double ex = LEPS * exp(GS / (sq * vi - RC));
+                    const double vi = rsqrt_fast(sq);
+                    const double ex = LEPS * exp_fast(GS * rcp_fast(sq * vi - RC));
                     const double ux = tx * vi, uy = ty * vi, uz = tz * vi;
                     const uint16_t qo = w.cq[c * 2], qn = w.cq[c * 2 + 1];
                     double vo = 0.0, vn = 0.0;
@@ -572,35 +665,11 @@ __device__ inline void local_energies_warp(const WalkerView& w, int imol, const 
                 }
             }
         }
-    };
-    {
-        int ni = 0;
-        for (int cb = 0; cb < nc; cb += 32) {
-            const int c = cb + lane;
-            const bool act = c < nc;
-            const uint32_t cm = act ? w.cmeta[c] : 0u;
-            const int lat = cm & 1, j = (cm >> 6) & 1023;
-            uint32_t m = act ? w.bmask[lat * N + j] : 0u;
-            const uint16_t* row = w.list + ((size_t)lat * N + j) * LC;
-            while (__any_sync(FULL, m != 0)) {
-                if (ni + 32 > IC) { __syncwarp(); flush_items(ni); __syncwarp(); ni = 0; }
-                bool valid = false; int s2 = 0;
-                if (m) {
-                    s2 = __ffs(m) - 1; m &= m - 1;
-                    valid = (row[s2] & 1023) != imol;
-                }
-                const uint32_t bv = __ballot_sync(FULL, valid);
-                if (valid) w.items[ni + __popc(bv & lt)] = (uint16_t)((c << 5) | s2);
-                ni += __popc(bv);
-            }
-        }
-        __syncwarp();
-        flush_items(ni);
     }
 
     reduce4(a0, a1, a2, a3);
     eo[0] = a0; en[0] = a1;
-    if (nlat == 2) { eo[1] = a2; en[1] = a3; }
+    if (NLAT == 2) { eo[1] = a2; en[1] = a3; }
     __syncwarp();
 }
 
@@ -609,9 +678,10 @@ __device__ inline void local_energies_warp(const WalkerView& w, int imol, const 
 // chunked: bonds of a chunk of molecules are compacted (stage 1), evaluated
 // (stage 2) and combined into i-centred triplets (stage 3).  Also refreshes the
 // bond masks of the lattice.  Returns E (uniform).
-__device__ inline double full_energy_warp(const WalkerView& w, int lat, int& err)
+__device__ __noinline__ double full_energy_warp(unsigned char* smem, int N, int nlat, int lat)
 {
-    const int N = w.N, lane = lane_id();
+    const WalkerView w = carve_walker(smem, N, nlat);
+    const int lane = lane_id();
     const unsigned lt = lt_mask();
     const double* P = w.pos + lat * 3 * N;
     const double* V = w.iv + lat * 3 * IVC;
@@ -634,16 +704,12 @@ __device__ inline double full_energy_warp(const WalkerView& w, int lat, int& err
             const bool f = has && r2 < RCSQ;
             const uint32_t bm = __ballot_sync(FULL, f);
             const int cnt = __popc(bm);
-            if (nq + cnt > QC) {
-                if (nq == 0) { err |= ERR_BOND_OVERFLOW; if (lane == 0) w.bmask[lat * N + a1] = bm; ++a1; }
-                break;
-            }
+            if (nq + cnt > QC) break;                 // cnt <= LC < QC: a chunk always holds >= 1 molecule
             if (lane == 0) w.bmask[lat * N + a1] = bm;
             if (f) {
                 const int io = nq + __popc(bm & lt);
                 q[io] = tx; q[QC + io] = ty; q[2 * QC + io] = tz; q[3 * QC + io] = r2;
-                // meta: molecule (segment id) in the high bits, index of the segment end filled below
-                w.qmeta[io] = (uint32_t)a1 << 8 | (uint32_t)(nq + cnt);
+                w.qmeta[io] = (uint32_t)(nq + cnt);  // end of this molecule's segment
             }
             nq += cnt;
         }
@@ -651,19 +717,19 @@ __device__ inline double full_energy_warp(const WalkerView& w, int lat, int& err
         // ---- bond evaluation: 0.5 * pair energy (molint.F90:464)
         for (int b = 0; b < nq; b += 32) {
             const int r = b + lane;
-            if (r < nq) acc += 0.5 * eval_bond(w, r);
+            if (r < nq) acc += 0.5 * eval_bond(q, r);
         }
         __syncwarp();
-        // ---- triplets centred on each molecule of the chunk
+        // ---- triplets centred on each molecule of the chunk (lanes = records, loop over later
+        // records of the same molecule)
         for (int b = 0; b < nq; b += 32) {
             const int r = b + lane;
             const bool act = r < nq;
-            const uint32_t meta = act ? w.qmeta[r] : 0u;
-            const int send = meta & 255;
+            const int send = act ? (int)w.qmeta[r] : 0;
             const double ux = act ? q[r] : 0.0, uy = act ? q[QC + r] : 0.0, uz = act ? q[2 * QC + r] : 0.0;
             const double g = act ? q[3 * QC + r] : 0.0;
             double tb = 0.0;
-            int more = act ? send - r - 1 : 0;
+            const int more = act ? send - r - 1 : 0;
             const int maxd = __reduce_max_sync(FULL, more);
             for (int d = 1; d <= maxd; ++d) {
                 const int r2i = r + d;

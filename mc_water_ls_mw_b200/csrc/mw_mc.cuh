@@ -1,34 +1,15 @@
 // mw_mc.cuh -- device side of the Monte-Carlo move loop (mc_moves.F90:217-255,
 // :893-964, :966-1213, :1216-1534, :1536-1594, :1597-1689, :2187-2215) for one
-// walker per warp, plus the global-memory layout of a walker.
+// walker per warp, plus the global-memory layout of a context.
+//
+// Code layout matters here: the hot loop (translation move + weight look-up +
+// histogram update + lattice switch) is kept small and inlined, everything that
+// runs rarely (volume move, list rebuild, full energy, image vectors) is
+// __noinline__ so that it does not share the instruction cache with the loop.
 #pragma once
 #include "mw_device.cuh"
 
 namespace mw {
-
-// Per-walker scalars that persist between launches.
-struct WalkerScalars {
-    double E[2];            // model_energy(1:2)                        molint.F90:41
-    double vol[2];          // volume(1:2)                              data_structures.f90:48
-    double mu;              // ls_mu                                    mc_moves.F90:63
-    double max_trans;       // mc_max_trans (Bohr) -- per walker: eq_adjust_mc tunes it per rank
-    double dv_max;          // mc_dv_max (Bohr)
-    double wl_factor;
-    double mu_lo, mu_hi;    // my_mu_min, my_mu_max                     mc_moves.F90:108
-    double avgE[2];         // average_energy                           mc_moves.F90:88
-    double min_dmu, max_dmu;
-    double refH[2];         // ref_enthalpy                             mc_moves.F90:88
-    double sumhist;
-    unsigned long long rng_index;   // next draw index (Philox) / FIFO position
-    int ls;                 // active lattice, 1-based                  data_structures.f90:51
-    int cycle;              // mc_cycle_num
-    int acc_r, acc_v, acc_s, att_r, att_v, att_s;
-    int start_bin, end_bin; // my_start_bin, my_end_bin (1-based)
-    int in_window;          // walker_in_window
-    int wl_invt_active;
-    int wmin_zero;          // invariant "min(weight(window)) == 0" established
-    int error;
-};
 
 // Run parameters shared by all walkers (kernel argument, by value).
 struct McParams {
@@ -74,7 +55,7 @@ struct DeviceState {
 };
 
 // ---------------------------------------------------------------- staging
-__device__ inline void load_walker(const DeviceState& S, int wi, const WalkerView& w)
+__device__ __forceinline__ void load_walker(const DeviceState& S, int wi, const WalkerView& w)
 {
     const int N = S.N, nlat = S.nlat, lane = lane_id();
     const double* gp = S.pos + (size_t)wi * nlat * 3 * N;
@@ -92,10 +73,14 @@ __device__ inline void load_walker(const DeviceState& S, int wi, const WalkerVie
     for (int t = lane; t < nlat * N * LC / 8; t += 32) sl[t] = gl[t];
     const uint8_t* gn = S.nn + (size_t)wi * nlat * N;
     for (int t = lane; t < nlat * N; t += 32) w.nn[t] = gn[t];
+    // scalars: word-wise copy
+    const uint32_t* gs = (const uint32_t*)(S.scal + wi);
+    uint32_t* ss = (uint32_t*)w.sc;
+    for (int t = lane; t < (int)(sizeof(WalkerScalars) / 4); t += 32) ss[t] = gs[t];
     __syncwarp();
 }
 
-__device__ inline void store_walker(const DeviceState& S, int wi, const WalkerView& w, bool lists)
+__device__ __forceinline__ void store_walker(const DeviceState& S, int wi, const WalkerView& w, bool lists)
 {
     const int N = S.N, nlat = S.nlat, lane = lane_id();
     __syncwarp();
@@ -115,136 +100,190 @@ __device__ inline void store_walker(const DeviceState& S, int wi, const WalkerVi
         uint8_t* gn = S.nn + (size_t)wi * nlat * N;
         for (int t = lane; t < nlat * N; t += 32) gn[t] = w.nn[t];
     }
+    uint32_t* gs = (uint32_t*)(S.scal + wi);
+    const uint32_t* ss = (const uint32_t*)w.sc;
+    for (int t = lane; t < (int)(sizeof(WalkerScalars) / 4); t += 32) gs[t] = ss[t];
 }
+
+// ---------------------------------------------------------------- random numbers
+// Per-walker stream of U[0,1) numbers (random.f90:87-102), buffered RB at a time in shared
+// memory.  mode 0: Philox (draw n = half n&1 of block n>>1); mode 1: host FIFO (draw n = fifo[n]).
+// `pos` (index of the next draw inside the buffer) is carried in a register by the caller.
+__device__ __noinline__ void rng_refill(unsigned char* smem, int N, int nlat, const DeviceState& S, const McParams& p, int wi)
+{
+    const WalkerView w = carve_walker(smem, N, nlat);
+    const int lane = lane_id();
+    const uint64_t base = *w.rngbase;
+    __syncwarp();
+    double v0, v1;
+    if (p.rng_mode == 0) {
+        philox_block(p.seed, p.stream0 + (uint32_t)wi, (base >> 1) + (uint64_t)lane, v0, v1);
+    } else {
+        const uint64_t i0 = base + 2u * (uint64_t)lane;
+        v0 = (i0 < S.fifo_len) ? S.fifo[i0] : 0.5;
+        v1 = (i0 + 1 < S.fifo_len) ? S.fifo[i0 + 1] : 0.5;
+    }
+    w.rngbuf[2 * lane] = v0; w.rngbuf[2 * lane + 1] = v1;
+    __syncwarp();
+}
+
+struct Rng {
+    unsigned char* smem; int N, nlat, wi;
+    const DeviceState* S; const McParams* p;
+    double* buf; uint64_t* base;
+    int pos;
+    __device__ __forceinline__ double draw()
+    {
+        if (pos == RB) {
+            __syncwarp();
+            *base = *base + RB;               // every lane stores the same value
+            rng_refill(smem, N, nlat, *S, *p, wi);
+            pos = 0;
+        }
+        return buf[pos++];
+    }
+};
 
 // ---------------------------------------------------------------- order parameter / weights
-// mc_moves.F90:2187-2215 (1-based bin)
-__device__ __forceinline__ int mu_to_bin(const McParams& p, double mu)
-{
-    const int nb = p.nbins;
-    if (fabs(mu) <= 0.5) return nb / 2 + 1;
-    if (mu > 0.0) {
-        const double arg = 1.0 - (mu - 0.5) * (1.0 - p.r_pos) / p.a_pos;
-        return nb / 2 + 2 + (int)(log(arg) / p.log_r_pos);
-    }
-    const double arg = 1.0 - (fabs(mu) - 0.5) * (1.0 - p.r_neg) / p.a_neg;
-    return nb / 2 - (int)(log(arg) / p.log_r_neg);
-}
+struct EtaBin { double eta; int k; };
 
-// mc_moves.F90:893-964.  wgt is this walker's weight array (global memory,
-// read through L2 because the same warp updates it when generating weights).
-__device__ inline double eta_weight(const McParams& p, const DeviceState& S, const WalkerScalars& sc,
-                                    const double* wgt, double mu)
+// mu_to_bin (mc_moves.F90:2187-2215, 1-based bin) and eta_weight (mc_moves.F90:893-964) in one
+// call.  The two sign branches of mu_to_bin share one log: for mu > 0, mu - 0.5 == |mu| - 0.5.
+// wgt is this walker's weight array (global memory, read through L2 because the same warp
+// updates it when generating weights).
+__device__ __noinline__ EtaBin eta_bin(const McParams& p, const double* __restrict__ mubin,
+                                       const double* __restrict__ binwidth, const WalkerScalars* sc,
+                                       const double* wgt, double mu)
 {
-    if (!sc.in_window) return 0.0;          // undefined in the reference (:913); defined as 0
-    if (mu < sc.mu_lo) return F_HUGE;
-    if (mu > sc.mu_hi) return F_HUGE;
-    int k = mu_to_bin(p, mu);
-    k = min(max(k, 1), p.nbins);            // memory safety at mu == mu_max (reference would overrun)
+    EtaBin r;
+    const int nb = p.nbins;
+    int k;
+    if (fabs(mu) <= 0.5) {
+        k = nb / 2 + 1;
+    } else {
+        const bool pos = mu > 0.0;
+        const double rr = pos ? p.r_pos : p.r_neg, aa = pos ? p.a_pos : p.a_neg, lr = pos ? p.log_r_pos : p.log_r_neg;
+        const double arg = 1.0 - (fabs(mu) - 0.5) * (1.0 - rr) / aa;
+        const int t = (int)(log(arg) / lr);
+        k = pos ? nb / 2 + 2 + t : nb / 2 - t;
+    }
+    r.k = k;
+    if (!sc->in_window) { r.eta = 0.0; return r; }          // undefined in the reference (:913); defined as 0
+    if (mu < sc->mu_lo || mu > sc->mu_hi) { r.eta = F_HUGE; return r; }
+    k = min(max(k, 1), nb);                                  // memory safety at mu == mu_max (reference would overrun)
     const double* w = wgt - 1;
-    const double* bw = S.binwidth - 1;
-    const double* mb = S.mubin - 1;
-    if (!p.eta_interp) return __ldcg(w + k);
-    int ka, kb, kr;                          // gradient between bins ka<kb, anchored at kr
-    if (k == sc.start_bin)      { ka = k; kb = k + 1; kr = k; }
-    else if (k == sc.end_bin)   { ka = k - 1; kb = k; kr = k; }
-    else if (mu > __ldg(mb + k)){ ka = k; kb = k + 1; kr = k; }
-    else                        { ka = k - 1; kb = k; kr = k - 1; }
-    ka = max(ka, 1); kb = min(kb, p.nbins);
+    const double* bw = binwidth - 1;
+    const double* mb = mubin - 1;
+    if (!p.eta_interp) { r.eta = __ldcg(w + k); return r; }
+    int ka, kb, kr;                                          // gradient between bins ka<kb, anchored at kr
+    if (k == sc->start_bin)      { ka = k; kb = k + 1; kr = k; }
+    else if (k == sc->end_bin)   { ka = k - 1; kb = k; kr = k; }
+    else if (mu > __ldg(mb + k)) { ka = k; kb = k + 1; kr = k; }
+    else                         { ka = k - 1; kb = k; kr = k - 1; }
+    ka = max(ka, 1); kb = min(kb, nb);
     const double wa = __ldcg(w + ka), wb = __ldcg(w + kb);
     const double g = 2.0 * (wb - wa) / (__ldg(bw + ka) + __ldg(bw + kb));
     const double wr = (kr == ka) ? wa : wb;
-    return wr + (mu - __ldg(mb + kr)) * g;
+    r.eta = wr + (mu - __ldg(mb + kr)) * g;
+    return r;
 }
 
 // mu recomputed from scratch, parenthesised association (mc_moves.F90:1370-1372, :1525-1527, :1583-1585)
-__device__ __forceinline__ double mu_paren(const McParams& p, const WalkerScalars& sc, double N, double lv12)
+__device__ __forceinline__ double mu_paren(const McParams& p, const WalkerScalars* sc, double N, double lv12)
 {
-    double mu = (sc.E[0] + p.pressure * sc.vol[0]) - (sc.E[1] + p.pressure * sc.vol[1]);
-    if (p.leshift) mu = mu - sc.refH[0] + sc.refH[1];
+    double mu = (sc->E[0] + p.pressure * sc->vol[0]) - (sc->E[1] + p.pressure * sc->vol[1]);
+    if (p.leshift) mu = mu - sc->refH[0] + sc->refH[1];
     return mu * p.beta - N * lv12;
 }
 
-// mc_moves.F90:1597-1689
-__device__ inline void update_wl_bins(const McParams& p, const DeviceState& S, WalkerScalars& sc,
-                                      double* wgt, double* hist, double* uhist, double eta_mu)
+// -(diffkT) of mc_lattice_switch (mc_moves.F90:1562-1574) for model energies (E0,E1); eta enters
+// as (x + eta) - eta exactly as in the reference
+__device__ __forceinline__ double switch_arg(const McParams& p, const WalkerView& w, double E0, double E1,
+                                             bool one, double eta, double N)
 {
-    if (sc.cycle < p.eq_mc_cycles) return;
-    const int nb = p.nbins, lane = lane_id();
-    const int k = mu_to_bin(p, sc.mu);
-    if (k < 1 || k > nb) return;
-    const double c = p.av_binwidth / __ldg(S.binwidth + k - 1);
-    if (p.samplerun) {
-        if (lane == 0) {
-            atomicAdd(hist + k - 1, c);
-            atomicAdd(uhist + k - 1, c * exp(eta_mu - p.log_unbiased_norm));
-        }
-        return;
+    const WalkerScalars* sc = w.sc;
+    const double Es = one ? E0 : E1, En = one ? E1 : E0;
+    double d;
+    if (p.npt) {
+        const double Vs = one ? sc->vol[0] : sc->vol[1], Vn = one ? sc->vol[1] : sc->vol[0];
+        const double lvn = one ? w.lv[1] : w.lv[0];                // log(volume(lsn)/volume(ls))
+        d = p.beta * En - p.beta * Es + p.beta * p.pressure * (Vn - Vs) - N * lvn + eta - eta;
+    } else {
+        d = p.beta * En - p.beta * Es + eta - eta;
     }
-    if (lane == 0) atomicAdd(hist + k - 1, c);
+    if (p.leshift) {
+        const double Rs = one ? sc->refH[0] : sc->refH[1], Rn = one ? sc->refH[1] : sc->refH[0];
+        d = d - p.beta * Rn + p.beta * Rs;
+    }
+    return -d;
+}
+
+// mc_lattice_switch (mc_moves.F90:1536-1594), stand-alone form (cold paths)
+__device__ __noinline__ int lattice_switch_cold(unsigned char* smem, const DeviceState& S, const McParams& p, int wi,
+                                                int nlat, int rng_pos)
+{
+    const int N = S.N;
+    const WalkerView w = carve_walker(smem, N, nlat);
+    WalkerScalars* sc = w.sc;
+    Rng rng{smem, N, nlat, wi, &S, &p, w.rngbuf, w.rngbase, rng_pos};
+    const double eta = eta_bin(p, S.mubin, S.binwidth, sc, S.weight + (size_t)wi * S.NB, sc->mu).eta;
+    const double arg = switch_arg(p, w, sc->E[0], sc->E[1], sc->ls == 1, eta, (double)N);
+    const double compare = (arg > 0.0) ? 1.0 : exp_fast(arg);
+    const double x = rng.draw();
+    if (x < compare) {
+        sc->acc_s += 1;
+        sc->mu = mu_paren(p, sc, (double)N, w.lv[0]);
+        sc->ls = 3 - sc->ls;
+    }
+    sc->att_s += 1;
+    return rng.pos;
+}
+
+// mc_moves.F90:1597-1689 for the weight-generation case (not samplerun): the histogram increment
+// is done by the caller; this updates wl_factor (Swetnam / 1-over-t variants) and the weights.
+__device__ __noinline__ void update_weights(unsigned char* smem, int N, int nlat, const McParams& p,
+                                            const double* __restrict__ binwidth, double* wgt, const double* hist, int k)
+{
+    const WalkerView w = carve_walker(smem, N, nlat);
+    WalkerScalars* sc = w.sc;
+    const int nb = p.nbins, lane = lane_id();
     if (p.wl_swetnam) {
-        // Swetnam's increment from the current histogram (:1636-1653)
+        // Swetnam's increment from the current histogram (:1636-1653); sequential order as in the reference
         __syncwarp();
-        sc.sumhist = sc.sumhist + 1.0;
+        const double sumhist = sc->sumhist + 1.0;
+        sc->sumhist = sumhist;
         double f = 0.0;
-        for (int i = 0; i < nb; ++i) {       // sequential order as in the reference; every lane redundantly
-            const double binfrac = __ldg(S.binwidth + i) / (p.mu_max - p.mu_min - 1.0);
-            const double d = __ldcg(hist + i) * __ldg(S.binwidth + i) / sc.sumhist - binfrac;
+        for (int i = 0; i < nb; ++i) {
+            const double bwi = __ldg(binwidth + i);
+            const double binfrac = bwi / (p.mu_max - p.mu_min - 1.0);
+            const double d = __ldcg(hist + i) * bwi / sumhist - binfrac;
             f = f + d * d;
         }
         f = sqrt(f / (double)nb);
         f = log(f);
         f = f * p.wl_alpha * (double)nb;
-        sc.wl_factor = fmin(f, p.orig_wl_factor);
-    } else if (sc.wl_invt_active) {
-        sc.wl_factor = fmin(sc.wl_factor, (double)nb / (double)(sc.cycle * S.N));
+        sc->wl_factor = fmin(f, p.orig_wl_factor);
+    } else if (sc->wl_invt_active) {
+        sc->wl_factor = fmin(sc->wl_factor, (double)nb / (double)(sc->cycle * N));
     }
     const double wk_old = __ldcg(wgt + k - 1);
     // weight(k) = weight(k) + av_binwidth*incr/binwidth(k)   (:1680)
-    const double wk = wk_old + p.av_binwidth * sc.wl_factor / __ldg(S.binwidth + k - 1);
+    const double wk = wk_old + p.av_binwidth * sc->wl_factor / __ldg(binwidth + k - 1);
     __syncwarp();
     if (lane == 0) wgt[k - 1] = wk;
     __syncwarp();
-    // minbin = minval(weight(start:end)); weight -= minbin (:1682-1685).  Subtracting
-    // an exact 0 is a no-op, and the minimum stays 0 unless bin k was a zero bin.
-    if (sc.wmin_zero && wk_old > 0.0) return;
+    // minbin = minval(weight(start:end)); weight -= minbin (:1682-1685).  Subtracting an exact 0 is a
+    // no-op, and the minimum stays 0 unless bin k was a zero bin.
+    if (sc->wmin_zero && wk_old > 0.0) return;
+    const int sb = sc->start_bin, eb = sc->end_bin;
     double mn = F_HUGE;
-    for (int i = sc.start_bin - 1 + lane; i < sc.end_bin; i += 32) mn = fmin(mn, __ldcg(wgt + i));
+    for (int i = sb - 1 + lane; i < eb; i += 32) mn = fmin(mn, __ldcg(wgt + i));
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) mn = fmin(mn, __shfl_xor_sync(FULL, mn, d));
     if (mn != 0.0)
-        for (int i = sc.start_bin - 1 + lane; i < sc.end_bin; i += 32) wgt[i] = __ldcg(wgt + i) - mn;
-    sc.wmin_zero = 1;
+        for (int i = sb - 1 + lane; i < eb; i += 32) wgt[i] = __ldcg(wgt + i) - mn;
+    sc->wmin_zero = 1;
     __syncwarp();
-}
-
-// mc_moves.F90:1536-1594
-__device__ inline void lattice_switch(const McParams& p, WalkerScalars& sc, WarpRng& rng, double N,
-                                      double eta, double lv12, double lv21)
-{
-    const int ls = sc.ls, lsn = 3 - ls;
-    const double b = p.beta;
-    double diffkT;
-    const bool one = (ls == 1);
-    const double Es = one ? sc.E[0] : sc.E[1], En = one ? sc.E[1] : sc.E[0];
-    const double Vs = one ? sc.vol[0] : sc.vol[1], Vn = one ? sc.vol[1] : sc.vol[0];
-    const double lvn = one ? lv21 : lv12;              // log(volume(lsn)/volume(ls))
-    if (p.npt) {
-        diffkT = b * En - b * Es + b * p.pressure * (Vn - Vs) - N * lvn + eta - eta;
-    } else {
-        diffkT = b * En - b * Es + eta - eta;
-    }
-    if (p.leshift) {
-        const double Rs = one ? sc.refH[0] : sc.refH[1], Rn = one ? sc.refH[1] : sc.refH[0];
-        diffkT = diffkT - b * Rn + b * Rs;
-    }
-    const double compare = fmin(1.0, exp(-diffkT));
-    const double x = rng.draw();
-    if (x < compare) {
-        sc.acc_s += 1;
-        sc.mu = mu_paren(p, sc, N, lv12);
-        sc.ls = lsn;
-    }
 }
 
 // fractional rescale of one position (mc_moves.F90:1290-1315 and its three copies): exact arithmetic
@@ -262,14 +301,15 @@ __device__ __forceinline__ void rescale_pos(double& x, double& y, double& z, con
     x = xa(x, t0); y = xa(y, t1); z = xa(z, t2);
 }
 
-__device__ inline void rescale_all(const DeviceState& S, int wi, const WalkerView& w, int lat)
+__device__ __noinline__ void rescale_all(unsigned char* smem, int N, int nlat, double* refpos, int lat)
 {
-    const int N = w.N, lane = lane_id();
+    const WalkerView w = carve_walker(smem, N, nlat);
+    const int lane = lane_id();
     double rm[9], hm[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) { rm[k] = w.recip[lat * 9 + k]; hm[k] = w.cell[lat * 9 + k]; }
     double* P = w.pos + lat * 3 * N;
-    double* R = S.ref + ((size_t)wi * w.nlat + lat) * 3 * N;
+    double* R = refpos + (size_t)lat * 3 * N;
     for (int i = lane; i < N; i += 32) {
         double x = P[i], y = P[N + i], z = P[2 * N + i];
         rescale_pos(x, y, z, rm, hm);
@@ -281,61 +321,58 @@ __device__ inline void rescale_all(const DeviceState& S, int wi, const WalkerVie
     __syncwarp();
 }
 
-// refresh volume, recip matrix, image vectors of a lattice from the cell in shared memory
-__device__ inline void refresh_cell(const WalkerView& w, int lat, double& vol, bool set_volume, int& err)
+// recip matrix of the cell in shared memory -> shared memory (uniform stores)
+__device__ __noinline__ void refresh_recip(unsigned char* smem, int N, int nlat, int lat)
 {
+    const WalkerView w = carve_walker(smem, N, nlat);
     double hm[9], rm[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) hm[k] = w.cell[lat * 9 + k];
-    if (set_volume) vol = fabs(determinant3(hm));
     recipmatrix3(hm, rm);
     __syncwarp();
-    if (lane_id() == 0) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) w.recip[lat * 9 + k] = rm[k];
-    }
+    for (int k = 0; k < 9; ++k) w.recip[lat * 9 + k] = rm[k];
     __syncwarp();
-    compute_ivects_warp(w, lat, err);
 }
 
-__device__ __forceinline__ double sel2(bool first, double a, double b) { return first ? a : b; }
-
-// mc_moves.F90:1216-1534
-template <int NLAT>
-__device__ inline void volume_move(const McParams& p, const DeviceState& S, int wi, const WalkerView& w,
-                                   WalkerScalars& sc, WarpRng& rng, const double* wgt,
-                                   double& lv12, double& lv21, int& err)
+__device__ __forceinline__ double cell_volume(const WalkerView& w, int lat)
 {
+    double hm[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) hm[k] = w.cell[lat * 9 + k];
+    return fabs(determinant3(hm));
+}
+
+// mc_moves.F90:1216-1534.  Cold path (0.26 % of the moves): not inlined.  Returns the new
+// position in the random-number buffer.
+template <int NLAT>
+__device__ __noinline__ int volume_move(unsigned char* smem, const DeviceState& S, const McParams& p, int wi, int rng_pos)
+{
+    const int N = S.N;
+    const WalkerView w = carve_walker(smem, N, NLAT);
+    WalkerScalars* sc = w.sc;
+    Rng rng{smem, N, NLAT, wi, &S, &p, w.rngbuf, w.rngbase, rng_pos};
     const int lane = lane_id();
-    const double Nd = (double)w.N;
+    const double Nd = (double)N;
+    const double* wgt = S.weight + (size_t)wi * S.NB;
     double backupE[2] = {0.0, 0.0}, old_vol[2] = {0.0, 0.0}, newE[2] = {0.0, 0.0};
+    int err = 0;
     // old cell + recip are parked in shared memory: save[0..17] = h, save[18..35] = recip
     double* save = w.save;
 #pragma unroll
     for (int lat = 0; lat < NLAT; ++lat) {
-        backupE[lat] = sc.E[lat];
-        old_vol[lat] = sc.vol[lat];
-        double hm[9], rm[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) hm[k] = w.cell[lat * 9 + k];
-        recipmatrix3(hm, rm);                              // :1260-1262
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                w.recip[lat * 9 + k] = rm[k];
-                save[lat * 9 + k] = hm[k];
-                save[18 + lat * 9 + k] = rm[k];
-            }
-        }
+        backupE[lat] = sc->E[lat];
+        old_vol[lat] = sc->vol[lat];
+        refresh_recip(smem, N, NLAT, lat);                 // :1260-1262
     }
+    if (lane < NLAT * 9) { save[lane] = w.cell[lane]; save[18 + lane] = w.recip[lane]; }
     __syncwarp();
     double x = rng.draw();
     const int idim = (int)xm(x, 3.0) + 1;
     x = rng.draw();
     const int jdim = (int)xm(x, 3.0) + 1;
     x = rng.draw();
-    const double dh = xm(xs(xm(2.0, x), 1.0), sc.dv_max);
+    const double dh = xm(xs(xm(2.0, x), 1.0), sc->dv_max);
     if (lane < NLAT) {
         double* hm = w.cell + lane * 9;
         const double v = xa(MW_H(hm, idim, jdim), dh);
@@ -343,36 +380,39 @@ __device__ inline void volume_move(const McParams& p, const DeviceState& S, int 
         MW_H(hm, idim, jdim) = v;
     }
     __syncwarp();
+    double* refpos = S.ref + (size_t)wi * NLAT * 3 * N;
 #pragma unroll
     for (int lat = 0; lat < NLAT; ++lat) {
-        rescale_all(S, wi, w, lat);                        // recip = old cell's, h = new cell
-        refresh_cell(w, lat, sc.vol[lat], true, err);
-        newE[lat] = full_energy_warp(w, lat, err);
-        sc.E[lat] = newE[lat];
+        rescale_all(smem, N, NLAT, refpos, lat);           // recip = old cell's, h = new cell
+        sc->vol[lat] = cell_volume(w, lat);
+        refresh_recip(smem, N, NLAT, lat);
+        err |= compute_ivects_warp(smem, N, NLAT, lat);
+        newE[lat] = full_energy_warp(smem, N, NLAT, lat);
+        sc->E[lat] = newE[lat];
     }
     double old_eta = 0.0, new_eta = 0.0, old_mu = 0.0;
-    const bool one = (sc.ls == 1);
-    double nlv12 = lv12, nlv21 = lv21;
+    const bool one = (sc->ls == 1);
+    double nlv12 = w.lv[0], nlv21 = w.lv[1];
     if (NLAT == 2) {
-        old_eta = eta_weight(p, S, sc, wgt, sc.mu);
-        old_mu = sc.mu;
-        nlv12 = log(sc.vol[0] / sc.vol[1]); nlv21 = log(sc.vol[1] / sc.vol[0]);
-        sc.mu = mu_paren(p, sc, Nd, nlv12);
-        new_eta = eta_weight(p, S, sc, wgt, sc.mu);
+        old_eta = eta_bin(p, S.mubin, S.binwidth, sc, wgt, sc->mu).eta;
+        old_mu = sc->mu;
+        nlv12 = log(sc->vol[0] / sc->vol[1]); nlv21 = log(sc->vol[1] / sc->vol[0]);
+        sc->mu = mu_paren(p, sc, Nd, nlv12);
+        new_eta = eta_bin(p, S.mubin, S.binwidth, sc, wgt, sc->mu).eta;
     }
     x = rng.draw();
-    const double dE = sel2(one, newE[0] - backupE[0], newE[1] - backupE[1]);
-    const double Vs = sel2(one, sc.vol[0], sc.vol[1]), Vo = sel2(one, old_vol[0], old_vol[1]);
+    const double dE = one ? newE[0] - backupE[0] : newE[1] - backupE[1];
+    const double Vs = one ? sc->vol[0] : sc->vol[1], Vo = one ? old_vol[0] : old_vol[1];
     const double diffkT = p.beta * dE + new_eta - old_eta + p.beta * p.pressure * (Vs - Vo) - Nd * log(Vs / Vo);
     const double compare = fmin(1.0, exp(-diffkT));
     if (x < compare) {
-        sc.acc_v += 1;
+        sc->acc_v += 1;
         if (NLAT == 2) {
-            const double dmu = fabs(old_mu - sc.mu);
-            if (dmu < sc.min_dmu) sc.min_dmu = dmu;
-            if (dmu > sc.max_dmu) sc.max_dmu = dmu;
+            const double dmu = fabs(old_mu - sc->mu);
+            if (dmu < sc->min_dmu) sc->min_dmu = dmu;
+            if (dmu > sc->max_dmu) sc->max_dmu = dmu;
         }
-        lv12 = nlv12; lv21 = nlv21;
+        w.lv[0] = nlv12; w.lv[1] = nlv21;
     } else {
         // :1434-1528: V,h <- old; rescale with recip(NEW) and h(OLD); recip <- old; ivects; E <- backup
         __syncwarp();
@@ -380,235 +420,283 @@ __device__ inline void volume_move(const McParams& p, const DeviceState& S, int 
         __syncwarp();
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {
-            sc.vol[lat] = old_vol[lat];
-            rescale_all(S, wi, w, lat);
+            sc->vol[lat] = old_vol[lat];
+            rescale_all(smem, N, NLAT, refpos, lat);
         }
         if (lane < NLAT * 9) w.recip[lane] = save[18 + lane];
         __syncwarp();
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {
-            compute_ivects_warp(w, lat, err);
-            sc.E[lat] = backupE[lat];
-            compute_bond_masks_warp(w, lat);               // positions moved by rounding; keep masks fresh
+            err |= compute_ivects_warp(smem, N, NLAT, lat);
+            sc->E[lat] = backupE[lat];
+            compute_bond_masks_warp(smem, N, NLAT, lat);   // positions moved by rounding; keep masks fresh
         }
-        if (NLAT == 2) sc.mu = mu_paren(p, sc, Nd, lv12);
+        if (NLAT == 2) sc->mu = mu_paren(p, sc, Nd, w.lv[0]);
     }
+    sc->error |= err;
+    return rng.pos;
 }
 
-// mc_moves.F90:966-1213
+// commit of an accepted translation: new position, own bond mask, and the reverse bits of the
+// bonds that formed / broke (rare)
 template <int NLAT>
-__device__ inline void translation_move(const McParams& p, const DeviceState& S, int wi, const WalkerView& w,
-                                        WalkerScalars& sc, WarpRng& rng, const double* wgt,
-                                        double& eta_final, int& err)
+__device__ __forceinline__ void commit_translation(const WalkerView& w, int imol, const double (*pnew)[3],
+                                                   const uint32_t* mo, const uint32_t* mn)
 {
     const int N = w.N, lane = lane_id();
-    const bool one = (sc.ls == 1);
-    double x = rng.draw();
-    int imol = (int)xm(x, (double)N) + 1;
-    if (imol > N) imol = N;
-    imol -= 1;
-    if (lane == 0) atomicAdd(S.transcount + (size_t)wi * N + imol, 1);
-
-    x = rng.draw();
-    double y = rng.draw();
-    double z = rng.draw();
-    x = xs(xm(2.0, x), 1.0); y = xs(xm(2.0, y), 1.0); z = xs(xm(2.0, z), 1.0);
-    const double norm = xd(1.0, xsqrt(xa(xa(xm(x, x), xm(y, y)), xm(z, z))));
-    x = xm(x, norm); y = xm(y, norm); z = xm(z, norm);
-    const double r = xs(xm(rng.draw(), 2.0), 1.0);
-    x = xm(xm(x, sc.max_trans), r);
-    y = xm(xm(y, sc.max_trans), r);
-    z = xm(xm(z, sc.max_trans), r);
-
-    // displacement in the active lattice (x,y,z) and, through the fractional
-    // coordinates of the active cell, in the other lattice (:1042-1067)
-    double bx = 0.0, by = 0.0, bz = 0.0;
-    if (NLAT == 2) {
-        const double* rm = w.recip + (one ? 0 : 9);
-        double sx = xa(xa(xm(MW_H(rm,1,1), x), xm(MW_H(rm,2,1), y)), xm(MW_H(rm,3,1), z));
-        double sy = xa(xa(xm(MW_H(rm,1,2), x), xm(MW_H(rm,2,2), y)), xm(MW_H(rm,3,2), z));
-        double sz = xa(xa(xm(MW_H(rm,1,3), x), xm(MW_H(rm,2,3), y)), xm(MW_H(rm,3,3), z));
-        sx = xm(xm(sx, 0.5), INV_PI); sy = xm(xm(sy, 0.5), INV_PI); sz = xm(xm(sz, 0.5), INV_PI);
-        const double* hm = w.cell + (one ? 9 : 0);
-        bx = xa(xa(xm(MW_H(hm,1,1), sx), xm(MW_H(hm,1,2), sy)), xm(MW_H(hm,1,3), sz));
-        by = xa(xa(xm(MW_H(hm,2,1), sx), xm(MW_H(hm,2,2), sy)), xm(MW_H(hm,2,3), sz));
-        bz = xa(xa(xm(MW_H(hm,3,1), sx), xm(MW_H(hm,3,2), sy)), xm(MW_H(hm,3,3), sz));
-    }
-    double tv[2][3];
-    tv[0][0] = sel2(one, x, bx); tv[0][1] = sel2(one, y, by); tv[0][2] = sel2(one, z, bz);
-    tv[1][0] = sel2(one, bx, x); tv[1][1] = sel2(one, by, y); tv[1][2] = sel2(one, bz, z);
-    double pnew[2][3];
+    __syncwarp();
 #pragma unroll
     for (int lat = 0; lat < NLAT; ++lat) {
-        const double* P = w.pos + lat * 3 * N;
-        pnew[lat][0] = xa(P[imol], tv[lat][0]);
-        pnew[lat][1] = xa(P[N + imol], tv[lat][1]);
-        pnew[lat][2] = xa(P[2 * N + imol], tv[lat][2]);
-    }
-
-    double eo[2] = {0.0, 0.0}, en[2] = {0.0, 0.0};
-    uint32_t mo[2] = {0, 0}, mn[2] = {0, 0};
-    local_energies_warp<NLAT, true>(w, imol, pnew, eo, en, mo, mn, err);
-
-    double backup[2] = {0.0, 0.0}, dE[2] = {0.0, 0.0};
-#pragma unroll
-    for (int lat = 0; lat < NLAT; ++lat) {
-        backup[lat] = sc.E[lat];
-        sc.E[lat] = sc.E[lat] - eo[lat];
-        sc.E[lat] = sc.E[lat] + en[lat];
-        dE[lat] = en[lat] - eo[lat];
-    }
-    double diffkT, mu_acc = sc.mu, mu_rej = sc.mu, eta_acc = 0.0, eta_rej = 0.0;
-    if (NLAT == 1) {
-        diffkT = p.beta * dE[0];
-    } else {
-        const double dm = (dE[0] - dE[1]) * p.beta;
-        mu_acc = sc.mu + dm;
-        mu_rej = mu_acc - dm;
-        // three weight look-ups in parallel lanes: eta(mu), eta(mu_acc), eta(mu_rej)
-        const double mine = (lane == 0) ? sc.mu : (lane == 1) ? mu_acc : mu_rej;
-        double e = 0.0;
-        if (lane < 3) e = eta_weight(p, S, sc, wgt, mine);
-        const double eta_old = __shfl_sync(FULL, e, 0);
-        eta_acc = __shfl_sync(FULL, e, 1);
-        eta_rej = __shfl_sync(FULL, e, 2);
-        diffkT = sel2(one, dE[0], dE[1]) * p.beta + eta_acc - eta_old;
-    }
-    const double zeta = rng.draw();
-    if (zeta < fmin(1.0, exp(-diffkT))) {
-        sc.acc_r += 1;
-        const double dmu = fabs(dE[0] - dE[1]) * p.beta;
-        if (dmu < sc.min_dmu) sc.min_dmu = dmu;
-        if (dmu > sc.max_dmu) sc.max_dmu = dmu;
-        sc.mu = mu_acc; eta_final = eta_acc;
-        // commit: position, own bond mask, and the reverse bits of bonds that formed / broke
-        __syncwarp();
-#pragma unroll
-        for (int lat = 0; lat < NLAT; ++lat) {
-            double* P = w.pos + lat * 3 * N;
-            if (lane < 3) P[lane * N + imol] = (lane == 0) ? pnew[lat][0] : (lane == 1) ? pnew[lat][1] : pnew[lat][2];
-            uint32_t changed = mo[lat] ^ mn[lat];
-            if (lane == 0) w.bmask[lat * N + imol] = mn[lat];
-            const int nv = w.niv[lat];
-            while (changed) {
-                const int s = __ffs(changed) - 1; changed &= changed - 1;
-                const uint32_t e = w.list[((size_t)lat * N + imol) * LC + s];
-                const int j = e & 1023, img = e >> 10;
-                const uint32_t target = ((uint32_t)inverse_image(img, nv) << 10) | (uint32_t)imol;
-                const int nnj = w.nn[lat * N + j];
-                const uint32_t e2 = (lane < nnj) ? w.list[((size_t)lat * N + j) * LC + lane] : 0xffffffffu;
-                const uint32_t hit = __ballot_sync(FULL, e2 == target);
-                if (hit && lane == 0) {
-                    const int s2 = __ffs(hit) - 1;
-                    const uint32_t bit = (mn[lat] >> s) & 1u;
-                    w.bmask[lat * N + j] = (w.bmask[lat * N + j] & ~(1u << s2)) | (bit << s2);
-                }
-                __syncwarp();
+        double* P = w.pos + lat * 3 * N;
+        if (lane < 3) P[lane * N + imol] = (lane == 0) ? pnew[lat][0] : (lane == 1) ? pnew[lat][1] : pnew[lat][2];
+        uint32_t changed = mo[lat] ^ mn[lat];
+        if (lane == 0) w.bmask[lat * N + imol] = mn[lat];
+        const int nv = w.niv[lat];
+        while (changed) {
+            const int s = __ffs(changed) - 1; changed &= changed - 1;
+            const uint32_t e = w.list[((size_t)lat * N + imol) * LC + s];
+            const int j = e & 1023, img = e >> 10;
+            const uint32_t target = ((uint32_t)inverse_image(img, nv) << 10) | (uint32_t)imol;
+            const int nnj = w.nn[lat * N + j];
+            const uint32_t e2 = (lane < nnj) ? w.list[((size_t)lat * N + j) * LC + lane] : 0xffffffffu;
+            const uint32_t hit = __ballot_sync(FULL, e2 == target);
+            if (hit && lane == 0) {
+                const int s2 = __ffs(hit) - 1;
+                const uint32_t bit = (mn[lat] >> s) & 1u;
+                w.bmask[lat * N + j] = (w.bmask[lat * N + j] & ~(1u << s2)) | (bit << s2);
             }
+            __syncwarp();
         }
-        __syncwarp();
-    } else {
-        // reject: the reference restores by (x+t)-t, not by copy (mc_moves.F90:1186)
-        __syncwarp();
-#pragma unroll
-        for (int lat = 0; lat < NLAT; ++lat) {
-            double* P = w.pos + lat * 3 * N;
-            const double pn = (lane == 0) ? pnew[lat][0] : (lane == 1) ? pnew[lat][1] : pnew[lat][2];
-            const double tt = (lane == 0) ? tv[lat][0] : (lane == 1) ? tv[lat][1] : tv[lat][2];
-            if (lane < 3) P[lane * N + imol] = xs(pn, tt);
-            sc.E[lat] = backup[lat];
-        }
-        if (NLAT == 2) { sc.mu = mu_rej; eta_final = eta_rej; }
-        __syncwarp();
     }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------- the walker kernel
 // One warp (= one CTA of 32 threads) per walker; ncycles MC cycles of the hot
 // part of mc_cycle (mc_moves.F90:117-255).
 template <int NLAT>
-__global__ void __launch_bounds__(32) k_mc_run(DeviceState S, McParams p, int ncycles)
+__global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceState S,
+                                               const __grid_constant__ McParams p, int ncycles)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int wi = blockIdx.x;
     if (wi >= S.W) return;
     const int lane = lane_id();
-    const WalkerView w = carve_walker(smem, S.N, NLAT);
-    load_walker(S, wi, w);
-    WalkerScalars sc = S.scal[wi];
     const int N = S.N;
+    const WalkerView w = carve_walker(smem, N, NLAT);
+    load_walker(S, wi, w);
+    WalkerScalars* sc = w.sc;
     const double Nd = (double)N;
     double* wgt = S.weight + (size_t)wi * S.NB;
     double* hist = S.hist + (size_t)wi * S.NB;
     double* uhist = S.uhist + (size_t)wi * S.NB;
-    int err = sc.error;
+    int err = 0;
     if (p.prob_error) err |= ERR_PROB;
 
 #pragma unroll
-    for (int lat = 0; lat < NLAT; ++lat) compute_bond_masks_warp(w, lat);
+    for (int lat = 0; lat < NLAT; ++lat) compute_bond_masks_warp(smem, N, NLAT, lat);
 
-    WarpRng rng;
-    rng.mode = p.rng_mode; rng.seed = p.seed; rng.stream = p.stream0 + (uint32_t)wi;
-    rng.fifo = S.fifo; rng.fifo_len = S.fifo_len;
-    rng.init(sc.rng_index);
-
-    double lv12 = 0.0, lv21 = 0.0;
-    if (NLAT == 2) { lv12 = log(sc.vol[0] / sc.vol[1]); lv21 = log(sc.vol[1] / sc.vol[0]); }
+    Rng rng{smem, N, NLAT, wi, &S, &p, w.rngbuf, w.rngbase, 0};
+    {
+        const uint64_t idx = sc->rng_index;
+        *w.rngbase = idx & ~(uint64_t)1;
+        rng.pos = (int)(idx & 1);
+        rng_refill(smem, N, NLAT, S, p, wi);
+    }
+    if (NLAT == 2) { w.lv[0] = log(sc->vol[0] / sc->vol[1]); w.lv[1] = log(sc->vol[1] / sc->vol[0]); }
 
     for (int cyc = 0; cyc < ncycles && !(err & (ERR_WINDOW | ERR_PROB)); ++cyc) {
-        sc.cycle += 1;
+        const int cycle = sc->cycle + 1;
+        sc->cycle = cycle;
         if (p.dd) {                                            // mc_moves.F90:181-210
-            if (sc.cycle < p.eq_mc_cycles) sc.in_window = (sc.mu > sc.mu_lo) && (sc.mu < sc.mu_hi);
-            else if (sc.cycle == p.eq_mc_cycles) { if (!sc.in_window) { err |= ERR_WINDOW; break; } }
-            else sc.in_window = 1;
+            if (cycle < p.eq_mc_cycles) sc->in_window = (sc->mu > sc->mu_lo) && (sc->mu < sc->mu_hi);
+            else if (cycle == p.eq_mc_cycles) { if (!sc->in_window) { err |= ERR_WINDOW; break; } }
+            else sc->in_window = 1;
         }
-        if (sc.cycle % p.list_update_int == 0) {               // :218-222
+        if (cycle % p.list_update_int == 0) {                  // :218-222
 #pragma unroll
             for (int lat = 0; lat < NLAT; ++lat) {
-                compute_neighbours_warp(w, lat, err);
-                compute_bond_masks_warp(w, lat);
+                err |= compute_neighbours_warp(smem, N, NLAT, lat);
+                compute_bond_masks_warp(smem, N, NLAT, lat);
             }
         }
-        const bool dd_eq = p.dd && (sc.cycle < p.eq_mc_cycles);
+        const bool dd_eq = p.dd && (cycle < p.eq_mc_cycles);
+        const bool bins_on = !(cycle < p.eq_mc_cycles);        // mc_update_wl_bins: :1615
+        const bool do_switch = (NLAT == 2) && p.always_switch && !dd_eq;
+        const bool fuse_switch = do_switch && p.samplerun;     // weights fixed: eta of the switch is already known
+
         for (int imove = 0; imove < N; ++imove) {              // :224-250
             const double xi = rng.draw();
-            double eta = 0.0;
-            bool eta_known = false;
             if (xi < p.transP) {
-                translation_move<NLAT>(p, S, wi, w, sc, rng, wgt, eta, err);
-                eta_known = (NLAT == 2);
-                if (p.samplerun && !eta_known) eta = eta_weight(p, S, sc, wgt, sc.mu);
-                update_wl_bins(p, S, sc, wgt, hist, uhist, eta);
-                sc.att_r += 1;
-            } else if (xi < p.volP) {
-                volume_move<NLAT>(p, S, wi, w, sc, rng, wgt, lv12, lv21, err);
-                eta = eta_weight(p, S, sc, wgt, sc.mu);
-                update_wl_bins(p, S, sc, wgt, hist, uhist, eta);
-                sc.att_v += 1;
-            } else if (xi < p.swP) {
-                if (NLAT == 2 && !dd_eq) {
-                    lattice_switch(p, sc, rng, Nd, eta_weight(p, S, sc, wgt, sc.mu), lv12, lv21);
-                    sc.att_s += 1;
+                // ====================== mc_water_translation (mc_moves.F90:966-1213) ======================
+                const bool one = (sc->ls == 1);
+                double x = rng.draw();
+                int imol = (int)xm(x, Nd) + 1;
+                if (imol > N) imol = N;
+                imol -= 1;
+                if (lane == 0) atomicAdd(S.transcount + (size_t)wi * N + imol, 1);
+                x = rng.draw();
+                double y = rng.draw();
+                double z = rng.draw();
+                x = xs(xm(2.0, x), 1.0); y = xs(xm(2.0, y), 1.0); z = xs(xm(2.0, z), 1.0);
+                const double norm = xd(1.0, xsqrt(xa(xa(xm(x, x), xm(y, y)), xm(z, z))));
+                x = xm(x, norm); y = xm(y, norm); z = xm(z, norm);
+                const double r = xs(xm(rng.draw(), 2.0), 1.0);
+                const double mt = sc->max_trans;
+                x = xm(xm(x, mt), r); y = xm(xm(y, mt), r); z = xm(xm(z, mt), r);
+                // displacement in the active lattice (x,y,z) and, through the fractional
+                // coordinates of the active cell, in the other lattice (:1042-1067)
+                double bx = 0.0, by = 0.0, bz = 0.0;
+                if (NLAT == 2) {
+                    const double* rm = w.recip + (one ? 0 : 9);
+                    double sx = xa(xa(xm(MW_H(rm,1,1), x), xm(MW_H(rm,2,1), y)), xm(MW_H(rm,3,1), z));
+                    double sy = xa(xa(xm(MW_H(rm,1,2), x), xm(MW_H(rm,2,2), y)), xm(MW_H(rm,3,2), z));
+                    double sz = xa(xa(xm(MW_H(rm,1,3), x), xm(MW_H(rm,2,3), y)), xm(MW_H(rm,3,3), z));
+                    sx = xm(xm(sx, 0.5), INV_PI); sy = xm(xm(sy, 0.5), INV_PI); sz = xm(xm(sz, 0.5), INV_PI);
+                    const double* hm = w.cell + (one ? 9 : 0);
+                    bx = xa(xa(xm(MW_H(hm,1,1), sx), xm(MW_H(hm,1,2), sy)), xm(MW_H(hm,1,3), sz));
+                    by = xa(xa(xm(MW_H(hm,2,1), sx), xm(MW_H(hm,2,2), sy)), xm(MW_H(hm,2,3), sz));
+                    bz = xa(xa(xm(MW_H(hm,3,1), sx), xm(MW_H(hm,3,2), sy)), xm(MW_H(hm,3,3), sz));
                 }
+                double tv[2][3];
+                tv[0][0] = one ? x : bx; tv[0][1] = one ? y : by; tv[0][2] = one ? z : bz;
+                tv[1][0] = one ? bx : x; tv[1][1] = one ? by : y; tv[1][2] = one ? bz : z;
+                double pnew[2][3];
+#pragma unroll
+                for (int lat = 0; lat < NLAT; ++lat) {
+                    const double* P = w.pos + lat * 3 * N;
+                    pnew[lat][0] = xa(P[imol], tv[lat][0]);
+                    pnew[lat][1] = xa(P[N + imol], tv[lat][1]);
+                    pnew[lat][2] = xa(P[2 * N + imol], tv[lat][2]);
+                }
+                double eo[2] = {0.0, 0.0}, en[2] = {0.0, 0.0};
+                uint32_t mo[2] = {0, 0}, mn[2] = {0, 0};
+                local_energies_warp<NLAT, true>(w, imol, pnew, eo, en, mo, mn);
+
+                // model_energy bookkeeping exactly as :1013-1016, :1087-1090
+                const double Eb0 = sc->E[0], Eb1 = sc->E[1];
+                const double Ea0 = (Eb0 - eo[0]) + en[0], Ea1 = (Eb1 - eo[1]) + en[1];
+                const double dE0 = en[0] - eo[0], dE1 = en[1] - eo[1];
+                const double mu_old = sc->mu;
+                double diffkT, mu_acc = mu_old, mu_rej = mu_old;
+                double eta_acc = 0.0, eta_rej = 0.0;
+                int k_acc = 0, k_rej = 0;
+                if (NLAT == 1) {
+                    diffkT = p.beta * dE0;
+                    if (bins_on) {       // single box: ls_mu is never assigned (0) but the bins are still updated
+                        const EtaBin eb = eta_bin(p, S.mubin, S.binwidth, sc, wgt, mu_old);
+                        eta_acc = eta_rej = eb.eta; k_acc = k_rej = eb.k;
+                    }
+                } else {
+                    const double dm = (dE0 - dE1) * p.beta;
+                    mu_acc = mu_old + dm;                         // :1113
+                    mu_rej = mu_acc - dm;                         // :1195 -- (mu + d) - d, not a copy
+                    // three weight look-ups in parallel lanes: eta(mu), eta(mu_acc), eta(mu_rej)
+                    const double mine = (lane == 0) ? mu_old : (lane == 1) ? mu_acc : mu_rej;
+                    EtaBin eb; eb.eta = 0.0; eb.k = 0;
+                    if (lane < 3) eb = eta_bin(p, S.mubin, S.binwidth, sc, wgt, mine);
+                    const double eta_old = __shfl_sync(FULL, eb.eta, 0);
+                    eta_acc = __shfl_sync(FULL, eb.eta, 1); eta_rej = __shfl_sync(FULL, eb.eta, 2);
+                    k_acc = __shfl_sync(FULL, eb.k, 1); k_rej = __shfl_sync(FULL, eb.k, 2);
+                    diffkT = (one ? dE0 : dE1) * p.beta + eta_acc - eta_old;
+                }
+                // one exponential pass for everything the rest of this move needs:
+                //   lane 0  : acceptance probability            exp(-diffkT)
+                //   lane 1/2: lattice-switch probability if this move is accepted / rejected
+                //   lane 3/4: unbiased-histogram factor exp(eta - log_unbiased_norm) if accepted / rejected
+                double arg = -diffkT;
+                if (fuse_switch && (lane == 1 || lane == 2)) {
+                    const bool a = (lane == 1);
+                    arg = switch_arg(p, w, a ? Ea0 : Eb0, a ? Ea1 : Eb1, one, a ? eta_acc : eta_rej, Nd);
+                }
+                if (lane == 3) arg = eta_acc - p.log_unbiased_norm;
+                if (lane == 4) arg = eta_rej - p.log_unbiased_norm;
+                // min(1, exp(.)) for the probabilities (lanes 0-2); plain exp for the histogram factors
+                const double ex = (arg > 0.0 && lane < 3) ? 1.0 : exp_fast(fmin(arg, 700.0));
+                const double zeta = rng.draw();
+                const bool accepted = zeta < __shfl_sync(FULL, ex, 0);                         // :1145-1146
+                if (accepted) {
+                    sc->acc_r += 1;
+                    const double dmu = fabs(dE0 - dE1) * p.beta;
+                    if (dmu < sc->min_dmu) sc->min_dmu = dmu;
+                    if (dmu > sc->max_dmu) sc->max_dmu = dmu;
+                    sc->E[0] = Ea0;
+                    if (NLAT == 2) { sc->E[1] = Ea1; sc->mu = mu_acc; }
+                    commit_translation<NLAT>(w, imol, pnew, mo, mn);
+                } else {
+                    // reject: the reference restores by (x+t)-t, not by copy (mc_moves.F90:1186)
+                    __syncwarp();
+#pragma unroll
+                    for (int lat = 0; lat < NLAT; ++lat) {
+                        double* P = w.pos + lat * 3 * N;
+                        const double pn = (lane == 0) ? pnew[lat][0] : (lane == 1) ? pnew[lat][1] : pnew[lat][2];
+                        const double tt = (lane == 0) ? tv[lat][0] : (lane == 1) ? tv[lat][1] : tv[lat][2];
+                        if (lane < 3) P[lane * N + imol] = xs(pn, tt);
+                    }
+                    if (NLAT == 2) sc->mu = mu_rej;
+                    __syncwarp();
+                }
+                sc->att_r += 1;
+                // ====================== mc_update_wl_bins (mc_moves.F90:1597-1689) ======================
+                const int kb = accepted ? k_acc : k_rej;
+                if (bins_on && kb >= 1 && kb <= p.nbins) {
+                    const double c = p.av_binwidth / __ldg(S.binwidth + kb - 1);
+                    if (lane == 0) atomicAdd(hist + kb - 1, c);
+                    if (p.samplerun) {
+                        const double uf = __shfl_sync(FULL, ex, accepted ? 3 : 4);
+                        if (lane == 0) atomicAdd(uhist + kb - 1, c * uf);
+                    } else {
+                        update_weights(smem, N, NLAT, p, S.binwidth, wgt, hist, kb);
+                    }
+                }
+                // ====================== mc_lattice_switch (mc_moves.F90:1536-1594) ======================
+                if (fuse_switch) {
+                    const double compare = __shfl_sync(FULL, ex, accepted ? 1 : 2);
+                    const double xs_ = rng.draw();
+                    if (xs_ < compare) {
+                        sc->acc_s += 1;
+                        sc->mu = mu_paren(p, sc, Nd, w.lv[0]);
+                        sc->ls = 3 - sc->ls;
+                    }
+                    sc->att_s += 1;
+                } else if (do_switch) {
+                    // weights may have moved in update_weights: the reference looks eta up again
+                    rng.pos = lattice_switch_cold(smem, S, p, wi, NLAT, rng.pos);
+                }
+                continue;
             }
-            if (NLAT == 2 && p.always_switch && !dd_eq) {
-                // weights may have moved in update_wl_bins when generating them: look eta up again then
-                if (!eta_known || !p.samplerun) eta = eta_weight(p, S, sc, wgt, sc.mu);
-                lattice_switch(p, sc, rng, Nd, eta, lv12, lv21);
-                sc.att_s += 1;
+            // ---------------- rare move types ----------------
+            if (xi < p.volP) {
+                rng.pos = volume_move<NLAT>(smem, S, p, wi, rng.pos);
+                const EtaBin eb = eta_bin(p, S.mubin, S.binwidth, sc, wgt, sc->mu);
+                if (bins_on && eb.k >= 1 && eb.k <= p.nbins) {
+                    const double c = p.av_binwidth / __ldg(S.binwidth + eb.k - 1);
+                    if (lane == 0) atomicAdd(hist + eb.k - 1, c);
+                    if (p.samplerun) {
+                        if (lane == 0) atomicAdd(uhist + eb.k - 1, c * exp(eb.eta - p.log_unbiased_norm));
+                    } else {
+                        update_weights(smem, N, NLAT, p, S.binwidth, wgt, hist, eb.k);
+                    }
+                }
+                sc->att_v += 1;
+            } else if (xi < p.swP) {
+                if (NLAT == 2 && !dd_eq) rng.pos = lattice_switch_cold(smem, S, p, wi, NLAT, rng.pos);
             }
+            if (do_switch) rng.pos = lattice_switch_cold(smem, S, p, wi, NLAT, rng.pos);
         }
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {                 // :253-255
-            sc.avgE[lat] = sc.avgE[lat] + sc.E[lat];
-            if (p.npt) sc.avgE[lat] = sc.avgE[lat] + p.pressure * sc.vol[lat];
+            double a = sc->avgE[lat] + sc->E[lat];
+            if (p.npt) a = a + p.pressure * sc->vol[lat];
+            sc->avgE[lat] = a;
         }
     }
-    if (rng.underrun) err |= ERR_RNG_UNDERRUN;
-    sc.rng_index = rng.index();
-    sc.error = err;
+    const uint64_t idx = *w.rngbase + (uint64_t)rng.pos;
+    if (p.rng_mode == 1 && idx > S.fifo_len) err |= ERR_RNG_UNDERRUN;
+    sc->rng_index = idx;
+    sc->error |= err;
+    __syncwarp();
     store_walker(S, wi, w, true);
-    if (lane == 0) S.scal[wi] = sc;
 }
 
 }  // namespace mw

@@ -353,7 +353,7 @@ struct OpArgs {
 };
 
 template <int NLAT>
-__global__ void __launch_bounds__(32) k_walker_op(DeviceState S, OpArgs a)
+__global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ DeviceState S, const __grid_constant__ OpArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int wi = a.w0 + blockIdx.x;
@@ -361,111 +361,89 @@ __global__ void __launch_bounds__(32) k_walker_op(DeviceState S, OpArgs a)
     const int lane = lane_id(), N = S.N;
     const WalkerView w = carve_walker(smem, N, NLAT);
     load_walker(S, wi, w);
-    WalkerScalars sc = S.scal[wi];
-    int err = sc.error;
+    WalkerScalars* sc = w.sc;
+    int err = 0;
     bool store_lists = false;
 
     switch (a.op) {
     case OP_ENERGY_INIT: {
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {
-            double hm[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) hm[k] = w.cell[lat * 9 + k];
-            sc.vol[lat] = fabs(determinant3(hm));                       // molint.F90:125
-            double rm[9];
-            recipmatrix3(hm, rm);                                       // init.f90:90
-            __syncwarp();
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < 9; ++k) w.recip[lat * 9 + k] = rm[k];
-            }
-            __syncwarp();
+            sc->vol[lat] = cell_volume(w, lat);                         // molint.F90:125
+            refresh_recip(smem, N, NLAT, lat);                          // init.f90:90
         }
-        err = 0;
+        sc->error = 0;
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {
-            compute_neighbours_warp(w, lat, err);                       // includes compute_ivects
-            sc.E[lat] = full_energy_warp(w, lat, err);
+            err |= compute_neighbours_warp(smem, N, NLAT, lat);         // includes compute_ivects
+            sc->E[lat] = full_energy_warp(smem, N, NLAT, lat);
         }
         if (NLAT == 2 && a.refresh_mu) {      // mc_moves.F90:857-862 (left-to-right association)
-            double mu = sc.E[0] + a.pressure * sc.vol[0] - sc.E[1] - a.pressure * sc.vol[1];
-            if (a.leshift) mu = mu - sc.refH[0] + sc.refH[1];
-            sc.mu = mu * a.beta - (double)N * log(sc.vol[0] / sc.vol[1]);
+            double mu = sc->E[0] + a.pressure * sc->vol[0] - sc->E[1] - a.pressure * sc->vol[1];
+            if (a.leshift) mu = mu - sc->refH[0] + sc->refH[1];
+            sc->mu = mu * a.beta - (double)N * log(sc->vol[0] / sc->vol[1]);
         }
         store_lists = true;
         break;
     }
     case OP_IVECTS:
-        compute_ivects_warp(w, a.lat, err);
+        err |= compute_ivects_warp(smem, N, NLAT, a.lat);
         break;
     case OP_NEIGHBOURS:
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat)
-            if (a.lat < 0 || a.lat == lat) compute_neighbours_warp(w, lat, err);
+            if (a.lat < 0 || a.lat == lat) err |= compute_neighbours_warp(smem, N, NLAT, lat);
         store_lists = true;
         break;
     case OP_MODEL_ENERGY:
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat)
             if (a.lat < 0 || a.lat == lat) {
-                sc.E[lat] = full_energy_warp(w, lat, err);
-                if (a.out && lane == 0) a.out[(size_t)(wi - a.w0) * NLAT + lat] = sc.E[lat];
+                const double e = full_energy_warp(smem, N, NLAT, lat);
+                sc->E[lat] = e;
+                if (a.out && lane == 0) a.out[(size_t)(wi - a.w0) * NLAT + lat] = e;
             }
         break;
     case OP_LOCAL_ONE:
     case OP_LOCAL_ALL: {
 #pragma unroll
-        for (int lat = 0; lat < NLAT; ++lat) compute_bond_masks_warp(w, lat);
+        for (int lat = 0; lat < NLAT; ++lat) compute_bond_masks_warp(smem, N, NLAT, lat);
         const int i0 = (a.op == OP_LOCAL_ONE) ? a.imol : 0;
         const int i1 = (a.op == OP_LOCAL_ONE) ? a.imol + 1 : N;
         for (int i = i0; i < i1; ++i) {
             double eo[2] = {0, 0}, en[2] = {0, 0};
             uint32_t mo[2], mn[2];
-            local_energies_warp<NLAT, false>(w, i, nullptr, eo, en, mo, mn, err);
+            local_energies_warp<NLAT, false>(w, i, nullptr, eo, en, mo, mn);
             if (lane == 0) a.out[i - i0] = (a.lat == 0) ? eo[0] : eo[1];
         }
         break;
     }
     case OP_MONITOR: {
         // mc_moves.F90:1722-1732 (exact arithmetic: the step sizes feed the state arithmetic)
-        const double atr = xd((double)sc.acc_r, (double)sc.att_r);
-        const double avr = xd((double)sc.acc_v, (double)sc.att_v);
-        if (a.eq_adjust && sc.cycle < a.eq_mc_cycles) {
-            sc.max_trans = fmax(xd(xm(sc.max_trans, atr), a.target_ratio), 0.1);
-            sc.dv_max = fmax(xd(xm(sc.dv_max, avr), a.target_ratio), 0.0001);
+        const double atr = xd((double)sc->acc_r, (double)sc->att_r);
+        const double avr = xd((double)sc->acc_v, (double)sc->att_v);
+        if (a.eq_adjust && sc->cycle < a.eq_mc_cycles) {
+            sc->max_trans = fmax(xd(xm(sc->max_trans, atr), a.target_ratio), 0.1);
+            sc->dv_max = fmax(xd(xm(sc->dv_max, avr), a.target_ratio), 0.0001);
         }
 #pragma unroll
-        for (int lat = 0; lat < NLAT; ++lat) sc.E[lat] = full_energy_warp(w, lat, err);   // :1786-1792
-        sc.acc_r = sc.acc_v = sc.acc_s = sc.att_r = sc.att_v = sc.att_s = 0;              // :1797-1810
+        for (int lat = 0; lat < NLAT; ++lat) sc->E[lat] = full_energy_warp(smem, N, NLAT, lat);   // :1786-1792
+        sc->acc_r = 0; sc->acc_v = 0; sc->acc_s = 0; sc->att_r = 0; sc->att_v = 0; sc->att_s = 0; // :1797-1810
         for (int i = lane; i < N; i += 32) S.transcount[(size_t)wi * N + i] = 0;
-        sc.avgE[0] = sc.avgE[1] = 0.0;
-        sc.max_dmu = 0.0; sc.min_dmu = F_HUGE;
+        sc->avgE[0] = 0.0; sc->avgE[1] = 0.0;
+        sc->max_dmu = 0.0; sc->min_dmu = F_HUGE;
         break;
     }
     case OP_CHAIN_SYNC: {
         // mc_moves.F90:2217-2416 (two lattices only)
         if (NLAT == 2) {
-            sc.E[0] = full_energy_warp(w, 0, err);
-            sc.E[1] = full_energy_warp(w, 1, err);
+            sc->E[0] = full_energy_warp(smem, N, NLAT, 0);
+            sc->E[1] = full_energy_warp(smem, N, NLAT, 1);
             const double* rh = S.refcell + (size_t)wi * NLAT * 9;
             if (lane < 9) w.cell[9 + lane] = xa(rh[9 + lane], xs(w.cell[lane], rh[lane]));     // :2262,2277
             __syncwarp();
-            double dummy;
-#pragma unroll
-            for (int lat = 0; lat < 2; ++lat) {
-                double hm[9], rm[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) hm[k] = w.cell[lat * 9 + k];
-                recipmatrix3(hm, rm);
-                __syncwarp();
-                if (lane == 0) {
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) w.recip[lat * 9 + k] = rm[k];
-                }
-                __syncwarp();
-            }
-            (void)dummy;
+            refresh_recip(smem, N, NLAT, 0);
+            refresh_recip(smem, N, NLAT, 1);
             const double* R = S.ref + (size_t)wi * NLAT * 3 * N;
             for (int i = lane; i < N; i += 32) {
                 double sv[2][3], rsv[2][3];
@@ -500,26 +478,23 @@ __global__ void __launch_bounds__(32) k_walker_op(DeviceState S, OpArgs a)
             __syncwarp();
 #pragma unroll
             for (int lat = 0; lat < 2; ++lat) {
-                double hm[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) hm[k] = w.cell[lat * 9 + k];
-                sc.vol[lat] = fabs(determinant3(hm));
-                compute_ivects_warp(w, lat, err);
+                sc->vol[lat] = cell_volume(w, lat);
+                err |= compute_ivects_warp(smem, N, NLAT, lat);
             }
-            sc.E[0] = full_energy_warp(w, 0, err);
-            sc.E[1] = full_energy_warp(w, 1, err);
+            sc->E[0] = full_energy_warp(smem, N, NLAT, 0);
+            sc->E[1] = full_energy_warp(smem, N, NLAT, 1);
             // left-to-right association (:2400-2402)
-            double mu = sc.E[0] + a.pressure * sc.vol[0] - sc.E[1] - a.pressure * sc.vol[1];
-            if (a.leshift) mu = mu - sc.refH[0] + sc.refH[1];
-            sc.mu = mu * a.beta - (double)N * log(sc.vol[0] / sc.vol[1]);
+            double mu = sc->E[0] + a.pressure * sc->vol[0] - sc->E[1] - a.pressure * sc->vol[1];
+            if (a.leshift) mu = mu - sc->refH[0] + sc->refH[1];
+            sc->mu = mu * a.beta - (double)N * log(sc->vol[0] / sc->vol[1]);
         }
         break;
     }
     default: break;
     }
-    sc.error = err;
+    sc->error |= err;
+    __syncwarp();
     store_walker(S, wi, w, store_lists);
-    if (lane == 0) S.scal[wi] = sc;
 }
 
 static int launch_op(mwgpu_ctx* c, OpArgs a, int nw, bool sync = true)
@@ -670,7 +645,7 @@ extern "C" int mwgpu_compute_local_real_energy_all(mwgpu_ctx* c, int walker, int
 // batched full energy: "full mW energy evals/s" kernel.  One warp per (walker, lattice);
 // needs only positions, lists and image vectors of that lattice.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_model_energy_all(DeviceState S, double* __restrict__ out)
+__global__ void __launch_bounds__(32) k_model_energy_all(const __grid_constant__ DeviceState S, double* __restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int unit = blockIdx.x;                 // walker * nlat + lat
@@ -689,11 +664,9 @@ __global__ void __launch_bounds__(32) k_model_energy_all(DeviceState S, double* 
     const uint8_t* gn = S.nn + ((size_t)wi * S.nlat + lat) * N;
     for (int t = lane; t < N; t += 32) w.nn[t] = gn[t];
     __syncwarp();
-    int err = 0;
-    const double e = full_energy_warp(w, 0, err);
+    const double e = full_energy_warp(smem, N, 1, 0);
     if (lane == 0) {
         S.scal[wi].E[lat] = e;
-        if (err) atomicOr(&S.scal[wi].error, err);
         if (out) out[unit] = e;
     }
 }

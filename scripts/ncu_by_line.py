@@ -50,3 +50,25 @@ print(f"{'inst%':>6} {'smp%':>6} {'lanes':>5} {'sass':>5}  where")
 for (f, ln), (ie, sm, te, ns) in items[:top]:
     print(f"{ie/tot*100:6.2f} {sm/max(tots,1)*100:6.2f} {te/max(ie,1):5.1f} {ns:5d}  {f}:{ln}  {srcline(f, ln)}")
 # per-file-function coarse buckets
+
+# ---- coarse buckets by (file, line range): edit RANGES to taste
+import os
+RANGES = os.environ.get("NCU_RANGES")
+if RANGES:
+    buckets = []
+    for item in RANGES.split(";"):
+        name, f, a, b = item.split(":")
+        buckets.append((name, f, int(a), int(b)))
+    sums = defaultdict(lambda: [0, 0])
+    other = [0, 0]
+    for (f, ln), (ie, sm, te, ns) in agg.items():
+        for name, bf, a, b in buckets:
+            if f == bf and a <= ln <= b:
+                sums[name][0] += ie; sums[name][1] += sm
+                break
+        else:
+            other[0] += ie; other[1] += sm
+            sums["other:" + f][0] += ie; sums["other:" + f][1] += sm
+    print("\nbuckets:")
+    for name, (ie, sm) in sorted(sums.items(), key=lambda kv: -kv[1][0]):
+        print(f"{ie/tot*100:6.2f}% inst {sm/max(tots,1)*100:6.2f}% smp  {name}")
