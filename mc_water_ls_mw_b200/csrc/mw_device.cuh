@@ -48,7 +48,7 @@ constexpr double F_HUGE  = 1.7976931348623157e308;
 // ---------------------------------------------------------------- capacities
 constexpr int LC  = 32;    // list slots per molecule held in shared memory (one lane per slot)
 constexpr int IVC = 32;    // image vectors per lattice (27 in every BASELINE config)
-constexpr int QC  = 128;   // bond records per batch: 4 evaluations x LC slots can never overflow it
+constexpr int QC  = 64;    // bond records per batch (a trial move has ~26; more than QC in-range bonds -> ERR_BOND_OVERFLOW)
 constexpr int CC  = 64;    // triplet centres per trial move: 2 lattices x LC slots
 constexpr int RB  = 64;    // random numbers buffered per refill
 constexpr int NMAX = 1024; // molecules (10 bits of a packed list entry)
@@ -59,7 +59,7 @@ constexpr uint16_t NONE16 = 0xffffu;
 enum : int {
     ERR_LIST_OVERFLOW  = 1,    // a molecule has more than LC list neighbours
     ERR_IVECT_OVERFLOW = 2,    // more than IVC image vectors (cell shrank below the cut-off)
-    ERR_BOND_OVERFLOW  = 4,    // (unused: the bond-record buffer cannot overflow)
+    ERR_BOND_OVERFLOW  = 4,    // more than QC bonds inside the cut-off in one trial move (unphysical density)
     ERR_ITEM_OVERFLOW  = 8,    // (unused)
     ERR_SELF_IMAGE     = 16,   // a molecule is its own list neighbour (cell narrower than 1.18*a*sigma)
     ERR_RNG_UNDERRUN   = 32,   // host FIFO ran dry
@@ -157,6 +157,33 @@ __device__ __forceinline__ double exp_fast(double x)
     p = fma(p, r, 1.0);
     const double s = __hiloint2double((n + 1023) << 20, 0);               // 2^n, n in [-1022, 1023]
     return (x < -708.0) ? 0.0 : p * s;
+}
+
+// log(x) for normal positive x (no special cases), ~2e-16 relative: x = m*2^e, m in [sqrt(1/2), sqrt(2)),
+// log m = 2 atanh((m-1)/(m+1))
+__device__ __forceinline__ double log_fast(double x)
+{
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;                 // m in [1,2)
+    if (hi >= 0x3ff6a09e) { hi -= 0x00100000; e += 1; }  // m >= sqrt(2) (high word): halve it
+    const double m = __hiloint2double(hi, lo);
+    const double s = (m - 1.0) * rcp_fast(m + 1.0);
+    const double z = s * s;
+    double p = 1.0 / 21.0;
+    p = fma(p, z, 1.0 / 19.0);
+    p = fma(p, z, 1.0 / 17.0);
+    p = fma(p, z, 1.0 / 15.0);
+    p = fma(p, z, 1.0 / 13.0);
+    p = fma(p, z, 1.0 / 11.0);
+    p = fma(p, z, 1.0 / 9.0);
+    p = fma(p, z, 1.0 / 7.0);
+    p = fma(p, z, 1.0 / 5.0);
+    p = fma(p, z, 1.0 / 3.0);
+    p = p * z;
+    const double lm = fma(2.0 * s, p, 2.0 * s);
+    return fma((double)e, 6.93147180559945286e-01, lm);
 }
 
 // ---------------------------------------------------------------- Philox-4x32-10
@@ -423,8 +450,11 @@ __device__ __forceinline__ double eval_bond(double* q, int r)
     const double ir = rsqrt_fast(r2);
     const double r1 = ir * r2;
     const double isr = rcp_fast(r1 - RC);
-    const double e2 = exp_fast(SIGMA * isr);
-    const double g = exp_fast(GS * isr);
+    // exp(sigma*isr) = e^5 and exp(gamma*sigma*isr) = e^6 with e = exp(0.2*sigma*isr)  (gamma = 1.2)
+    const double e1 = exp_fast((0.2 * SIGMA) * isr);
+    const double e_2 = e1 * e1, e_4 = e_2 * e_2;
+    const double e2 = e_4 * e1;
+    const double g = e_4 * e_2;
     const double s2 = SS * ir * ir;
     q[r] = tx * ir; q[QC + r] = ty * ir; q[2 * QC + r] = tz * ir; q[3 * QC + r] = g;
     return AEPS * (BIGB * (s2 * s2) - 1.0) * e2;
@@ -546,20 +576,26 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
         const uint32_t bu = bo | bn;
         const int ic = nc + __popc(bu & lt);
         nc += __popc(bu);
-        // nq <= 4*LC == QC and nc <= 2*LC == CC by construction
-        if (fo) {
+        // nc <= 2*LC == CC by construction; nq may exceed QC only at unphysical densities (flagged below)
+        if (fo && io < QC) {
             q[io] = tox; q[QC + io] = toy; q[2 * QC + io] = toz; q[3 * QC + io] = r2o;
             w.qmeta[io] = (uint32_t)(lat * 2) | ((uint32_t)j << 8);
         }
-        if (WITH_NEW && fn) {
+        if (WITH_NEW && fn && in_ < QC) {
             q[in_] = tnx; q[QC + in_] = tny; q[2 * QC + in_] = tnz; q[3 * QC + in_] = r2n;
             w.qmeta[in_] = (uint32_t)(lat * 2 + 1) | ((uint32_t)j << 8);
         }
         if (fo || fn) {
             w.cmeta[ic] = (uint32_t)lat | ((uint32_t)j << 6);
-            w.cq[ic * 2] = fo ? (uint16_t)io : NONE16;
-            w.cq[ic * 2 + 1] = fn ? (uint16_t)in_ : NONE16;
+            w.cq[ic * 2] = (fo && io < QC) ? (uint16_t)io : NONE16;
+            w.cq[ic * 2 + 1] = (fn && in_ < QC) ? (uint16_t)in_ : NONE16;
         }
+    }
+    if (nq > QC) {                                  // results of this call are invalid; the walker is flagged
+        w.sc->error |= ERR_BOND_OVERFLOW;
+        nq = QC;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { seg_start[c] = 0; seg_n[c] = 0; }
     }
     __syncwarp();
 

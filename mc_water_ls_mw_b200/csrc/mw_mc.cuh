@@ -15,7 +15,7 @@ namespace mw {
 struct McParams {
     double beta, pressure;
     double transP, volP, swP;
-    double r_pos, r_neg, a_pos, a_neg, log_r_pos, log_r_neg;
+    double r_pos, r_neg, a_pos, a_neg, log_r_pos, log_r_neg, inv_log_r_pos, inv_log_r_neg;
     double av_binwidth, log_unbiased_norm;
     double mu_min, mu_max;
     double orig_wl_factor, wl_alpha;
@@ -147,6 +147,8 @@ struct Rng {
 // ---------------------------------------------------------------- order parameter / weights
 struct EtaBin { double eta; int k; };
 
+__device__ __noinline__ int bin_exact(double arg, double lr) { return (int)(log(arg) / lr); }
+
 // mu_to_bin (mc_moves.F90:2187-2215, 1-based bin) and eta_weight (mc_moves.F90:893-964) in one
 // call.  The two sign branches of mu_to_bin share one log: for mu > 0, mu - 0.5 == |mu| - 0.5.
 // wgt is this walker's weight array (global memory, read through L2 because the same warp
@@ -164,7 +166,11 @@ __device__ __noinline__ EtaBin eta_bin(const McParams& p, const double* __restri
         const bool pos = mu > 0.0;
         const double rr = pos ? p.r_pos : p.r_neg, aa = pos ? p.a_pos : p.a_neg, lr = pos ? p.log_r_pos : p.log_r_neg;
         const double arg = 1.0 - (fabs(mu) - 0.5) * (1.0 - rr) / aa;
-        const int t = (int)(log(arg) / lr);
+        // int(log(arg)/log(r)): fast logarithm; the library log and the true division decide only
+        // when the quotient is within 1e-7 of an integer
+        const double y = log_fast(arg) * (pos ? p.inv_log_r_pos : p.inv_log_r_neg);
+        int t = (int)y;
+        if (fabs(y - rint(y)) < 1e-7 || !(arg > 0.0)) t = bin_exact(arg, lr);
         k = pos ? nb / 2 + 2 + t : nb / 2 - t;
     }
     r.k = k;

@@ -876,6 +876,7 @@ extern "C" int mwgpu_mc_init(mwgpu_ctx* c, const mwgpu_mc_params* up, int first_
     P.prob_error = (P.swP < 0.999) ? 1 : 0;
     P.r_pos = r_pos; P.r_neg = r_neg; P.a_pos = a_pos; P.a_neg = a_neg;
     P.log_r_pos = std::log(r_pos); P.log_r_neg = std::log(r_neg);
+    P.inv_log_r_pos = 1.0 / P.log_r_pos; P.inv_log_r_neg = 1.0 / P.log_r_neg;
     P.av_binwidth = av_bw; P.log_unbiased_norm = lun;
     P.mu_min = u.mu_min; P.mu_max = u.mu_max;
     P.orig_wl_factor = orig_wl_factor; P.wl_alpha = u.wl_alpha;
