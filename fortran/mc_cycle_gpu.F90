@@ -1,0 +1,132 @@
+! -*- mode: F90 -*-
+!=============================================================================!
+! Coarse GPU path for mc_moves.F90 of keb721/mc_water_ls_mw.                  !
+!                                                                             !
+! This file is a PATCH FRAGMENT, not a module: the three routines below are   !
+! added to the `contains` section of module mc_moves (they use its private    !
+! variables), and two call sites change:                                      !
+!                                                                             !
+!  (1) end of mc_init (mc_moves.F90:862, after ls_mu is first computed):      !
+!          call mc_gpu_init()                                                 !
+!  (2) mc_cycle, mc_moves.F90:212-255 (list refresh + "do imove = 1,nwater"   !
+!      loop + average_energy accumulation) are replaced by                    !
+!          call mc_gpu_cycle()                                                !
+!      and the comms_allreduce_* calls at :264-268 by                         !
+!          call mwgpu_check(mwgpu_comms_allreduce_bins(gpu_ctx),'mc_cycle')   !
+!          call mc_gpu_pull_bins()                                            !
+!  (3) mc_monitor_stats / mc_check_flatness / mc_check_chain_synchronisation  !
+!      / mc_checkpoint_write start with  call mc_gpu_pull()  so that the host  !
+!      copies of ljr, hmatrix, model_energy, counters, histogram and weight   !
+!      are current; routines that MODIFY state (monitor: step sizes + energy  !
+!      re-sync :1722-1792; flatness: histogram reset / wl_factor :1977-2106;  !
+!      chain sync :2262-2402) end with  call mc_gpu_push().                    !
+!                                                                             !
+! Everything else in mc_moves.F90 / main.f90 / io.f90 is untouched: program   !
+! entry, input decks and output formats stay as they are.                     !
+!                                                                             !
+! NOT COMPILED in this repository (no Fortran compiler in the build image).   !
+!=============================================================================!
+
+  subroutine mc_gpu_init()
+    !--------------------------------------------------------------------------!
+    ! Hands the run parameters, bin grid inputs, weights and the random stream !
+    ! to the device (replaces nothing; mirrors mc_init :504-877 on the device).!
+    !--------------------------------------------------------------------------!
+    use iso_c_binding
+    use mwgpu
+    use energy,     only : gpu_ctx
+    use comms,      only : myrank,size
+    use model,      only : ls
+    use userparams
+    implicit none
+    type(mwgpu_mc_params) :: p
+
+    p%temperature = temperature          ; p%pressure = pressure          ! internal units (io.f90:165)
+    p%npt = merge(1,0,mc_ensemble=='npt')
+    p%mc_max_trans = mc_max_trans        ; p%mc_dv_max = mc_dv_max        ! Bohr (io.f90:185-186)
+    p%mc_target_ratio = mc_target_ratio
+    p%wl_factor = orig_wl_factor         ; p%wl_swetnam = merge(1,0,wl_schedule==2)
+    p%wl_alpha = wl_alpha
+    p%eta_interp = merge(1,0,eta_interp) ; p%samplerun = merge(1,0,samplerun)
+    p%leshift = merge(1,0,leshift)       ; p%nbins = nbins
+    p%mu_min = mu_min                    ; p%mu_max = mu_max
+    p%allow_switch = merge(1,0,allow_switch) ; p%allow_vol = merge(1,0,allow_vol)
+    p%allow_trans = merge(1,0,allow_trans)
+    p%mc_trans_prob = mc_trans_prob      ; p%mc_vol_prob = mc_vol_prob
+    p%mc_switch_prob = mc_switch_prob    ; p%mc_always_switch = merge(1,0,mc_always_switch)
+    p%list_update_int = list_update_int  ; p%eq_mc_cycles = eq_mc_cycles
+    p%max_mc_cycles = max_mc_cycles      ; p%eq_adjust_mc = merge(1,0,eq_adjust_mc)
+    p%monitor_int = monitor_int          ; p%dd = merge(1,0,parallel_strategy=='dd')
+    p%window_overlap = window_overlap
+    p%input_ref_enthalpy = input_ref_enthalpy
+    p%ls = ls
+
+    ! one walker per rank, rank = myrank of size ranks (windows in dd mode, log_unbiased_norm)
+    call mwgpu_check(mwgpu_mc_init(gpu_ctx,p,int(myrank,c_int),int(max(size,1),c_int), &
+                                   weight,int(nbins,c_int),wl_factor),'mc_gpu_init')
+    ! host-side state that mc_init may have restored from a checkpoint
+    call mc_gpu_push()
+    ! random stream: the compiler's random_number is unpinned (random.f90:62-63); the device
+    ! uses Philox-4x32-10 keyed by (seed, rank); main.f90:79-81 burns 1 000 000 draws first.
+    call mwgpu_check(mwgpu_mc_set_rng_philox(gpu_ctx,20141211_c_int64_t,int(myrank,c_int32_t), &
+                                             1000000_c_int64_t),'mc_gpu_init')
+  end subroutine mc_gpu_init
+
+  subroutine mc_gpu_cycle()
+    !--------------------------------------------------------------------------!
+    ! mc_moves.F90:212-255 for one cycle on the device, then the scalars the    !
+    ! rest of mc_cycle reads.                                                   !
+    !--------------------------------------------------------------------------!
+    use iso_c_binding
+    use mwgpu
+    use energy,     only : gpu_ctx,model_energy
+    use model,      only : volume,ls
+    use userparams, only : num_lattices,mc_max_trans,mc_dv_max,wl_factor
+    implicit none
+    type(mwgpu_walker_state) :: st
+    call mwgpu_check(mwgpu_mc_run(gpu_ctx,1_c_int),'mc_gpu_cycle')
+    call mwgpu_check(mwgpu_mc_get_state(gpu_ctx,0_c_int,st),'mc_gpu_cycle')
+    model_energy(1:num_lattices) = st%model_energy(1:num_lattices)
+    volume(1:num_lattices)       = st%volume(1:num_lattices)
+    average_energy               = st%average_energy
+    ls_mu = st%ls_mu ; ls = st%ls
+    mc_accepted_rsteps  = st%accepted(1)  ; mc_accepted_vsteps  = st%accepted(2)  ; mc_accepted_swtch  = st%accepted(3)
+    mc_attempted_rsteps = st%attempted(1) ; mc_attempted_vsteps = st%attempted(2) ; mc_attempted_swtch = st%attempted(3)
+    min_dmu = st%min_dmu ; max_dmu = st%max_dmu
+    wl_factor = st%wl_factor
+    walker_in_window = (st%walker_in_window/=0)
+  end subroutine mc_gpu_cycle
+
+  subroutine mc_gpu_pull_bins()
+    use iso_c_binding
+    use mwgpu
+    use energy, only : gpu_ctx
+    implicit none
+    call mwgpu_check(mwgpu_mc_get_bins(gpu_ctx,0_c_int,weight,histogram,unbiased_hist),'mc_gpu_pull_bins')
+  end subroutine mc_gpu_pull_bins
+
+  subroutine mc_gpu_pull()
+    ! device -> host before host-side bookkeeping (monitor, flatness, chain sync, checkpoint, dcd)
+    use iso_c_binding
+    use mwgpu
+    use energy, only : gpu_ctx,energy_pull_from_device
+    implicit none
+    call energy_pull_from_device()
+    call mc_gpu_pull_bins()
+    call mwgpu_check(mwgpu_mc_get_translations(gpu_ctx,0_c_int,mc_translations),'mc_gpu_pull')
+  end subroutine mc_gpu_pull
+
+  subroutine mc_gpu_push()
+    ! host -> device after host-side bookkeeping changed the state
+    use iso_c_binding
+    use mwgpu
+    use energy,     only : gpu_ctx,energy_push_to_device
+    use model,      only : ls
+    use userparams, only : wl_factor
+    implicit none
+    call energy_push_to_device()
+    call mwgpu_check(mwgpu_energy_init(gpu_ctx),'mc_gpu_push')          ! lists, energies, ls_mu (:842-862)
+    call mwgpu_check(mwgpu_mc_set_bins(gpu_ctx,0_c_int,weight,histogram,unbiased_hist),'mc_gpu_push')
+    call mwgpu_check(mwgpu_mc_set_wl_factor(gpu_ctx,0_c_int,wl_factor,merge(1_c_int,0_c_int,wl_invt_active)),'mc_gpu_push')
+    call mwgpu_check(mwgpu_mc_set_active_lattice(gpu_ctx,0_c_int,int(ls,c_int)),'mc_gpu_push')
+  end subroutine mc_gpu_push
