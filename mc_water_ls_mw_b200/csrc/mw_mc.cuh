@@ -40,6 +40,8 @@ struct DeviceState {
     int*    niv;        // [W][2]
     uint16_t* list;     // [W][nlat][N][LC]
     uint8_t*  nn;       // [W][nlat][N]
+    double* ten;        // [W][nlat][N][TS]  per-molecule bond tensors (cache, rebuilt on demand)
+    float*  disp;       // [W][nlat][N]      path length moved since the last list build
     WalkerScalars* scal;// [W]
     double* weight;     // [W][NB]
     double* hist;       // [W][NB]
@@ -109,9 +111,9 @@ __device__ __forceinline__ void store_walker(const DeviceState& S, int wi, const
 // Per-walker stream of U[0,1) numbers (random.f90:87-102), buffered RB at a time in shared
 // memory.  mode 0: Philox (draw n = half n&1 of block n>>1); mode 1: host FIFO (draw n = fifo[n]).
 // `pos` (index of the next draw inside the buffer) is carried in a register by the caller.
-__device__ __noinline__ void rng_refill(unsigned char* smem, int N, int nlat, const DeviceState& S, const McParams& p, int wi)
+__device__ __noinline__ void rng_refill(WalkerRef ref, const DeviceState& S, const McParams& p, int wi)
 {
-    const WalkerView w = carve_walker(smem, N, nlat);
+    const WalkerView w = ref.view();
     const int lane = lane_id();
     const uint64_t base = *w.rngbase;
     __syncwarp();
@@ -128,7 +130,7 @@ __device__ __noinline__ void rng_refill(unsigned char* smem, int N, int nlat, co
 }
 
 struct Rng {
-    unsigned char* smem; int N, nlat, wi;
+    WalkerRef ref; int wi;
     const DeviceState* S; const McParams* p;
     double* buf; uint64_t* base;
     int pos;
@@ -137,7 +139,7 @@ struct Rng {
         if (pos == RB) {
             __syncwarp();
             *base = *base + RB;               // every lane stores the same value
-            rng_refill(smem, N, nlat, *S, *p, wi);
+            rng_refill(ref, *S, *p, wi);
             pos = 0;
         }
         return buf[pos++];
@@ -225,13 +227,12 @@ __device__ __forceinline__ double switch_arg(const McParams& p, const WalkerView
 }
 
 // mc_lattice_switch (mc_moves.F90:1536-1594), stand-alone form (cold paths)
-__device__ __noinline__ int lattice_switch_cold(unsigned char* smem, const DeviceState& S, const McParams& p, int wi,
-                                                int nlat, int rng_pos)
+__device__ __noinline__ int lattice_switch_cold(WalkerRef ref, const DeviceState& S, const McParams& p, int wi, int rng_pos)
 {
     const int N = S.N;
-    const WalkerView w = carve_walker(smem, N, nlat);
+    const WalkerView w = ref.view();
     WalkerScalars* sc = w.sc;
-    Rng rng{smem, N, nlat, wi, &S, &p, w.rngbuf, w.rngbase, rng_pos};
+    Rng rng{ref, wi, &S, &p, w.rngbuf, w.rngbase, rng_pos};
     const double eta = eta_bin(p, S.mubin, S.binwidth, sc, S.weight + (size_t)wi * S.NB, sc->mu).eta;
     const double arg = switch_arg(p, w, sc->E[0], sc->E[1], sc->ls == 1, eta, (double)N);
     const double compare = (arg > 0.0) ? 1.0 : exp_fast(arg);
@@ -247,10 +248,11 @@ __device__ __noinline__ int lattice_switch_cold(unsigned char* smem, const Devic
 
 // mc_moves.F90:1597-1689 for the weight-generation case (not samplerun): the histogram increment
 // is done by the caller; this updates wl_factor (Swetnam / 1-over-t variants) and the weights.
-__device__ __noinline__ void update_weights(unsigned char* smem, int N, int nlat, const McParams& p,
+__device__ __noinline__ void update_weights(WalkerRef ref, const McParams& p,
                                             const double* __restrict__ binwidth, double* wgt, const double* hist, int k)
 {
-    const WalkerView w = carve_walker(smem, N, nlat);
+    const WalkerView w = ref.view();
+    const int N = w.N;
     WalkerScalars* sc = w.sc;
     const int nb = p.nbins, lane = lane_id();
     if (p.wl_swetnam) {
@@ -307,9 +309,10 @@ __device__ __forceinline__ void rescale_pos(double& x, double& y, double& z, con
     x = xa(x, t0); y = xa(y, t1); z = xa(z, t2);
 }
 
-__device__ __noinline__ void rescale_all(unsigned char* smem, int N, int nlat, double* refpos, int lat)
+__device__ __noinline__ void rescale_all(WalkerRef ref, double* refpos, int lat)
 {
-    const WalkerView w = carve_walker(smem, N, nlat);
+    const WalkerView w = ref.view();
+    const int N = w.N;
     const int lane = lane_id();
     double rm[9], hm[9];
 #pragma unroll
@@ -328,9 +331,9 @@ __device__ __noinline__ void rescale_all(unsigned char* smem, int N, int nlat, d
 }
 
 // recip matrix of the cell in shared memory -> shared memory (uniform stores)
-__device__ __noinline__ void refresh_recip(unsigned char* smem, int N, int nlat, int lat)
+__device__ __noinline__ void refresh_recip(WalkerRef ref, int lat)
 {
-    const WalkerView w = carve_walker(smem, N, nlat);
+    const WalkerView w = ref.view();
     double hm[9], rm[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) hm[k] = w.cell[lat * 9 + k];
@@ -349,15 +352,24 @@ __device__ __forceinline__ double cell_volume(const WalkerView& w, int lat)
     return fabs(determinant3(hm));
 }
 
+// (Re)build the bond-tensor cache of every lattice from the current positions and lists.
+__device__ __noinline__ void rebuild_tensors_all(WalkerRef ref)
+{
+    const WalkerView w = ref.view();
+    for (int lat = 0; lat < w.nlat; ++lat) full_energy_warp(ref, lat, 2);
+    w.sc->tensors_valid = 1;
+    __syncwarp();
+}
+
 // mc_moves.F90:1216-1534.  Cold path (0.26 % of the moves): not inlined.  Returns the new
 // position in the random-number buffer.
 template <int NLAT>
-__device__ __noinline__ int volume_move(unsigned char* smem, const DeviceState& S, const McParams& p, int wi, int rng_pos)
+__device__ __noinline__ int volume_move(WalkerRef ref, const DeviceState& S, const McParams& p, int wi, int rng_pos)
 {
     const int N = S.N;
-    const WalkerView w = carve_walker(smem, N, NLAT);
+    const WalkerView w = ref.view();
     WalkerScalars* sc = w.sc;
-    Rng rng{smem, N, NLAT, wi, &S, &p, w.rngbuf, w.rngbase, rng_pos};
+    Rng rng{ref, wi, &S, &p, w.rngbuf, w.rngbase, rng_pos};
     const int lane = lane_id();
     const double Nd = (double)N;
     const double* wgt = S.weight + (size_t)wi * S.NB;
@@ -369,7 +381,7 @@ __device__ __noinline__ int volume_move(unsigned char* smem, const DeviceState& 
     for (int lat = 0; lat < NLAT; ++lat) {
         backupE[lat] = sc->E[lat];
         old_vol[lat] = sc->vol[lat];
-        refresh_recip(smem, N, NLAT, lat);                 // :1260-1262
+        refresh_recip(ref, lat);                           // :1260-1262
     }
     if (lane < NLAT * 9) { save[lane] = w.cell[lane]; save[18 + lane] = w.recip[lane]; }
     __syncwarp();
@@ -389,11 +401,11 @@ __device__ __noinline__ int volume_move(unsigned char* smem, const DeviceState& 
     double* refpos = S.ref + (size_t)wi * NLAT * 3 * N;
 #pragma unroll
     for (int lat = 0; lat < NLAT; ++lat) {
-        rescale_all(smem, N, NLAT, refpos, lat);           // recip = old cell's, h = new cell
+        rescale_all(ref, refpos, lat);                     // recip = old cell's, h = new cell
         sc->vol[lat] = cell_volume(w, lat);
-        refresh_recip(smem, N, NLAT, lat);
-        err |= compute_ivects_warp(smem, N, NLAT, lat);
-        newE[lat] = full_energy_warp(smem, N, NLAT, lat);
+        refresh_recip(ref, lat);
+        err |= compute_ivects_warp(ref, lat);
+        newE[lat] = full_energy_warp(ref, lat, 3);         // energy + bond tensors of the trial cell
         sc->E[lat] = newE[lat];
     }
     double old_eta = 0.0, new_eta = 0.0, old_mu = 0.0;
@@ -419,6 +431,16 @@ __device__ __noinline__ int volume_move(unsigned char* smem, const DeviceState& 
             if (dmu > sc->max_dmu) sc->max_dmu = dmu;
         }
         w.lv[0] = nlv12; w.lv[1] = nlv21;
+        // every separation was multiplied by at least 1 - |dh| * sqrt(2) * ||h_old^-1||_F : shrink the
+        // bound on the distance of unlisted pairs accordingly (guard of the tensor path)
+#pragma unroll
+        for (int lat = 0; lat < NLAT; ++lat) {
+            double f2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) f2 += save[18 + lat * 9 + k] * save[18 + lat * 9 + k];
+            const float eps = (float)(fabs(dh) * 1.4143 * sqrt(f2) * (0.5 * INV_PI)) * 1.001f;
+            sc->rn_eff[lat] = sc->rn_eff[lat] * fmaxf(0.f, 1.f - eps);
+        }
     } else {
         // :1434-1528: V,h <- old; rescale with recip(NEW) and h(OLD); recip <- old; ivects; E <- backup
         __syncwarp();
@@ -427,15 +449,15 @@ __device__ __noinline__ int volume_move(unsigned char* smem, const DeviceState& 
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {
             sc->vol[lat] = old_vol[lat];
-            rescale_all(smem, N, NLAT, refpos, lat);
+            rescale_all(ref, refpos, lat);
         }
         if (lane < NLAT * 9) w.recip[lane] = save[18 + lane];
         __syncwarp();
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {
-            err |= compute_ivects_warp(smem, N, NLAT, lat);
+            err |= compute_ivects_warp(ref, lat);
             sc->E[lat] = backupE[lat];
-            compute_bond_masks_warp(smem, N, NLAT, lat);   // positions moved by rounding; keep masks fresh
+            full_energy_warp(ref, lat, 2);                 // bond tensors of the restored positions
         }
         if (NLAT == 2) sc->mu = mu_paren(p, sc, Nd, w.lv[0]);
     }
@@ -443,35 +465,56 @@ __device__ __noinline__ int volume_move(unsigned char* smem, const DeviceState& 
     return rng.pos;
 }
 
-// commit of an accepted translation: new position, own bond mask, and the reverse bits of the
-// bonds that formed / broke (rare)
+// commit of an accepted translation: new position, and the bond-tensor cache follows the move
 template <int NLAT>
 __device__ __forceinline__ void commit_translation(const WalkerView& w, int imol, const double (*pnew)[3],
-                                                   const uint32_t* mo, const uint32_t* mn)
+                                                   const float* tlen, const LocalCtx& cx)
 {
     const int N = w.N, lane = lane_id();
+    WalkerScalars* sc = w.sc;
     __syncwarp();
 #pragma unroll
     for (int lat = 0; lat < NLAT; ++lat) {
         double* P = w.pos + lat * 3 * N;
         if (lane < 3) P[lane * N + imol] = (lane == 0) ? pnew[lat][0] : (lane == 1) ? pnew[lat][1] : pnew[lat][2];
-        uint32_t changed = mo[lat] ^ mn[lat];
-        if (lane == 0) w.bmask[lat * N + imol] = mn[lat];
-        const int nv = w.niv[lat];
-        while (changed) {
-            const int s = __ffs(changed) - 1; changed &= changed - 1;
-            const uint32_t e = w.list[((size_t)lat * N + imol) * LC + s];
-            const int j = e & 1023, img = e >> 10;
-            const uint32_t target = ((uint32_t)inverse_image(img, nv) << 10) | (uint32_t)imol;
-            const int nnj = w.nn[lat * N + j];
-            const uint32_t e2 = (lane < nnj) ? w.list[((size_t)lat * N + j) * LC + lane] : 0xffffffffu;
-            const uint32_t hit = __ballot_sync(FULL, e2 == target);
-            if (hit && lane == 0) {
-                const int s2 = __ffs(hit) - 1;
-                const uint32_t bit = (mn[lat] >> s) & 1u;
-                w.bmask[lat * N + j] = (w.bmask[lat * N + j] & ~(1u << s2)) | (bit << s2);
+        const float d = cx.dispi[lat] + tlen[lat];
+        if (lane == 0) __stcg(w.gdisp + lat * N + imol, d);
+        sc->dmax[lat] = fmaxf(sc->dmax[lat], d);
+    }
+    __syncwarp();
+    if (!sc->tensors_valid) return;
+    {
+        const double* q = w.q;
+        // tensor of imol at its new position
+        if (lane < NLAT * TS) {
+            const int lat = lane / TS, comp = lane - lat * TS;
+            __stcg(w.gten + ((size_t)lat * N + imol) * TS + comp, w.ti[(lat * 2 + 1) * TS + comp]);
+        }
+        // neighbours (lanes = list slots of imol): T_j loses the old bonds to imol and gains the new ones;
+        // the lowest slot of a group of images of one molecule applies the whole group's change
+#pragma unroll
+        for (int lat = 0; lat < NLAT; ++lat) {
+            const uint32_t bo = cx.mo[lat], bn = cx.mn[lat], grp = cx.grp[lat];
+            if ((((bo | bn) >> lane) & 1u) && (int)(__ffs(grp) - 1) == lane) {
+                const int j = w.list[((size_t)lat * N + imol) * LC + lane] & 1023;
+                double* gp = w.gten + ((size_t)lat * N + j) * TS;
+                Ten T;
+                T.load(gp);
+                uint32_t m = grp;
+                while (m) {
+                    const int s2 = __ffs(m) - 1; m &= m - 1;
+                    const uint32_t below = (1u << s2) - 1u;
+                    if ((bo >> s2) & 1u) {
+                        const int c = cx.seg_start[lat * 2] + __popc(bo & below);
+                        T.add(-1.0, -q[c], -q[QC + c], -q[2 * QC + c], q[3 * QC + c]);
+                    }
+                    if ((bn >> s2) & 1u) {
+                        const int c = cx.seg_start[lat * 2 + 1] + __popc(bn & below);
+                        T.add(1.0, -q[c], -q[QC + c], -q[2 * QC + c], q[3 * QC + c]);
+                    }
+                }
+                T.store(gp);
             }
-            __syncwarp();
         }
     }
     __syncwarp();
@@ -489,7 +532,8 @@ __global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceSta
     if (wi >= S.W) return;
     const int lane = lane_id();
     const int N = S.N;
-    const WalkerView w = carve_walker(smem, N, NLAT);
+    const WalkerRef ref{smem, S.ten + (size_t)wi * NLAT * N * TS, S.disp + (size_t)wi * NLAT * N, N, NLAT};
+    const WalkerView w = ref.view();
     load_walker(S, wi, w);
     WalkerScalars* sc = w.sc;
     const double Nd = (double)N;
@@ -499,15 +543,14 @@ __global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceSta
     int err = 0;
     if (p.prob_error) err |= ERR_PROB;
 
-#pragma unroll
-    for (int lat = 0; lat < NLAT; ++lat) compute_bond_masks_warp(smem, N, NLAT, lat);
+    if (!sc->tensors_valid) rebuild_tensors_all(ref);
 
-    Rng rng{smem, N, NLAT, wi, &S, &p, w.rngbuf, w.rngbase, 0};
+    Rng rng{ref, wi, &S, &p, w.rngbuf, w.rngbase, 0};
     {
         const uint64_t idx = sc->rng_index;
         *w.rngbase = idx & ~(uint64_t)1;
         rng.pos = (int)(idx & 1);
-        rng_refill(smem, N, NLAT, S, p, wi);
+        rng_refill(ref, S, p, wi);
     }
     if (NLAT == 2) { w.lv[0] = log(sc->vol[0] / sc->vol[1]); w.lv[1] = log(sc->vol[1] / sc->vol[0]); }
 
@@ -522,9 +565,10 @@ __global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceSta
         if (cycle % p.list_update_int == 0) {                  // :218-222
 #pragma unroll
             for (int lat = 0; lat < NLAT; ++lat) {
-                err |= compute_neighbours_warp(smem, N, NLAT, lat);
-                compute_bond_masks_warp(smem, N, NLAT, lat);
+                err |= compute_neighbours_warp(ref, lat);
+                reset_guard(w, lat);
             }
+            rebuild_tensors_all(ref);
         }
         const bool dd_eq = p.dd && (cycle < p.eq_mc_cycles);
         const bool bins_on = !(cycle < p.eq_mc_cycles);        // mc_update_wl_bins: :1615
@@ -568,16 +612,19 @@ __global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceSta
                 tv[0][0] = one ? x : bx; tv[0][1] = one ? y : by; tv[0][2] = one ? z : bz;
                 tv[1][0] = one ? bx : x; tv[1][1] = one ? by : y; tv[1][2] = one ? bz : z;
                 double pnew[2][3];
+                float tlen[2] = {0.f, 0.f};                    // displacement lengths, rounded up (guard)
 #pragma unroll
                 for (int lat = 0; lat < NLAT; ++lat) {
                     const double* P = w.pos + lat * 3 * N;
                     pnew[lat][0] = xa(P[imol], tv[lat][0]);
                     pnew[lat][1] = xa(P[N + imol], tv[lat][1]);
                     pnew[lat][2] = xa(P[2 * N + imol], tv[lat][2]);
+                    const float fx = (float)tv[lat][0], fy = (float)tv[lat][1], fz = (float)tv[lat][2];
+                    tlen[lat] = sqrtf(fx * fx + fy * fy + fz * fz) * 1.0001f;
                 }
                 double eo[2] = {0.0, 0.0}, en[2] = {0.0, 0.0};
-                uint32_t mo[2] = {0, 0}, mn[2] = {0, 0};
-                local_energies_warp<NLAT, true>(w, imol, pnew, eo, en, mo, mn);
+                LocalCtx cx;
+                local_energies_warp<NLAT, true>(ref, w, imol, pnew, tlen, eo, en, cx);
 
                 // model_energy bookkeeping exactly as :1013-1016, :1087-1090
                 const double Eb0 = sc->E[0], Eb1 = sc->E[1];
@@ -628,7 +675,7 @@ __global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceSta
                     if (dmu > sc->max_dmu) sc->max_dmu = dmu;
                     sc->E[0] = Ea0;
                     if (NLAT == 2) { sc->E[1] = Ea1; sc->mu = mu_acc; }
-                    commit_translation<NLAT>(w, imol, pnew, mo, mn);
+                    commit_translation<NLAT>(w, imol, pnew, tlen, cx);
                 } else {
                     // reject: the reference restores by (x+t)-t, not by copy (mc_moves.F90:1186)
                     __syncwarp();
@@ -652,7 +699,7 @@ __global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceSta
                         const double uf = __shfl_sync(FULL, ex, accepted ? 3 : 4);
                         if (lane == 0) atomicAdd(uhist + kb - 1, c * uf);
                     } else {
-                        update_weights(smem, N, NLAT, p, S.binwidth, wgt, hist, kb);
+                        update_weights(ref, p, S.binwidth, wgt, hist, kb);
                     }
                 }
                 // ====================== mc_lattice_switch (mc_moves.F90:1536-1594) ======================
@@ -667,13 +714,13 @@ __global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceSta
                     sc->att_s += 1;
                 } else if (do_switch) {
                     // weights may have moved in update_weights: the reference looks eta up again
-                    rng.pos = lattice_switch_cold(smem, S, p, wi, NLAT, rng.pos);
+                    rng.pos = lattice_switch_cold(ref, S, p, wi, rng.pos);
                 }
                 continue;
             }
             // ---------------- rare move types ----------------
             if (xi < p.volP) {
-                rng.pos = volume_move<NLAT>(smem, S, p, wi, rng.pos);
+                rng.pos = volume_move<NLAT>(ref, S, p, wi, rng.pos);
                 const EtaBin eb = eta_bin(p, S.mubin, S.binwidth, sc, wgt, sc->mu);
                 if (bins_on && eb.k >= 1 && eb.k <= p.nbins) {
                     const double c = p.av_binwidth / __ldg(S.binwidth + eb.k - 1);
@@ -681,14 +728,14 @@ __global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceSta
                     if (p.samplerun) {
                         if (lane == 0) atomicAdd(uhist + eb.k - 1, c * exp(eb.eta - p.log_unbiased_norm));
                     } else {
-                        update_weights(smem, N, NLAT, p, S.binwidth, wgt, hist, eb.k);
+                        update_weights(ref, p, S.binwidth, wgt, hist, eb.k);
                     }
                 }
                 sc->att_v += 1;
             } else if (xi < p.swP) {
-                if (NLAT == 2 && !dd_eq) rng.pos = lattice_switch_cold(smem, S, p, wi, NLAT, rng.pos);
+                if (NLAT == 2 && !dd_eq) rng.pos = lattice_switch_cold(ref, S, p, wi, rng.pos);
             }
-            if (do_switch) rng.pos = lattice_switch_cold(smem, S, p, wi, NLAT, rng.pos);
+            if (do_switch) rng.pos = lattice_switch_cold(ref, S, p, wi, rng.pos);
         }
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {                 // :253-255

@@ -118,6 +118,8 @@ extern "C" int mwgpu_create(int nwater, int nlat, int nwalkers, int device, mwgp
     rc |= dalloc(&S.niv, W * 2);
     rc |= dalloc(&S.list, W * L * N * LC);
     rc |= dalloc(&S.nn, W * L * N);
+    rc |= dalloc(&S.ten, W * L * N * TS);
+    rc |= dalloc(&S.disp, W * L * N);
     rc |= dalloc(&S.scal, W);
     rc |= dalloc(&S.transcount, W * N);
     c->stage_doubles = W * L * (2 * 3 * N + 9);
@@ -145,7 +147,7 @@ extern "C" void mwgpu_destroy(mwgpu_ctx* c)
     cudaSetDevice(c->device);
     nccl_destroy(c);
     DeviceState& S = c->S;
-    void* ptrs[] = {S.pos, S.ref, S.cell, S.recip, S.refcell, S.iv, S.niv, S.list, S.nn, S.scal,
+    void* ptrs[] = {S.pos, S.ref, S.cell, S.recip, S.refcell, S.iv, S.niv, S.list, S.nn, S.ten, S.disp, S.scal,
                     S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.transcount, S.mubin,
                     S.binwidth, c->stage, c->out, c->iout, c->delta, c->fifo};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -243,6 +245,7 @@ __global__ void k_unpack(DeviceState S, const double* __restrict__ ljr, const do
         const double v = hm[(bcast ? 0 : (size_t)w * L * 9) + rem];
         S.cell[(size_t)(w0 + w) * L * 9 + rem] = v;
         S.refcell[(size_t)(w0 + w) * L * 9 + rem] = v;
+        if (rem == 0) S.scal[w0 + w].tensors_valid = 0;      // positions changed under the bond-tensor cache
     }
 }
 
@@ -359,7 +362,8 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
     const int wi = a.w0 + blockIdx.x;
     if (wi >= S.W) return;
     const int lane = lane_id(), N = S.N;
-    const WalkerView w = carve_walker(smem, N, NLAT);
+    const WalkerRef ref{smem, S.ten + (size_t)wi * NLAT * N * TS, S.disp + (size_t)wi * NLAT * N, N, NLAT};
+    const WalkerView w = ref.view();
     load_walker(S, wi, w);
     WalkerScalars* sc = w.sc;
     int err = 0;
@@ -370,14 +374,16 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {
             sc->vol[lat] = cell_volume(w, lat);                         // molint.F90:125
-            refresh_recip(smem, N, NLAT, lat);                          // init.f90:90
+            refresh_recip(ref, lat);                                    // init.f90:90
         }
         sc->error = 0;
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {
-            err |= compute_neighbours_warp(smem, N, NLAT, lat);         // includes compute_ivects
-            sc->E[lat] = full_energy_warp(smem, N, NLAT, lat);
+            err |= compute_neighbours_warp(ref, lat);                   // includes compute_ivects
+            reset_guard(w, lat);
+            sc->E[lat] = full_energy_warp(ref, lat, 3);
         }
+        sc->tensors_valid = 1;
         if (NLAT == 2 && a.refresh_mu) {      // mc_moves.F90:857-862 (left-to-right association)
             double mu = sc->E[0] + a.pressure * sc->vol[0] - sc->E[1] - a.pressure * sc->vol[1];
             if (a.leshift) mu = mu - sc->refH[0] + sc->refH[1];
@@ -387,33 +393,34 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
         break;
     }
     case OP_IVECTS:
-        err |= compute_ivects_warp(smem, N, NLAT, a.lat);
+        err |= compute_ivects_warp(ref, a.lat);
+        sc->tensors_valid = 0;
         break;
     case OP_NEIGHBOURS:
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat)
-            if (a.lat < 0 || a.lat == lat) err |= compute_neighbours_warp(smem, N, NLAT, lat);
+            if (a.lat < 0 || a.lat == lat) { err |= compute_neighbours_warp(ref, lat); reset_guard(w, lat); }
+        sc->tensors_valid = 0;
         store_lists = true;
         break;
     case OP_MODEL_ENERGY:
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat)
             if (a.lat < 0 || a.lat == lat) {
-                const double e = full_energy_warp(smem, N, NLAT, lat);
+                const double e = full_energy_warp(ref, lat, 1);
                 sc->E[lat] = e;
                 if (a.out && lane == 0) a.out[(size_t)(wi - a.w0) * NLAT + lat] = e;
             }
         break;
     case OP_LOCAL_ONE:
     case OP_LOCAL_ALL: {
-#pragma unroll
-        for (int lat = 0; lat < NLAT; ++lat) compute_bond_masks_warp(smem, N, NLAT, lat);
+        if (!sc->tensors_valid) rebuild_tensors_all(ref);
         const int i0 = (a.op == OP_LOCAL_ONE) ? a.imol : 0;
         const int i1 = (a.op == OP_LOCAL_ONE) ? a.imol + 1 : N;
         for (int i = i0; i < i1; ++i) {
             double eo[2] = {0, 0}, en[2] = {0, 0};
-            uint32_t mo[2], mn[2];
-            local_energies_warp<NLAT, false>(w, i, nullptr, eo, en, mo, mn);
+            LocalCtx cx;
+            local_energies_warp<NLAT, false>(ref, w, i, nullptr, nullptr, eo, en, cx);
             if (lane == 0) a.out[i - i0] = (a.lat == 0) ? eo[0] : eo[1];
         }
         break;
@@ -427,7 +434,9 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
             sc->dv_max = fmax(xd(xm(sc->dv_max, avr), a.target_ratio), 0.0001);
         }
 #pragma unroll
-        for (int lat = 0; lat < NLAT; ++lat) sc->E[lat] = full_energy_warp(smem, N, NLAT, lat);   // :1786-1792
+        for (int lat = 0; lat < NLAT; ++lat) sc->E[lat] = full_energy_warp(ref, lat, 3);   // :1786-1792
+        sc->tensors_valid = 1;
+        sc->fast_moves = 0; sc->slow_moves[0] = sc->slow_moves[1] = sc->slow_moves[2] = sc->slow_moves[3] = 0;
         sc->acc_r = 0; sc->acc_v = 0; sc->acc_s = 0; sc->att_r = 0; sc->att_v = 0; sc->att_s = 0; // :1797-1810
         for (int i = lane; i < N; i += 32) S.transcount[(size_t)wi * N + i] = 0;
         sc->avgE[0] = 0.0; sc->avgE[1] = 0.0;
@@ -437,13 +446,13 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
     case OP_CHAIN_SYNC: {
         // mc_moves.F90:2217-2416 (two lattices only)
         if (NLAT == 2) {
-            sc->E[0] = full_energy_warp(smem, N, NLAT, 0);
-            sc->E[1] = full_energy_warp(smem, N, NLAT, 1);
+            sc->E[0] = full_energy_warp(ref, 0, 1);
+            sc->E[1] = full_energy_warp(ref, 1, 1);
             const double* rh = S.refcell + (size_t)wi * NLAT * 9;
             if (lane < 9) w.cell[9 + lane] = xa(rh[9 + lane], xs(w.cell[lane], rh[lane]));     // :2262,2277
             __syncwarp();
-            refresh_recip(smem, N, NLAT, 0);
-            refresh_recip(smem, N, NLAT, 1);
+            refresh_recip(ref, 0);
+            refresh_recip(ref, 1);
             const double* R = S.ref + (size_t)wi * NLAT * 3 * N;
             for (int i = lane; i < N; i += 32) {
                 double sv[2][3], rsv[2][3];
@@ -479,10 +488,13 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
 #pragma unroll
             for (int lat = 0; lat < 2; ++lat) {
                 sc->vol[lat] = cell_volume(w, lat);
-                err |= compute_ivects_warp(smem, N, NLAT, lat);
+                err |= compute_ivects_warp(ref, lat);
             }
-            sc->E[0] = full_energy_warp(smem, N, NLAT, 0);
-            sc->E[1] = full_energy_warp(smem, N, NLAT, 1);
+            sc->E[0] = full_energy_warp(ref, 0, 3);
+            sc->E[1] = full_energy_warp(ref, 1, 3);
+            sc->tensors_valid = 1;
+            // lattice 2 was moved by an unbounded amount relative to its lists: no tensor path until the next list build
+            sc->rn_eff[1] = 0.f;
             // left-to-right association (:2400-2402)
             double mu = sc->E[0] + a.pressure * sc->vol[0] - sc->E[1] - a.pressure * sc->vol[1];
             if (a.leshift) mu = mu - sc->refH[0] + sc->refH[1];
@@ -653,7 +665,8 @@ __global__ void __launch_bounds__(32) k_model_energy_all(const __grid_constant__
     const int wi = unit / S.nlat, lat = unit % S.nlat;
     const int lane = lane_id(), N = S.N;
     // a one-lattice view: lattice `lat` of the walker is staged as lattice 0
-    const WalkerView w = carve_walker(smem, N, 1);
+    const WalkerRef ref{smem, nullptr, nullptr, N, 1};
+    const WalkerView w = ref.view();
     const double* gp = S.pos + ((size_t)wi * S.nlat + lat) * 3 * N;
     for (int t = lane; t < 3 * N; t += 32) w.pos[t] = gp[t];
     const double* gi = S.iv + ((size_t)wi * S.nlat + lat) * 3 * IVC;
@@ -664,7 +677,7 @@ __global__ void __launch_bounds__(32) k_model_energy_all(const __grid_constant__
     const uint8_t* gn = S.nn + ((size_t)wi * S.nlat + lat) * N;
     for (int t = lane; t < N; t += 32) w.nn[t] = gn[t];
     __syncwarp();
-    const double e = full_energy_warp(smem, N, 1, 0);
+    const double e = full_energy_warp(ref, 0, 1);
     if (lane == 0) {
         S.scal[wi].E[lat] = e;
         if (out) out[unit] = e;
@@ -847,7 +860,8 @@ extern "C" int mwgpu_mc_init(mwgpu_ctx* c, const mwgpu_mc_params* up, int first_
         sc.rng_index = 0; sc.cycle = 0;
         sc.acc_r = sc.acc_v = sc.acc_s = sc.att_r = sc.att_v = sc.att_s = 0;
         sc.in_window = u.dd ? 0 : 1;
-        sc.wl_invt_active = 0; sc.wmin_zero = 0; sc.error = 0;
+        sc.wl_invt_active = 0; sc.wmin_zero = 0; sc.error = 0; sc.fast_moves = 0;
+        sc.slow_moves[0] = sc.slow_moves[1] = sc.slow_moves[2] = sc.slow_moves[3] = 0;
         for (int i = 0; i < nb; ++i) {
             hb[(size_t)w * nb + i] = weight[i];                            // eta_last_sync = weight (:776)
             double v = weight[i];
@@ -1056,6 +1070,29 @@ extern "C" int mwgpu_mc_set_active_lattice(mwgpu_ctx* c, int walker, int ls)
     CUDA_TRY(cudaMemcpy(h.data(), c->S.scal, sizeof(WalkerScalars) * c->W, cudaMemcpyDeviceToHost));
     for (int w = 0; w < c->W; ++w) if (walker < 0 || walker == w) h[w].ls = ls;
     CUDA_TRY(cudaMemcpy(c->S.scal, h.data(), sizeof(WalkerScalars) * c->W, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int mwgpu_mc_set_exact_enumeration(mwgpu_ctx* c, int walker, int exact)
+{
+    if (int rc = check_ctx(c, walker, true)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<WalkerScalars> h(c->W);
+    CUDA_TRY(cudaMemcpy(h.data(), c->S.scal, sizeof(WalkerScalars) * c->W, cudaMemcpyDeviceToHost));
+    for (int w = 0; w < c->W; ++w) if (walker < 0 || walker == w) h[w].force_exact = exact ? 1 : 0;
+    CUDA_TRY(cudaMemcpy(c->S.scal, h.data(), sizeof(WalkerScalars) * c->W, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int mwgpu_mc_get_path_counts(mwgpu_ctx* c, int walker, int* counts)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    if (!counts) return fail("mwgpu_mc_get_path_counts: NULL");
+    WalkerScalars s;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(&s, c->S.scal + walker, sizeof(s), cudaMemcpyDeviceToHost));
+    counts[0] = s.fast_moves;
+    for (int k = 0; k < 4; ++k) counts[1 + k] = s.slow_moves[k];
     return 0;
 }
 
