@@ -268,6 +268,8 @@ struct WalkerView {
     double*   recip;   // [nlat][9]
     double*   q;       // [4][QC] scratch: tx,ty,tz,r2 -> ux,uy,uz,g
     double*   ti;      // [4][TS] bond tensors of the moved molecule, one per evaluation
+    double*   pn;      // [2][3]  trial position of the moved molecule
+    double*   tv;      // [2][3]  trial displacement
     double*   save;    // [36]    old cell + recip during a volume move
     double*   rngbuf;  // [RB]    buffered U[0,1) numbers
     double*   lv;      // [2]     log(V1/V2), log(V2/V1)
@@ -275,11 +277,12 @@ struct WalkerView {
     uint64_t* rngbase; // draw index of rngbuf[0]
     uint32_t* qmeta;   // [QC]   evaluation | slot<<2 | j<<8   (full energy: end of the molecule's segment)
     uint32_t* qgrp;    // [QC]   slots of imol's list that are bonded images of the same molecule j (incl. own)
+    uint32_t* cxs;     // [16]   per-move uniforms: see CX_* below
     int*      niv;     // [2]
     uint16_t* seg;     // [MC+2] record offsets of the molecules of a full-energy chunk
-    uint16_t* list;    // [nlat][N][LC] packed entries img<<10 | j   (0-based)
     uint8_t*  nn;      // [nlat][N]
-    // global memory of this walker (L2-resident)
+    // global memory of this walker (L2-resident; read with ld.cg: another SM may have written it)
+    uint16_t* list;    // [nlat][N][LC] packed Verlet entries img<<10 | j   (0-based)
     double*   gten;    // [nlat][N][TS] per-molecule bond tensors
     float*    gdisp;   // [nlat][N] path length moved since the last list build
 };
@@ -287,25 +290,24 @@ struct WalkerView {
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t smem_doubles(int N, int nlat)
 {
-    return (size_t)nlat * 3 * N + (size_t)nlat * 3 * IVC + (size_t)nlat * 18 + 4 * QC + 4 * TS + 36 + RB + 2;
+    return (size_t)nlat * 3 * N + (size_t)nlat * 3 * IVC + (size_t)nlat * 18 + 4 * QC + 4 * TS + 12 + 36 + RB + 2;
 }
 
-// Layout (every block 16-byte aligned): doubles | scalars | list | 32-bit words | 16-bit words | bytes
+// Layout (every block 16-byte aligned): doubles | scalars | 32-bit words | 16-bit words | bytes
 __host__ __device__ inline size_t walker_smem_bytes(int N, int nlat)
 {
     size_t b = 0;
     b += align16(sizeof(double) * smem_doubles(N, nlat));
     b += align16(sizeof(WalkerScalars) + sizeof(uint64_t));
-    b += align16(sizeof(uint16_t) * (size_t)nlat * N * LC);                       // list
-    b += align16(sizeof(uint32_t) * (2 * QC + 2));                                // qmeta, qgrp, niv
+    b += align16(sizeof(uint32_t) * (2 * QC + 16 + 2));                           // qmeta, qgrp, cxs, niv
     b += align16(sizeof(uint16_t) * (MC + 2));                                    // seg
     b += align16((size_t)nlat * N);                                               // nn
     return b;
 }
 
-__device__ __forceinline__ WalkerView carve_walker(unsigned char* base, int N, int nlat, double* gten, float* gdisp)
+__device__ __forceinline__ WalkerView carve_walker(unsigned char* base, int N, int nlat, uint16_t* glist, double* gten, float* gdisp)
 {
-    WalkerView w; w.N = N; w.nlat = nlat; w.gten = gten; w.gdisp = gdisp;
+    WalkerView w; w.N = N; w.nlat = nlat; w.list = glist; w.gten = gten; w.gdisp = gdisp;
     unsigned char* p = base;
     w.pos    = (double*)p;
     w.iv     = w.pos + (size_t)nlat * 3 * N;
@@ -313,19 +315,20 @@ __device__ __forceinline__ WalkerView carve_walker(unsigned char* base, int N, i
     w.recip  = w.cell + (size_t)nlat * 9;
     w.q      = w.recip + (size_t)nlat * 9;
     w.ti     = w.q + 4 * QC;
-    w.save   = w.ti + 4 * TS;
+    w.pn     = w.ti + 4 * TS;
+    w.tv     = w.pn + 6;
+    w.save   = w.tv + 6;
     w.rngbuf = w.save + 36;
     w.lv     = w.rngbuf + RB;
     p += align16(sizeof(double) * smem_doubles(N, nlat));
     w.sc      = (WalkerScalars*)p;
     w.rngbase = (uint64_t*)(p + sizeof(WalkerScalars));
     p += align16(sizeof(WalkerScalars) + sizeof(uint64_t));
-    w.list  = (uint16_t*)p;
-    p += align16(sizeof(uint16_t) * (size_t)nlat * N * LC);
     w.qmeta = (uint32_t*)p;
     w.qgrp  = w.qmeta + QC;
-    w.niv   = (int*)(w.qgrp + QC);
-    p += align16(sizeof(uint32_t) * (2 * QC + 2));
+    w.cxs   = w.qgrp + QC;
+    w.niv   = (int*)(w.cxs + 16);
+    p += align16(sizeof(uint32_t) * (2 * QC + 16 + 2));
     w.seg   = (uint16_t*)p;
     p += align16(sizeof(uint16_t) * (MC + 2));
     w.nn    = (uint8_t*)p;
@@ -334,8 +337,8 @@ __device__ __forceinline__ WalkerView carve_walker(unsigned char* base, int N, i
 
 // What the __noinline__ routines need to rebuild a WalkerView (passed in registers)
 struct WalkerRef {
-    unsigned char* smem; double* gten; float* gdisp; int N, nlat;
-    __device__ __forceinline__ WalkerView view() const { return carve_walker(smem, N, nlat, gten, gdisp); }
+    unsigned char* smem; uint16_t* glist; double* gten; float* gdisp; int N, nlat;
+    __device__ __forceinline__ WalkerView view() const { return carve_walker(smem, N, nlat, glist, gten, gdisp); }
 };
 
 // ---------------------------------------------------------------- image vectors
@@ -524,24 +527,25 @@ __device__ __forceinline__ double ten_term(int comp, double ux, double uy, doubl
 }
 
 // The same for lanes that each own one component (comp is lane-dependent): branch-free operand
-// selection by shared-memory row.  sel = ia | ib<<2 | mode<<4; rows 0..2 = ux,uy,uz, 3 = the constant 1;
-// mode 0: g*a*b, 1: [g > GSAFE], 2: 0.
-__device__ __forceinline__ int ten_sel(int comp)
+// selection by shared-memory row.  TenSel: rows of the two factors (offsets into q; the constant 1
+// is encoded as one = true) and the kind of component.
+struct TenSel { int offa, offb; bool onea, oneb; int mode; };      // mode 0: g*a*b, 1: [g > GSAFE], 2: 0
+__device__ __forceinline__ TenSel ten_sel(int comp)
 {
     const int ia = (comp < 3 || comp == 6) ? 0 : (comp == 3 || comp == 4 || comp == 7) ? 1 : (comp == 5 || comp == 8) ? 2 : 3;
     const int ib = (comp == 0) ? 0 : (comp == 1 || comp == 3) ? 1 : (comp == 2 || comp == 4 || comp == 5) ? 2 : 3;
-    const int mode = (comp < 10) ? 0 : (comp == 10) ? 1 : 2;
-    return ia | (ib << 2) | (mode << 4);
+    TenSel t;
+    t.onea = ia == 3; t.oneb = ib == 3;
+    t.offa = t.onea ? 0 : ia * QC; t.offb = t.oneb ? 0 : ib * QC;
+    t.mode = (comp < 10) ? 0 : (comp == 10) ? 1 : 2;
+    return t;
 }
-__device__ __forceinline__ double ten_term_sel(int sel, const double* q, int c)
+__device__ __forceinline__ double ten_term_sel(const TenSel& t, const double* q, int c)
 {
-    const int ia = sel & 3, ib = (sel >> 2) & 3;
     const double g = q[3 * QC + c];
-    const double a = q[(ia % 3) * QC + c];                                // (any valid row when ia == 3)
-    const double b = q[(ib % 3) * QC + c];
-    const double av = (ia == 3) ? 1.0 : a, bv = (ib == 3) ? 1.0 : b;
-    const double v = g * av * bv;
-    return (sel < 16) ? v : ((sel < 32 && g > GSAFE) ? 1.0 : 0.0);
+    const double a = q[t.offa + c], b = q[t.offb + c];
+    const double v = g * (t.onea ? 1.0 : a) * (t.oneb ? 1.0 : b);
+    return (t.mode == 0) ? v : ((t.mode == 1 && g > GSAFE) ? 1.0 : 0.0);
 }
 
 struct Ten {
@@ -602,13 +606,15 @@ struct Ten {
 // of imol or of the neighbour shorter than RSAFE -- is re-done by the reference's enumeration.
 // EXACT path: enumeration for every centre; used when forced (testing) or when the
 // displacement guard cannot vouch for molecules missing from the stale Verlet lists.
-struct LocalCtx {
-    uint32_t mo[2], mn[2];     // in-range slot masks of imol, old / new position
-    uint32_t grp[2];           // per lane (= slot): bonded slots that are images of the same molecule (incl. own)
-    int nq;
-    int seg_start[4], seg_n[4];
-    bool fast;
-    float dispi[2];            // path length of imol since the last list build
+// per-move uniforms kept in shared memory (w.cxs): every lane stores the same value
+enum : int {
+    CX_MO = 0,      // [2] in-range slot masks of imol, old position
+    CX_MN = 2,      // [2] ... trial position
+    CX_SEG = 4,     // [4] first bond record of evaluation ev = lat*2 + new
+    CX_NSEG = 8,    // [4] number of bond records of evaluation ev
+    CX_NQ = 12,
+    CX_FAST = 13,   // tensor path (else: enumeration for every centre)
+    CX_DISP = 14,   // [2] float bits: path length of imol since the last list build
 };
 
 struct Acc4 { double a0, a1, a2, a3; };
@@ -658,7 +664,7 @@ __device__ __noinline__ double jcentre_enum_warp(WalkerRef ref, int imol, int re
     const int nnj = w.nn[lat * N + j];
     double v = 0.0;
     if (lane < nnj) {
-        const uint32_t e2 = w.list[((size_t)lat * N + j) * LC + lane];
+        const uint32_t e2 = __ldcg(w.list + ((size_t)lat * N + j) * LC + lane);
         const int k = e2 & 1023, img = e2 >> 10;
         if (k != imol) {
             const double tx = (P[k] + V[img]) - P[j];
@@ -676,55 +682,55 @@ __device__ __noinline__ double jcentre_enum_warp(WalkerRef ref, int imol, int re
     return v;
 }
 
+// Inputs in shared memory: w.pn (trial position per lattice, WITH_NEW), w.cxs[CX_DISP..] is written here.
+// tlen0/tlen1: length of the trial displacement per lattice (guard).  Results: eo/en (uniform).
 template <int NLAT, bool WITH_NEW>
-__device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerView& w, int imol, const double (*pnew)[3],
-                                                    const float* tlen, double* eo, double* en, LocalCtx& cx)
+__device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerView& w, int imol,
+                                                    float tlen0, float tlen1, double* eo, double* en)
 {
     const int N = w.N, lane = lane_id();
     const unsigned lt = lt_mask();
     double* q = w.q;
     WalkerScalars* sc = w.sc;
+    uint32_t* cxs = w.cxs;
     int nq = 0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) { cx.seg_start[c] = 0; cx.seg_n[c] = 0; }
 
     // cached tensor of imol (old position) and its path length: issued early, used after stage 2
     double told = 0.0;
     if (lane < NLAT * TS) told = __ldcg(w.gten + ((size_t)(lane / TS) * N + imol) * TS + (lane % TS));
-    cx.dispi[0] = __ldcg(w.gdisp + imol);
-    cx.dispi[1] = (NLAT == 2) ? __ldcg(w.gdisp + N + imol) : 0.f;
+    const float disp0 = __ldcg(w.gdisp + imol);
+    const float disp1 = (NLAT == 2) ? __ldcg(w.gdisp + N + imol) : 0.f;
 
     // ---- stage 1: distance tests over imol's own list (lanes = slots), compaction into bond records
-#pragma unroll
+#pragma unroll 1
     for (int lat = 0; lat < NLAT; ++lat) {
         const double* P = w.pos + lat * 3 * N;
         const double* V = w.iv + lat * 3 * IVC;
         const int nni = w.nn[lat * N + imol];
         const bool has = lane < nni;
-        const uint32_t e = has ? w.list[((size_t)lat * N + imol) * LC + lane] : 0u;
+        const uint32_t e = has ? (uint32_t)__ldcg(w.list + ((size_t)lat * N + imol) * LC + lane) : 0u;
         const int j = e & 1023, img = e >> 10;
         const double pjx = P[j] + V[img], pjy = P[N + j] + V[IVC + img], pjz = P[2 * N + j] + V[2 * IVC + img];
         const double tox = pjx - P[imol], toy = pjy - P[N + imol], toz = pjz - P[2 * N + imol];
         const double r2o = tox * tox + toy * toy + toz * toz;
         const bool fo = has && r2o < RCSQ;
         const uint32_t bo = __ballot_sync(FULL, fo);
-        cx.mo[lat] = bo;
         const int io = nq + __popc(bo & lt);
-        cx.seg_start[lat * 2] = nq; cx.seg_n[lat * 2] = __popc(bo); nq += __popc(bo);
+        cxs[CX_MO + lat] = bo; cxs[CX_SEG + 2 * lat] = nq; cxs[CX_NSEG + 2 * lat] = __popc(bo);
+        nq += __popc(bo);
         bool fn = false; int in_ = 0; uint32_t bn = 0;
         double tnx = 0, tny = 0, tnz = 0, r2n = 0;
         if (WITH_NEW) {
-            tnx = pjx - pnew[lat][0]; tny = pjy - pnew[lat][1]; tnz = pjz - pnew[lat][2];
+            tnx = pjx - w.pn[lat * 3]; tny = pjy - w.pn[lat * 3 + 1]; tnz = pjz - w.pn[lat * 3 + 2];
             r2n = tnx * tnx + tny * tny + tnz * tnz;
             fn = has && r2n < RCSQ;
             bn = __ballot_sync(FULL, fn);
             in_ = nq + __popc(bn & lt);
-            cx.seg_start[lat * 2 + 1] = nq; cx.seg_n[lat * 2 + 1] = __popc(bn); nq += __popc(bn);
         }
-        cx.mn[lat] = bn;
+        cxs[CX_MN + lat] = bn; cxs[CX_SEG + 2 * lat + 1] = nq; cxs[CX_NSEG + 2 * lat + 1] = __popc(bn);
+        nq += __popc(bn);
         // bonded slots that are images of the same molecule (narrow cells): handled as one group
         const uint32_t grp = __match_any_sync(FULL, (fo || fn) ? (uint32_t)j : 0x8000u + (uint32_t)lane);
-        cx.grp[lat] = grp;
         // nq may exceed QC only at unphysical densities (flagged below)
         if (fo && io < QC) {
             q[io] = tox; q[QC + io] = toy; q[2 * QC + io] = toz; q[3 * QC + io] = r2o;
@@ -737,28 +743,28 @@ __device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerV
             w.qgrp[in_] = grp;
         }
     }
+    if (NLAT == 1) { cxs[CX_MO + 1] = 0; cxs[CX_MN + 1] = 0; cxs[CX_SEG + 2] = nq; cxs[CX_SEG + 3] = nq; cxs[CX_NSEG + 2] = 0; cxs[CX_NSEG + 3] = 0; }
     if (nq > QC) {                                  // results of this call are invalid; the walker is flagged
         sc->error |= ERR_BOND_OVERFLOW;
         nq = QC;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { cx.seg_start[c] = 0; cx.seg_n[c] = 0; }
+        if (lane < 8) cxs[CX_SEG + lane] = 0;       // all segments empty
     }
-    cx.nq = nq;
-    __syncwarp();
 
     // ---- which path?  (uniform over the warp)
-    bool guard = true;
-#pragma unroll
-    for (int lat = 0; lat < NLAT; ++lat)
-        guard = guard && (sc->rn_eff[lat] - cx.dispi[lat] - (WITH_NEW ? tlen[lat] : 0.f) - sc->dmax[lat] > (float)(RSAFE * 1.0001));
+    const float margin = (float)(RSAFE * 1.0001);
+    bool guard = sc->rn_eff[0] - disp0 - (WITH_NEW ? tlen0 : 0.f) - sc->dmax[0] > margin;
+    if (NLAT == 2) guard = guard && (sc->rn_eff[1] - disp1 - (WITH_NEW ? tlen1 : 0.f) - sc->dmax[1] > margin);
     const bool forced = sc->force_exact || !sc->tensors_valid;
     const bool fast = guard && !forced;
-    cx.fast = fast;
+    cxs[CX_NQ] = nq; cxs[CX_FAST] = fast;
+    cxs[CX_DISP] = __float_as_uint(disp0); cxs[CX_DISP + 1] = __float_as_uint(disp1);
+    __syncwarp();
 
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;     // per-lane partial sums of the 4 evaluations
 
     // ---- stage 2: bond evaluation (pair energy, g, unit vector); which evaluations own a short bond
     uint32_t shortev = 0;
+#pragma unroll 1
     for (int b = 0; b < nq; b += 32) {
         const int r = b + lane;
         if (r < nq) {
@@ -778,19 +784,19 @@ __device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerV
         w.ti[(lat * 2) * TS + comp] = told;
         if (WITH_NEW) {
             double tn = 0.0;
-            const int s0 = lat ? cx.seg_start[3] : cx.seg_start[1], s1 = s0 + (lat ? cx.seg_n[3] : cx.seg_n[1]);
-            const int sel = ten_sel(comp);
+            const int s0 = cxs[CX_SEG + 2 * lat + 1], s1 = s0 + cxs[CX_NSEG + 2 * lat + 1];
+            const TenSel sel = ten_sel(comp);
+#pragma unroll 1
             for (int c = s0; c < s1; ++c) tn += ten_term_sel(sel, q, c);
             w.ti[(lat * 2 + 1) * TS + comp] = tn;
         }
     }
     __syncwarp();
 
-    const uint32_t segs = (uint32_t)cx.seg_start[0] | ((uint32_t)cx.seg_start[1] << 8) | ((uint32_t)cx.seg_start[2] << 16) | ((uint32_t)cx.seg_start[3] << 24);
-    const uint32_t segn = (uint32_t)cx.seg_n[0] | ((uint32_t)cx.seg_n[1] << 8) | ((uint32_t)cx.seg_n[2] << 16) | ((uint32_t)cx.seg_n[3] << 24);
     bool anybad = !fast;
     double i0 = 0.0, i1 = 0.0, i2 = 0.0, i3 = 0.0;     // i-centred sums through the tensors of imol
     // ---- lanes = bond records: i-centred and j-centred triplet sums as quadratic forms
+#pragma unroll 1
     for (int b = 0; b < nq; b += 32) {
         const int r = b + lane;
         bool bad = false;
@@ -804,9 +810,10 @@ __device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerV
                 T.load(w.gten + ((size_t)lat * N + j) * TS);
                 // the bonds of j to (images of) imol at its OLD position leave the sum (outward vector -u_c):
                 // they are the old records of the slots of this record's group
-                const uint32_t bo = pick2(lat, cx.mo), grp = w.qgrp[r];
-                const int so = lat ? cx.seg_start[2] : cx.seg_start[0], se = pick4(ev, cx.seg_start);
+                const uint32_t bo = cxs[CX_MO + lat], grp = w.qgrp[r];
+                const int so = cxs[CX_SEG + 2 * lat], se = cxs[CX_SEG + ev];
                 uint32_t m = grp & bo;
+#pragma unroll 1
                 while (m) {
                     const int s2 = __ffs(m) - 1; m &= m - 1;
                     const int c = so + __popc(bo & ((1u << s2) - 1u));
@@ -814,12 +821,12 @@ __device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerV
                 }
                 bad = bad || fabs(T.ns) > 0.5;                               // j keeps a bond shorter than RSAFE
                 double tj = bad ? 0.0 : T.quad(ux, uy, uz, -1.0);            // centre j: cos = -u.u_jk
-                Ten Ti;
-                Ti.load_shared(w.ti + ev * TS);
-                double ti = 0.5 * (Ti.quad(ux, uy, uz, 1.0) - g * OMC0SQ);   // centre i: ordered pairs, minus c == b
+                T.load_shared(w.ti + ev * TS);
+                double ti = 0.5 * (T.quad(ux, uy, uz, 1.0) - g * OMC0SQ);    // centre i: ordered pairs, minus c == b
                 // two bonds to different images of the same j: the reference counts that pair 3 times
-                const uint32_t be = (ev & 1) ? pick2(lat, cx.mn) : bo;
+                const uint32_t be = (ev & 1) ? cxs[CX_MN + lat] : bo;
                 m = grp & be & ~(1u << s);
+#pragma unroll 1
                 while (m) {
                     const int s2 = __ffs(m) - 1; m &= m - 1;
                     const int c = se + __popc(be & ((1u << s2) - 1u));
@@ -836,6 +843,7 @@ __device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerV
         // ---- centres that need the reference's enumeration (rare): one pass over j's list each
         uint32_t badm = __ballot_sync(FULL, bad);
         anybad = anybad || badm;
+#pragma unroll 1
         while (badm) {
             const int c = __ffs(badm) - 1; badm &= badm - 1;
             const int ev = w.qmeta[b + c] & 3;
@@ -845,21 +853,21 @@ __device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerV
         }
     }
     if (anybad) {                                   // a close contact somewhere near imol: i-centred pairs one by one
+        const uint32_t segs = cxs[CX_SEG] | (cxs[CX_SEG + 1] << 8) | (cxs[CX_SEG + 2] << 16) | (cxs[CX_SEG + 3] << 24);
+        const uint32_t segn = cxs[CX_NSEG] | (cxs[CX_NSEG + 1] << 8) | (cxs[CX_NSEG + 2] << 16) | (cxs[CX_NSEG + 3] << 24);
         const Acc4 p = icentre_pairs_warp(ref, segs, segn);
         a0 += p.a0; a1 += p.a1; a2 += p.a2; a3 += p.a3;
+        sc->slow_moves[!fast ? (forced ? 3 : 2) : 1] += 1;
     } else {
         a0 += i0; a1 += i1; a2 += i2; a3 += i3;
+        sc->fast_moves += 1;
     }
-    if (!fast) sc->slow_moves[forced ? 3 : 2] += 1;
-    else if (anybad) sc->slow_moves[1] += 1;
-    else sc->fast_moves += 1;
 
     reduce4(a0, a1, a2, a3);
     eo[0] = a0; en[0] = a1;
     if (NLAT == 2) { eo[1] = a2; en[1] = a3; }
     __syncwarp();
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // Full energy of one lattice (compute_model_energy, molint.F90:407-499), molecule-
@@ -885,7 +893,7 @@ __device__ __noinline__ double full_energy_warp(WalkerRef ref, int lat, int what
         for (; a1 < N && a1 - a < MC; ++a1) {
             const int nna = w.nn[lat * N + a1];
             const bool has = lane < nna;
-            const uint32_t e = has ? w.list[((size_t)lat * N + a1) * LC + lane] : 0u;
+            const uint32_t e = has ? (uint32_t)__ldcg(w.list + ((size_t)lat * N + a1) * LC + lane) : 0u;
             const int j = e & 1023, img = e >> 10;
             const double tx = (P[j] + V[img]) - P[a1];
             const double ty = (P[N + j] + V[IVC + img]) - P[N + a1];
@@ -944,7 +952,7 @@ __device__ __noinline__ double full_energy_warp(WalkerRef ref, int lat, int what
                     const int m = t / TS, comp = t - m * TS;
                     const int s0 = w.seg[m], s1 = w.seg[m + 1];
                     double tn = 0.0;
-                    const int sel = ten_sel(comp);
+                    const TenSel sel = ten_sel(comp);
                     for (int c = s0; c < s1; ++c) tn += ten_term_sel(sel, q, c);
                     __stcg(w.gten + ((size_t)lat * N + a + m) * TS + comp, tn);
                 }

@@ -57,32 +57,30 @@ struct DeviceState {
 };
 
 // ---------------------------------------------------------------- staging
+// Global -> shared at the start of a work unit and back at its end.  Loads bypass L1 (ld.cg): the
+// previous unit of this walker may have run on another SM during the same launch.
 __device__ __forceinline__ void load_walker(const DeviceState& S, int wi, const WalkerView& w)
 {
     const int N = S.N, nlat = S.nlat, lane = lane_id();
     const double* gp = S.pos + (size_t)wi * nlat * 3 * N;
-    for (int t = lane; t < nlat * 3 * N; t += 32) w.pos[t] = gp[t];
+    for (int t = lane; t < nlat * 3 * N; t += 32) w.pos[t] = __ldcg(gp + t);
     const double* gi = S.iv + (size_t)wi * nlat * 3 * IVC;
-    for (int t = lane; t < nlat * 3 * IVC; t += 32) w.iv[t] = gi[t];
+    for (int t = lane; t < nlat * 3 * IVC; t += 32) w.iv[t] = __ldcg(gi + t);
     if (lane < nlat * 9) {
-        w.cell[lane] = S.cell[(size_t)wi * nlat * 9 + lane];
-        w.recip[lane] = S.recip[(size_t)wi * nlat * 9 + lane];
+        w.cell[lane] = __ldcg(S.cell + (size_t)wi * nlat * 9 + lane);
+        w.recip[lane] = __ldcg(S.recip + (size_t)wi * nlat * 9 + lane);
     }
-    if (lane < 2) w.niv[lane] = S.niv[wi * 2 + lane];
-    // lists: 16-byte vector copies (N*LC*2 bytes per lattice is a multiple of 16)
-    const uint4* gl = (const uint4*)(S.list + (size_t)wi * nlat * N * LC);
-    uint4* sl = (uint4*)w.list;
-    for (int t = lane; t < nlat * N * LC / 8; t += 32) sl[t] = gl[t];
+    if (lane < 2) w.niv[lane] = __ldcg(S.niv + wi * 2 + lane);
     const uint8_t* gn = S.nn + (size_t)wi * nlat * N;
-    for (int t = lane; t < nlat * N; t += 32) w.nn[t] = gn[t];
+    for (int t = lane; t < nlat * N; t += 32) w.nn[t] = __ldcg(gn + t);
     // scalars: word-wise copy
     const uint32_t* gs = (const uint32_t*)(S.scal + wi);
     uint32_t* ss = (uint32_t*)w.sc;
-    for (int t = lane; t < (int)(sizeof(WalkerScalars) / 4); t += 32) ss[t] = gs[t];
+    for (int t = lane; t < (int)(sizeof(WalkerScalars) / 4); t += 32) ss[t] = __ldcg(gs + t);
     __syncwarp();
 }
 
-__device__ __forceinline__ void store_walker(const DeviceState& S, int wi, const WalkerView& w, bool lists)
+__device__ __forceinline__ void store_walker(const DeviceState& S, int wi, const WalkerView& w)
 {
     const int N = S.N, nlat = S.nlat, lane = lane_id();
     __syncwarp();
@@ -95,13 +93,8 @@ __device__ __forceinline__ void store_walker(const DeviceState& S, int wi, const
         S.recip[(size_t)wi * nlat * 9 + lane] = w.recip[lane];
     }
     if (lane < 2) S.niv[wi * 2 + lane] = w.niv[lane];
-    if (lists) {
-        uint4* gl = (uint4*)(S.list + (size_t)wi * nlat * N * LC);
-        const uint4* sl = (const uint4*)w.list;
-        for (int t = lane; t < nlat * N * LC / 8; t += 32) gl[t] = sl[t];
-        uint8_t* gn = S.nn + (size_t)wi * nlat * N;
-        for (int t = lane; t < nlat * N; t += 32) gn[t] = w.nn[t];
-    }
+    uint8_t* gn = S.nn + (size_t)wi * nlat * N;
+    for (int t = lane; t < nlat * N; t += 32) gn[t] = w.nn[t];
     uint32_t* gs = (uint32_t*)(S.scal + wi);
     const uint32_t* ss = (const uint32_t*)w.sc;
     for (int t = lane; t < (int)(sizeof(WalkerScalars) / 4); t += 32) gs[t] = ss[t];
@@ -134,17 +127,26 @@ struct Rng {
     const DeviceState* S; const McParams* p;
     double* buf; uint64_t* base;
     int pos;
-    __device__ __forceinline__ double draw()
+    // make sure the next n draws are in the buffer (n <= RB - 1); called once per trial move, so that
+    // draw() itself is branch-free.  The buffer always starts at an even draw index (Philox block).
+    __device__ __forceinline__ void reserve(int n)
     {
-        if (pos == RB) {
+        if (pos + n > RB) {
             __syncwarp();
-            *base = *base + RB;               // every lane stores the same value
+            const uint64_t next = *base + (uint64_t)pos;
+            __syncwarp();
+            *base = next & ~(uint64_t)1;      // every lane stores the same value
             rng_refill(ref, *S, *p, wi);
-            pos = 0;
+            pos = (int)(next & 1);
         }
-        return buf[pos++];
     }
+    __device__ __forceinline__ double draw() { return buf[pos++]; }
 };
+#ifndef MWGPU_MC_BLOCKS
+#define MWGPU_MC_BLOCKS 24
+#endif
+constexpr int MC_BLOCKS_PER_SM = MWGPU_MC_BLOCKS;   // register budget of k_mc_run: 65536 / (32 * blocks) per thread
+constexpr int DRAWS_PER_MOVE = 8;            // at most 8 draws per trial move (+ switch)
 
 // ---------------------------------------------------------------- order parameter / weights
 struct EtaBin { double eta; int k; };
@@ -323,7 +325,7 @@ __device__ __noinline__ void rescale_all(WalkerRef ref, double* refpos, int lat)
         double x = P[i], y = P[N + i], z = P[2 * N + i];
         rescale_pos(x, y, z, rm, hm);
         P[i] = x; P[N + i] = y; P[2 * N + i] = z;
-        x = R[i]; y = R[N + i]; z = R[2 * N + i];
+        x = __ldcg(R + i); y = __ldcg(R + N + i); z = __ldcg(R + 2 * N + i);
         rescale_pos(x, y, z, rm, hm);
         R[i] = x; R[N + i] = y; R[2 * N + i] = z;
     }
@@ -467,76 +469,101 @@ __device__ __noinline__ int volume_move(WalkerRef ref, const DeviceState& S, con
 
 // commit of an accepted translation: new position, and the bond-tensor cache follows the move
 template <int NLAT>
-__device__ __forceinline__ void commit_translation(const WalkerView& w, int imol, const double (*pnew)[3],
-                                                   const float* tlen, const LocalCtx& cx)
+__device__ __forceinline__ void commit_translation(const WalkerView& w, int imol, float tlen0, float tlen1)
 {
     const int N = w.N, lane = lane_id();
     WalkerScalars* sc = w.sc;
+    const uint32_t* cxs = w.cxs;
+    const double* q = w.q;
     __syncwarp();
-#pragma unroll
-    for (int lat = 0; lat < NLAT; ++lat) {
-        double* P = w.pos + lat * 3 * N;
-        if (lane < 3) P[lane * N + imol] = (lane == 0) ? pnew[lat][0] : (lane == 1) ? pnew[lat][1] : pnew[lat][2];
-        const float d = cx.dispi[lat] + tlen[lat];
-        if (lane == 0) __stcg(w.gdisp + lat * N + imol, d);
-        sc->dmax[lat] = fmaxf(sc->dmax[lat], d);
-    }
-    __syncwarp();
-    if (!sc->tensors_valid) return;
+    if (lane < NLAT * 3) w.pos[(lane / 3) * 3 * N + (lane % 3) * N + imol] = w.pn[lane];
     {
-        const double* q = w.q;
-        // tensor of imol at its new position
-        if (lane < NLAT * TS) {
-            const int lat = lane / TS, comp = lane - lat * TS;
-            __stcg(w.gten + ((size_t)lat * N + imol) * TS + comp, w.ti[(lat * 2 + 1) * TS + comp]);
+        const float d0 = __uint_as_float(cxs[CX_DISP]) + tlen0;
+        sc->dmax[0] = fmaxf(sc->dmax[0], d0);
+        if (lane == 0) __stcg(w.gdisp + imol, d0);
+        if (NLAT == 2) {
+            const float d1 = __uint_as_float(cxs[CX_DISP + 1]) + tlen1;
+            sc->dmax[1] = fmaxf(sc->dmax[1], d1);
+            if (lane == 0) __stcg(w.gdisp + N + imol, d1);
         }
-        // neighbours (lanes = list slots of imol): T_j loses the old bonds to imol and gains the new ones;
-        // the lowest slot of a group of images of one molecule applies the whole group's change
-#pragma unroll
-        for (int lat = 0; lat < NLAT; ++lat) {
-            const uint32_t bo = cx.mo[lat], bn = cx.mn[lat], grp = cx.grp[lat];
-            if ((((bo | bn) >> lane) & 1u) && (int)(__ffs(grp) - 1) == lane) {
-                const int j = w.list[((size_t)lat * N + imol) * LC + lane] & 1023;
-                double* gp = w.gten + ((size_t)lat * N + j) * TS;
-                Ten T;
-                T.load(gp);
-                uint32_t m = grp;
+    }
+    if (!sc->tensors_valid) { __syncwarp(); return; }
+    // tensor of imol at its new position
+    if (lane < NLAT * TS) {
+        const int lat = lane / TS, comp = lane - lat * TS;
+        __stcg(w.gten + ((size_t)lat * N + imol) * TS + comp, w.ti[(lat * 2 + 1) * TS + comp]);
+    }
+    // neighbours (lanes = list slots of imol): T_j loses the old bonds to imol and gains the new ones;
+    // the lowest slot of a group of images of one molecule applies the whole group's change
+#pragma unroll 1
+    for (int lat = 0; lat < NLAT; ++lat) {
+        const uint32_t bo = cxs[CX_MO + lat], bn = cxs[CX_MN + lat];
+        const bool mine = ((bo | bn) >> lane) & 1u;
+        const int j = mine ? (__ldcg(w.list + ((size_t)lat * N + imol) * LC + lane) & 1023) : 0;
+        const uint32_t grp = __match_any_sync(FULL, mine ? (uint32_t)j : 0x8000u + (uint32_t)lane);
+        if (mine && (int)(__ffs(grp) - 1) == lane) {
+            double* gp = w.gten + ((size_t)lat * N + j) * TS;
+            Ten T;
+            T.load(gp);
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const uint32_t bm = pass ? bn : bo;
+                const int s0 = cxs[CX_SEG + 2 * lat + pass];
+                const double sign = pass ? 1.0 : -1.0;
+                uint32_t m = grp & bm;
+#pragma unroll 1
                 while (m) {
                     const int s2 = __ffs(m) - 1; m &= m - 1;
-                    const uint32_t below = (1u << s2) - 1u;
-                    if ((bo >> s2) & 1u) {
-                        const int c = cx.seg_start[lat * 2] + __popc(bo & below);
-                        T.add(-1.0, -q[c], -q[QC + c], -q[2 * QC + c], q[3 * QC + c]);
-                    }
-                    if ((bn >> s2) & 1u) {
-                        const int c = cx.seg_start[lat * 2 + 1] + __popc(bn & below);
-                        T.add(1.0, -q[c], -q[QC + c], -q[2 * QC + c], q[3 * QC + c]);
-                    }
+                    const int c = s0 + __popc(bm & ((1u << s2) - 1u));
+                    T.add(sign, -q[c], -q[QC + c], -q[2 * QC + c], q[3 * QC + c]);
                 }
-                T.store(gp);
             }
+            T.store(gp);
         }
     }
     __syncwarp();
 }
 
 // ---------------------------------------------------------------- the walker kernel
-// One warp (= one CTA of 32 threads) per walker; ncycles MC cycles of the hot
-// part of mc_cycle (mc_moves.F90:117-255).
+// Persistent kernel: one warp (= one CTA of 32 threads) per resident slot; every slot claims work
+// units (chunk c of `chunk` MC cycles of walker wi) from a global counter in chunk-major order and
+// advances that walker through the hot part of mc_cycle (mc_moves.F90:117-255).  Chunk c of a
+// walker starts only after its chunk c-1 was published (sched[1 + wi] >= c); since units are
+// claimed in order and every claimed unit is resident, the wait cannot deadlock.  The tail of a
+// launch is then at most one chunk long, whatever the ratio of walkers to resident slots.
+struct Sched { int ncycles, chunk, nchunks; int* state; };     // state[0] = next unit, state[1 + w] = chunks done
+
 template <int NLAT>
-__global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceState S,
-                                               const __grid_constant__ McParams p, int ncycles)
+__global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_constant__ DeviceState S,
+                                                             const __grid_constant__ McParams p,
+                                                             const __grid_constant__ Sched sd)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int wi = blockIdx.x;
-    if (wi >= S.W) return;
     const int lane = lane_id();
     const int N = S.N;
-    const WalkerRef ref{smem, S.ten + (size_t)wi * NLAT * N * TS, S.disp + (size_t)wi * NLAT * N, N, NLAT};
+    const double Nd = (double)N;
+    const int nunits = sd.nchunks * S.W;
+  for (;;) {
+    int unit = 0;
+    if (lane == 0) unit = atomicAdd(sd.state, 1);
+    unit = __shfl_sync(FULL, unit, 0);
+    if (unit >= nunits) break;
+    const int chunk_id = unit / S.W;
+    const int wi = unit - chunk_id * S.W;
+    const int ncycles = min(sd.chunk, sd.ncycles - chunk_id * sd.chunk);
+    if (chunk_id > 0) {
+        if (lane == 0) {
+            volatile int* done = sd.state + 1 + wi;
+            while (*done < chunk_id) __nanosleep(256);
+        }
+        __syncwarp();
+        __threadfence();
+    }
+    const WalkerRef ref{smem, S.list + (size_t)wi * NLAT * N * LC, S.ten + (size_t)wi * NLAT * N * TS,
+                        S.disp + (size_t)wi * NLAT * N, N, NLAT};
     const WalkerView w = ref.view();
     load_walker(S, wi, w);
     WalkerScalars* sc = w.sc;
-    const double Nd = (double)N;
     double* wgt = S.weight + (size_t)wi * S.NB;
     double* hist = S.hist + (size_t)wi * S.NB;
     double* uhist = S.uhist + (size_t)wi * S.NB;
@@ -554,7 +581,7 @@ __global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceSta
     }
     if (NLAT == 2) { w.lv[0] = log(sc->vol[0] / sc->vol[1]); w.lv[1] = log(sc->vol[1] / sc->vol[0]); }
 
-    for (int cyc = 0; cyc < ncycles && !(err & (ERR_WINDOW | ERR_PROB)); ++cyc) {
+    for (int cyc = 0; cyc < ncycles && !((err | sc->error) & (ERR_WINDOW | ERR_PROB)); ++cyc) {
         const int cycle = sc->cycle + 1;
         sc->cycle = cycle;
         if (p.dd) {                                            // mc_moves.F90:181-210
@@ -576,6 +603,7 @@ __global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceSta
         const bool fuse_switch = do_switch && p.samplerun;     // weights fixed: eta of the switch is already known
 
         for (int imove = 0; imove < N; ++imove) {              // :224-250
+            rng.reserve(DRAWS_PER_MOVE);
             const double xi = rng.draw();
             if (xi < p.transP) {
                 // ====================== mc_water_translation (mc_moves.F90:966-1213) ======================
@@ -608,23 +636,25 @@ __global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceSta
                     by = xa(xa(xm(MW_H(hm,2,1), sx), xm(MW_H(hm,2,2), sy)), xm(MW_H(hm,2,3), sz));
                     bz = xa(xa(xm(MW_H(hm,3,1), sx), xm(MW_H(hm,3,2), sy)), xm(MW_H(hm,3,3), sz));
                 }
-                double tv[2][3];
-                tv[0][0] = one ? x : bx; tv[0][1] = one ? y : by; tv[0][2] = one ? z : bz;
-                tv[1][0] = one ? bx : x; tv[1][1] = one ? by : y; tv[1][2] = one ? bz : z;
-                double pnew[2][3];
-                float tlen[2] = {0.f, 0.f};                    // displacement lengths, rounded up (guard)
-#pragma unroll
-                for (int lat = 0; lat < NLAT; ++lat) {
-                    const double* P = w.pos + lat * 3 * N;
-                    pnew[lat][0] = xa(P[imol], tv[lat][0]);
-                    pnew[lat][1] = xa(P[N + imol], tv[lat][1]);
-                    pnew[lat][2] = xa(P[2 * N + imol], tv[lat][2]);
-                    const float fx = (float)tv[lat][0], fy = (float)tv[lat][1], fz = (float)tv[lat][2];
-                    tlen[lat] = sqrtf(fx * fx + fy * fy + fz * fz) * 1.0001f;
+                // trial displacement tv[lat][d] and trial position pn[lat][d] live in shared memory
+                // (uniform values): lane l < 6 owns component l
+                float tlen0, tlen1 = 0.f;                      // displacement lengths, rounded up (guard)
+                {
+                    const float fa = sqrtf((float)(x * x + y * y + z * z)) * 1.0001f;
+                    const float fb = sqrtf((float)(bx * bx + by * by + bz * bz)) * 1.0001f;
+                    tlen0 = one ? fa : fb; tlen1 = one ? fb : fa;
+                    __syncwarp();
+                    if (lane < NLAT * 3) {
+                        const int lat = lane / 3, d = lane - lat * 3;
+                        const bool act = (lat == 0) == one;    // this lattice is the active one
+                        const double t = (d == 0) ? (act ? x : bx) : (d == 1) ? (act ? y : by) : (act ? z : bz);
+                        w.tv[lane] = t;
+                        w.pn[lane] = xa(w.pos[lat * 3 * N + d * N + imol], t);
+                    }
+                    __syncwarp();
                 }
                 double eo[2] = {0.0, 0.0}, en[2] = {0.0, 0.0};
-                LocalCtx cx;
-                local_energies_warp<NLAT, true>(ref, w, imol, pnew, tlen, eo, en, cx);
+                local_energies_warp<NLAT, true>(ref, w, imol, tlen0, tlen1, eo, en);
 
                 // model_energy bookkeeping exactly as :1013-1016, :1087-1090
                 const double Eb0 = sc->E[0], Eb1 = sc->E[1];
@@ -675,17 +705,11 @@ __global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceSta
                     if (dmu > sc->max_dmu) sc->max_dmu = dmu;
                     sc->E[0] = Ea0;
                     if (NLAT == 2) { sc->E[1] = Ea1; sc->mu = mu_acc; }
-                    commit_translation<NLAT>(w, imol, pnew, tlen, cx);
+                    commit_translation<NLAT>(w, imol, tlen0, tlen1);
                 } else {
                     // reject: the reference restores by (x+t)-t, not by copy (mc_moves.F90:1186)
                     __syncwarp();
-#pragma unroll
-                    for (int lat = 0; lat < NLAT; ++lat) {
-                        double* P = w.pos + lat * 3 * N;
-                        const double pn = (lane == 0) ? pnew[lat][0] : (lane == 1) ? pnew[lat][1] : pnew[lat][2];
-                        const double tt = (lane == 0) ? tv[lat][0] : (lane == 1) ? tv[lat][1] : tv[lat][2];
-                        if (lane < 3) P[lane * N + imol] = xs(pn, tt);
-                    }
+                    if (lane < NLAT * 3) w.pos[(lane / 3) * 3 * N + (lane % 3) * N + imol] = xs(w.pn[lane], w.tv[lane]);
                     if (NLAT == 2) sc->mu = mu_rej;
                     __syncwarp();
                 }
@@ -749,7 +773,12 @@ __global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceSta
     sc->rng_index = idx;
     sc->error |= err;
     __syncwarp();
-    store_walker(S, wi, w, true);
+    store_walker(S, wi, w);
+    // publish: this walker's next chunk may start (on any SM)
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(sd.state + 1 + wi, chunk_id + 1);
+  }
 }
 
 }  // namespace mw

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <dlfcn.h>
 
 using namespace mw;
@@ -58,6 +59,8 @@ struct mwgpu_ctx {
     size_t iout_ints = 0;
     double* delta = nullptr;       // [3][NBP] summed increments
     double* fifo = nullptr;
+    int* sched = nullptr;          // [1 + W] unit counter + per-walker chunks done (k_mc_run)
+    int mc_grid = 0;               // resident slots of k_mc_run on this device
     int64_t launches = 0;
     float last_ms = 0.f;
     std::vector<double> h_mubin, h_binwidth;
@@ -122,6 +125,7 @@ extern "C" int mwgpu_create(int nwater, int nlat, int nwalkers, int device, mwgp
     rc |= dalloc(&S.disp, W * L * N);
     rc |= dalloc(&S.scal, W);
     rc |= dalloc(&S.transcount, W * N);
+    rc |= dalloc(&c->sched, W + 1);
     c->stage_doubles = W * L * (2 * 3 * N + 9);
     rc |= dalloc(&c->stage, c->stage_doubles);
     c->out_doubles = W * 2 > N ? W * 2 : N;
@@ -149,7 +153,7 @@ extern "C" void mwgpu_destroy(mwgpu_ctx* c)
     DeviceState& S = c->S;
     void* ptrs[] = {S.pos, S.ref, S.cell, S.recip, S.refcell, S.iv, S.niv, S.list, S.nn, S.ten, S.disp, S.scal,
                     S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.transcount, S.mubin,
-                    S.binwidth, c->stage, c->out, c->iout, c->delta, c->fifo};
+                    S.binwidth, c->stage, c->out, c->iout, c->delta, c->fifo, c->sched};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -362,12 +366,12 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
     const int wi = a.w0 + blockIdx.x;
     if (wi >= S.W) return;
     const int lane = lane_id(), N = S.N;
-    const WalkerRef ref{smem, S.ten + (size_t)wi * NLAT * N * TS, S.disp + (size_t)wi * NLAT * N, N, NLAT};
+    const WalkerRef ref{smem, S.list + (size_t)wi * NLAT * N * LC, S.ten + (size_t)wi * NLAT * N * TS,
+                        S.disp + (size_t)wi * NLAT * N, N, NLAT};
     const WalkerView w = ref.view();
     load_walker(S, wi, w);
     WalkerScalars* sc = w.sc;
     int err = 0;
-    bool store_lists = false;
 
     switch (a.op) {
     case OP_ENERGY_INIT: {
@@ -389,7 +393,6 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
             if (a.leshift) mu = mu - sc->refH[0] + sc->refH[1];
             sc->mu = mu * a.beta - (double)N * log(sc->vol[0] / sc->vol[1]);
         }
-        store_lists = true;
         break;
     }
     case OP_IVECTS:
@@ -401,7 +404,6 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
         for (int lat = 0; lat < NLAT; ++lat)
             if (a.lat < 0 || a.lat == lat) { err |= compute_neighbours_warp(ref, lat); reset_guard(w, lat); }
         sc->tensors_valid = 0;
-        store_lists = true;
         break;
     case OP_MODEL_ENERGY:
 #pragma unroll
@@ -419,8 +421,7 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
         const int i1 = (a.op == OP_LOCAL_ONE) ? a.imol + 1 : N;
         for (int i = i0; i < i1; ++i) {
             double eo[2] = {0, 0}, en[2] = {0, 0};
-            LocalCtx cx;
-            local_energies_warp<NLAT, false>(ref, w, i, nullptr, nullptr, eo, en, cx);
+            local_energies_warp<NLAT, false>(ref, w, i, 0.f, 0.f, eo, en);
             if (lane == 0) a.out[i - i0] = (a.lat == 0) ? eo[0] : eo[1];
         }
         break;
@@ -506,7 +507,7 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
     }
     sc->error |= err;
     __syncwarp();
-    store_walker(S, wi, w, store_lists);
+    store_walker(S, wi, w);
 }
 
 static int launch_op(mwgpu_ctx* c, OpArgs a, int nw, bool sync = true)
@@ -665,15 +666,12 @@ __global__ void __launch_bounds__(32) k_model_energy_all(const __grid_constant__
     const int wi = unit / S.nlat, lat = unit % S.nlat;
     const int lane = lane_id(), N = S.N;
     // a one-lattice view: lattice `lat` of the walker is staged as lattice 0
-    const WalkerRef ref{smem, nullptr, nullptr, N, 1};
+    const WalkerRef ref{smem, S.list + ((size_t)wi * S.nlat + lat) * N * LC, nullptr, nullptr, N, 1};
     const WalkerView w = ref.view();
     const double* gp = S.pos + ((size_t)wi * S.nlat + lat) * 3 * N;
     for (int t = lane; t < 3 * N; t += 32) w.pos[t] = gp[t];
     const double* gi = S.iv + ((size_t)wi * S.nlat + lat) * 3 * IVC;
     for (int t = lane; t < 3 * IVC; t += 32) w.iv[t] = gi[t];
-    const uint4* gl = (const uint4*)(S.list + ((size_t)wi * S.nlat + lat) * N * LC);
-    uint4* sl = (uint4*)w.list;
-    for (int t = lane; t < N * LC / 8; t += 32) sl[t] = gl[t];
     const uint8_t* gn = S.nn + ((size_t)wi * S.nlat + lat) * N;
     for (int t = lane; t < N; t += 32) w.nn[t] = gn[t];
     __syncwarp();
@@ -936,22 +934,40 @@ extern "C" int mwgpu_mc_set_rng_fifo(mwgpu_ctx* c, const double* u, int64_t n)
 // ------------------------------------------------------------------------------------------------
 // the hot loop
 // ------------------------------------------------------------------------------------------------
+template <int NLAT>
+static int launch_mc(mwgpu_ctx* c, int ncycles)
+{
+    const size_t smem = walker_smem_bytes(c->N, c->nlat);
+    if (!c->mc_grid) {
+        CUDA_TRY(cudaFuncSetAttribute(k_mc_run<NLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0, sms = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mc_run<NLAT>, 32, smem));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        if (per_sm < 1) return fail("mwgpu_mc_run: the walker kernel does not fit on this device");
+        c->mc_grid = per_sm * sms;                  // every block of the grid is resident: units may wait on each other
+    }
+    Sched sd;
+    sd.ncycles = ncycles;
+    sd.chunk = 1;                                   // work unit = one MC cycle of one walker
+    sd.nchunks = (ncycles + sd.chunk - 1) / sd.chunk;
+    sd.state = c->sched;
+    const long long nunits = (long long)sd.nchunks * c->W;
+    if (nunits > 0x7fffffffLL) return fail("mwgpu_mc_run: too many work units in one launch");
+    CUDA_TRY(cudaMemsetAsync(c->sched, 0, sizeof(int) * (c->W + 1), c->stream));
+    const int grid = (int)std::min<long long>(nunits, c->mc_grid);
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    if (grid > 0) k_mc_run<NLAT><<<grid, 32, smem, c->stream>>>(c->S, c->P, sd);
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->launches++;
+    return 0;
+}
+
 static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
 {
     if (int rc = check_ctx(c, 0, false)) return rc;
     if (!c->mc_ready) return fail("mwgpu_mc_run: call mwgpu_mc_init first");
     if (ncycles < 0) return fail("mwgpu_mc_run: ncycles must be >= 0");
-    const size_t smem = walker_smem_bytes(c->N, c->nlat);
-    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    if (c->nlat == 2) {
-        CUDA_TRY(cudaFuncSetAttribute(k_mc_run<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_mc_run<2><<<c->W, 32, smem, c->stream>>>(c->S, c->P, ncycles);
-    } else {
-        CUDA_TRY(cudaFuncSetAttribute(k_mc_run<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_mc_run<1><<<c->W, 32, smem, c->stream>>>(c->S, c->P, ncycles);
-    }
-    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
-    c->launches++;
+    if (int rc = (c->nlat == 2) ? launch_mc<2>(c, ncycles) : launch_mc<1>(c, ncycles)) return rc;
     if (int rc = finish(c, sync)) return rc;
     if (sync) return collect_errors(c, "mwgpu_mc_run");
     return 0;
