@@ -116,7 +116,7 @@ __device__ __forceinline__ void recipmatrix3(const double* h, double* r)
     MW_H(r,3,2) = xs(xm(MW_H(h,1,3), MW_H(h,2,1)), xm(MW_H(h,1,1), MW_H(h,2,3)));
     MW_H(r,3,3) = xs(xm(MW_H(h,1,1), MW_H(h,2,2)), xm(MW_H(h,1,2), MW_H(h,2,1)));
     const double vol = xa(xa(xm(MW_H(h,1,1), MW_H(r,1,1)), xm(MW_H(h,1,2), MW_H(r,1,2))), xm(MW_H(h,1,3), MW_H(r,1,3)));
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 9; ++k) r[k] = xd(xm(xm(r[k], 2.0), PI), vol);
 }
 
@@ -619,34 +619,41 @@ enum : int {
 
 struct Acc4 { double a0, a1, a2, a3; };
 
-// exact stage 3: triplets centred on imol: all pairs (a<b) of bond records of one evaluation
-// (lanes = pairs).  segs/segn: start / length of the 4 record segments, one byte each.
-__device__ __noinline__ Acc4 icentre_pairs_warp(WalkerRef ref, uint32_t segs, uint32_t segn)
+// exact stage 3: triplets centred on imol: all pairs (b<c) of bond records of one evaluation
+// (lanes = records b, loop over the later records c of the same evaluation).
+__device__ __noinline__ Acc4 icentre_pairs_warp(WalkerRef ref)
 {
     const WalkerView w = ref.view();
     const double* q = w.q;
+    const uint32_t* cxs = w.cxs;
     const int lane = lane_id();
-    const int n0 = segn & 255, n1 = (segn >> 8) & 255, n2 = (segn >> 16) & 255, n3 = segn >> 24;
-    const int p0 = n0 * (n0 - 1) / 2, p1 = p0 + n1 * (n1 - 1) / 2, p2 = p1 + n2 * (n2 - 1) / 2, p3 = p2 + n3 * (n3 - 1) / 2;
-    Acc4 r{0.0, 0.0, 0.0, 0.0};
-    for (int pb = 0; pb < p3; pb += 32) {
-        const int p = pb + lane;
-        if (p < p3) {
-            const int c = (p >= p2) ? 3 : (p >= p1) ? 2 : (p >= p0) ? 1 : 0;
-            const int m = p - ((c == 3) ? p2 : (c == 2) ? p1 : (c == 1) ? p0 : 0);
-            const int s0 = (segs >> (8 * c)) & 255;
-            int bb = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)m)) * 0.5f);      // m = b(b-1)/2 + a with a < b
-            if (bb * (bb - 1) / 2 > m) --bb;
-            if ((bb + 1) * bb / 2 <= m) ++bb;
-            const int ra = s0 + (m - bb * (bb - 1) / 2), rb = s0 + bb;
-            const double ct = q[ra] * q[rb] + q[QC + ra] * q[QC + rb] + q[2 * QC + ra] * q[2 * QC + rb];
-            const double mult = ((w.qmeta[ra] >> 8) == (w.qmeta[rb] >> 8)) ? 3.0 * LEPS : LEPS;
-            const double tb = q[3 * QC + ra] * q[3 * QC + rb] * hfun(ct) * mult;
-            r.a0 += (c == 0) ? tb : 0.0; r.a1 += (c == 1) ? tb : 0.0;
-            r.a2 += (c == 2) ? tb : 0.0; r.a3 += (c == 3) ? tb : 0.0;
+    const int nq = cxs[CX_NQ];
+    Acc4 acc{0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+    for (int b0 = 0; b0 < nq; b0 += 32) {
+        const int r = b0 + lane;
+        const bool act = r < nq;
+        const uint32_t qm = act ? w.qmeta[r] : 0u;
+        const int ev = qm & 3;
+        const int send = act ? (int)(cxs[CX_SEG + ev] + cxs[CX_NSEG + ev]) : 0;
+        const double ux = act ? q[r] : 0.0, uy = act ? q[QC + r] : 0.0, uz = act ? q[2 * QC + r] : 0.0;
+        const double g = act ? q[3 * QC + r] : 0.0;
+        const int maxd = __reduce_max_sync(FULL, act ? send - r - 1 : 0);
+        double tb = 0.0;
+#pragma unroll 1
+        for (int d = 1; d <= maxd; ++d) {
+            const int c = r + d;
+            if (c < send) {
+                const double ct = ux * q[c] + uy * q[QC + c] + uz * q[2 * QC + c];
+                const double mult = ((qm >> 8) == (w.qmeta[c] >> 8)) ? 3.0 : 1.0;   // images of one molecule
+                tb += q[3 * QC + c] * hfun(ct) * mult;
+            }
         }
+        tb *= LEPS * g;
+        acc.a0 += (ev == 0) ? tb : 0.0; acc.a1 += (ev == 1) ? tb : 0.0;
+        acc.a2 += (ev == 2) ? tb : 0.0; acc.a3 += (ev == 3) ? tb : 0.0;
     }
-    return r;
+    return acc;
 }
 
 // exact stages 4+5 for ONE centre: triplets centred on the neighbour j of bond record rec
@@ -684,8 +691,9 @@ __device__ __noinline__ double jcentre_enum_warp(WalkerRef ref, int imol, int re
 
 // Inputs in shared memory: w.pn (trial position per lattice, WITH_NEW), w.cxs[CX_DISP..] is written here.
 // tlen0/tlen1: length of the trial displacement per lattice (guard).  Results: eo/en (uniform).
+// e0/e1: this lane's entry of imol's Verlet row in lattice 1/2 (loaded early by the caller).
 template <int NLAT, bool WITH_NEW>
-__device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerView& w, int imol,
+__device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerView& w, int imol, uint32_t e0, uint32_t e1,
                                                     float tlen0, float tlen1, double* eo, double* en)
 {
     const int N = w.N, lane = lane_id();
@@ -708,7 +716,7 @@ __device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerV
         const double* V = w.iv + lat * 3 * IVC;
         const int nni = w.nn[lat * N + imol];
         const bool has = lane < nni;
-        const uint32_t e = has ? (uint32_t)__ldcg(w.list + ((size_t)lat * N + imol) * LC + lane) : 0u;
+        const uint32_t e = has ? (lat ? e1 : e0) : 0u;
         const int j = e & 1023, img = e >> 10;
         const double pjx = P[j] + V[img], pjy = P[N + j] + V[IVC + img], pjz = P[2 * N + j] + V[2 * IVC + img];
         const double tox = pjx - P[imol], toy = pjy - P[N + imol], toz = pjz - P[2 * N + imol];
@@ -853,9 +861,7 @@ __device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerV
         }
     }
     if (anybad) {                                   // a close contact somewhere near imol: i-centred pairs one by one
-        const uint32_t segs = cxs[CX_SEG] | (cxs[CX_SEG + 1] << 8) | (cxs[CX_SEG + 2] << 16) | (cxs[CX_SEG + 3] << 24);
-        const uint32_t segn = cxs[CX_NSEG] | (cxs[CX_NSEG + 1] << 8) | (cxs[CX_NSEG + 2] << 16) | (cxs[CX_NSEG + 3] << 24);
-        const Acc4 p = icentre_pairs_warp(ref, segs, segn);
+        const Acc4 p = icentre_pairs_warp(ref);
         a0 += p.a0; a1 += p.a1; a2 += p.a2; a3 += p.a3;
         sc->slow_moves[!fast ? (forced ? 3 : 2) : 1] += 1;
     } else {

@@ -16,6 +16,7 @@ struct McParams {
     double beta, pressure;
     double transP, volP, swP;
     double r_pos, r_neg, a_pos, a_neg, log_r_pos, log_r_neg, inv_log_r_pos, inv_log_r_neg;
+    double c_pos, c_neg;    // (1 - r)/a of the two geometric progressions
     double av_binwidth, log_unbiased_norm;
     double mu_min, mu_max;
     double orig_wl_factor, wl_alpha;
@@ -52,6 +53,8 @@ struct DeviceState {
     int*    transcount; // [W][N]   mc_translations
     double* mubin;      // [NB]
     double* binwidth;   // [NB]
+    double* ginv;       // [NB]  ginv[k-1] = 2/(binwidth(k) + binwidth(k+1)), k = 1..NB-1
+    double* hinc;       // [NB]  av_binwidth/binwidth(k): histogram increment of bin k (mc_moves.F90:1621)
     const double* fifo; // host-supplied random numbers (walker 0 only)
     unsigned long long fifo_len;
 };
@@ -143,7 +146,7 @@ struct Rng {
     __device__ __forceinline__ double draw() { return buf[pos++]; }
 };
 #ifndef MWGPU_MC_BLOCKS
-#define MWGPU_MC_BLOCKS 24
+#define MWGPU_MC_BLOCKS 16
 #endif
 constexpr int MC_BLOCKS_PER_SM = MWGPU_MC_BLOCKS;   // register budget of k_mc_run: 65536 / (32 * blocks) per thread
 constexpr int DRAWS_PER_MOVE = 8;            // at most 8 draws per trial move (+ switch)
@@ -158,7 +161,7 @@ __device__ __noinline__ int bin_exact(double arg, double lr) { return (int)(log(
 // wgt is this walker's weight array (global memory, read through L2 because the same warp
 // updates it when generating weights).
 __device__ __noinline__ EtaBin eta_bin(const McParams& p, const double* __restrict__ mubin,
-                                       const double* __restrict__ binwidth, const WalkerScalars* sc,
+                                       const double* __restrict__ binwidth /* = DeviceState::ginv */, const WalkerScalars* sc,
                                        const double* wgt, double mu)
 {
     EtaBin r;
@@ -168,13 +171,13 @@ __device__ __noinline__ EtaBin eta_bin(const McParams& p, const double* __restri
         k = nb / 2 + 1;
     } else {
         const bool pos = mu > 0.0;
-        const double rr = pos ? p.r_pos : p.r_neg, aa = pos ? p.a_pos : p.a_neg, lr = pos ? p.log_r_pos : p.log_r_neg;
-        const double arg = 1.0 - (fabs(mu) - 0.5) * (1.0 - rr) / aa;
+        // (|mu| - 0.5)*(1 - r)/a with (1 - r)/a precomputed: identical to the reference's order for a == 1
+        const double arg = 1.0 - (fabs(mu) - 0.5) * (pos ? p.c_pos : p.c_neg);
         // int(log(arg)/log(r)): fast logarithm; the library log and the true division decide only
         // when the quotient is within 1e-7 of an integer
         const double y = log_fast(arg) * (pos ? p.inv_log_r_pos : p.inv_log_r_neg);
         int t = (int)y;
-        if (fabs(y - rint(y)) < 1e-7 || !(arg > 0.0)) t = bin_exact(arg, lr);
+        if (fabs(y - rint(y)) < 1e-7 || !(arg > 0.0)) t = bin_exact(arg, pos ? p.log_r_pos : p.log_r_neg);
         k = pos ? nb / 2 + 2 + t : nb / 2 - t;
     }
     r.k = k;
@@ -182,7 +185,6 @@ __device__ __noinline__ EtaBin eta_bin(const McParams& p, const double* __restri
     if (mu < sc->mu_lo || mu > sc->mu_hi) { r.eta = F_HUGE; return r; }
     k = min(max(k, 1), nb);                                  // memory safety at mu == mu_max (reference would overrun)
     const double* w = wgt - 1;
-    const double* bw = binwidth - 1;
     const double* mb = mubin - 1;
     if (!p.eta_interp) { r.eta = __ldcg(w + k); return r; }
     int ka, kb, kr;                                          // gradient between bins ka<kb, anchored at kr
@@ -192,7 +194,7 @@ __device__ __noinline__ EtaBin eta_bin(const McParams& p, const double* __restri
     else                         { ka = k - 1; kb = k; kr = k - 1; }
     ka = max(ka, 1); kb = min(kb, nb);
     const double wa = __ldcg(w + ka), wb = __ldcg(w + kb);
-    const double g = 2.0 * (wb - wa) / (__ldg(bw + ka) + __ldg(bw + kb));
+    const double g = (wb - wa) * __ldg(binwidth + ka - 1);       // binwidth = the 2/(bw(ka)+bw(kb)) table here
     const double wr = (kr == ka) ? wa : wb;
     r.eta = wr + (mu - __ldg(mb + kr)) * g;
     return r;
@@ -235,7 +237,7 @@ __device__ __noinline__ int lattice_switch_cold(WalkerRef ref, const DeviceState
     const WalkerView w = ref.view();
     WalkerScalars* sc = w.sc;
     Rng rng{ref, wi, &S, &p, w.rngbuf, w.rngbase, rng_pos};
-    const double eta = eta_bin(p, S.mubin, S.binwidth, sc, S.weight + (size_t)wi * S.NB, sc->mu).eta;
+    const double eta = eta_bin(p, S.mubin, S.ginv, sc, S.weight + (size_t)wi * S.NB, sc->mu).eta;
     const double arg = switch_arg(p, w, sc->E[0], sc->E[1], sc->ls == 1, eta, (double)N);
     const double compare = (arg > 0.0) ? 1.0 : exp_fast(arg);
     const double x = rng.draw();
@@ -414,11 +416,11 @@ __device__ __noinline__ int volume_move(WalkerRef ref, const DeviceState& S, con
     const bool one = (sc->ls == 1);
     double nlv12 = w.lv[0], nlv21 = w.lv[1];
     if (NLAT == 2) {
-        old_eta = eta_bin(p, S.mubin, S.binwidth, sc, wgt, sc->mu).eta;
+        old_eta = eta_bin(p, S.mubin, S.ginv, sc, wgt, sc->mu).eta;
         old_mu = sc->mu;
         nlv12 = log(sc->vol[0] / sc->vol[1]); nlv21 = log(sc->vol[1] / sc->vol[0]);
         sc->mu = mu_paren(p, sc, Nd, nlv12);
-        new_eta = eta_bin(p, S.mubin, S.binwidth, sc, wgt, sc->mu).eta;
+        new_eta = eta_bin(p, S.mubin, S.ginv, sc, wgt, sc->mu).eta;
     }
     x = rng.draw();
     const double dE = one ? newE[0] - backupE[0] : newE[1] - backupE[1];
@@ -613,6 +615,9 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
                 if (imol > N) imol = N;
                 imol -= 1;
                 if (lane == 0) atomicAdd(S.transcount + (size_t)wi * N + imol, 1);
+                // this lane's entries of imol's Verlet rows: in flight while the displacement is generated
+                const uint32_t e0 = __ldcg(w.list + (size_t)imol * LC + lane);
+                const uint32_t e1 = (NLAT == 2) ? (uint32_t)__ldcg(w.list + ((size_t)N + imol) * LC + lane) : 0u;
                 x = rng.draw();
                 double y = rng.draw();
                 double z = rng.draw();
@@ -654,7 +659,7 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
                     __syncwarp();
                 }
                 double eo[2] = {0.0, 0.0}, en[2] = {0.0, 0.0};
-                local_energies_warp<NLAT, true>(ref, w, imol, tlen0, tlen1, eo, en);
+                local_energies_warp<NLAT, true>(ref, w, imol, e0, e1, tlen0, tlen1, eo, en);
 
                 // model_energy bookkeeping exactly as :1013-1016, :1087-1090
                 const double Eb0 = sc->E[0], Eb1 = sc->E[1];
@@ -667,7 +672,7 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
                 if (NLAT == 1) {
                     diffkT = p.beta * dE0;
                     if (bins_on) {       // single box: ls_mu is never assigned (0) but the bins are still updated
-                        const EtaBin eb = eta_bin(p, S.mubin, S.binwidth, sc, wgt, mu_old);
+                        const EtaBin eb = eta_bin(p, S.mubin, S.ginv, sc, wgt, mu_old);
                         eta_acc = eta_rej = eb.eta; k_acc = k_rej = eb.k;
                     }
                 } else {
@@ -677,7 +682,7 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
                     // three weight look-ups in parallel lanes: eta(mu), eta(mu_acc), eta(mu_rej)
                     const double mine = (lane == 0) ? mu_old : (lane == 1) ? mu_acc : mu_rej;
                     EtaBin eb; eb.eta = 0.0; eb.k = 0;
-                    if (lane < 3) eb = eta_bin(p, S.mubin, S.binwidth, sc, wgt, mine);
+                    if (lane < 3) eb = eta_bin(p, S.mubin, S.ginv, sc, wgt, mine);
                     const double eta_old = __shfl_sync(FULL, eb.eta, 0);
                     eta_acc = __shfl_sync(FULL, eb.eta, 1); eta_rej = __shfl_sync(FULL, eb.eta, 2);
                     k_acc = __shfl_sync(FULL, eb.k, 1); k_rej = __shfl_sync(FULL, eb.k, 2);
@@ -717,7 +722,7 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
                 // ====================== mc_update_wl_bins (mc_moves.F90:1597-1689) ======================
                 const int kb = accepted ? k_acc : k_rej;
                 if (bins_on && kb >= 1 && kb <= p.nbins) {
-                    const double c = p.av_binwidth / __ldg(S.binwidth + kb - 1);
+                    const double c = __ldg(S.hinc + kb - 1);
                     if (lane == 0) atomicAdd(hist + kb - 1, c);
                     if (p.samplerun) {
                         const double uf = __shfl_sync(FULL, ex, accepted ? 3 : 4);
@@ -745,9 +750,9 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
             // ---------------- rare move types ----------------
             if (xi < p.volP) {
                 rng.pos = volume_move<NLAT>(ref, S, p, wi, rng.pos);
-                const EtaBin eb = eta_bin(p, S.mubin, S.binwidth, sc, wgt, sc->mu);
+                const EtaBin eb = eta_bin(p, S.mubin, S.ginv, sc, wgt, sc->mu);
                 if (bins_on && eb.k >= 1 && eb.k <= p.nbins) {
-                    const double c = p.av_binwidth / __ldg(S.binwidth + eb.k - 1);
+                    const double c = __ldg(S.hinc + eb.k - 1);
                     if (lane == 0) atomicAdd(hist + eb.k - 1, c);
                     if (p.samplerun) {
                         if (lane == 0) atomicAdd(uhist + eb.k - 1, c * exp(eb.eta - p.log_unbiased_norm));

@@ -153,7 +153,7 @@ extern "C" void mwgpu_destroy(mwgpu_ctx* c)
     DeviceState& S = c->S;
     void* ptrs[] = {S.pos, S.ref, S.cell, S.recip, S.refcell, S.iv, S.niv, S.list, S.nn, S.ten, S.disp, S.scal,
                     S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.transcount, S.mubin,
-                    S.binwidth, c->stage, c->out, c->iout, c->delta, c->fifo, c->sched};
+                    S.binwidth, S.ginv, S.hinc, c->stage, c->out, c->iout, c->delta, c->fifo, c->sched};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -421,7 +421,9 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
         const int i1 = (a.op == OP_LOCAL_ONE) ? a.imol + 1 : N;
         for (int i = i0; i < i1; ++i) {
             double eo[2] = {0, 0}, en[2] = {0, 0};
-            local_energies_warp<NLAT, false>(ref, w, i, 0.f, 0.f, eo, en);
+            const uint32_t e0 = __ldcg(w.list + (size_t)i * LC + lane);
+            const uint32_t e1 = (NLAT == 2) ? (uint32_t)__ldcg(w.list + ((size_t)N + i) * LC + lane) : 0u;
+            local_energies_warp<NLAT, false>(ref, w, i, e0, e1, 0.f, 0.f, eo, en);
             if (lane == 0) a.out[i - i0] = (a.lat == 0) ? eo[0] : eo[1];
         }
         break;
@@ -795,17 +797,24 @@ extern "C" int mwgpu_mc_init(mwgpu_ctx* c, const mwgpu_mc_params* up, int first_
 
     // ---- (re)allocate per-walker bin arrays
     DeviceState& S = c->S;
-    void* old[] = {S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.mubin, S.binwidth, c->delta};
+    void* old[] = {S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.mubin, S.binwidth, S.ginv, S.hinc, c->delta};
     for (void* p : old) if (p) cudaFree(p);
     S.NB = nb;
     int rc = 0;
     rc |= dalloc(&S.weight, (size_t)W * nb); rc |= dalloc(&S.hist, (size_t)W * nb); rc |= dalloc(&S.uhist, (size_t)W * nb);
     rc |= dalloc(&S.wbase, (size_t)W * nb); rc |= dalloc(&S.hbase, (size_t)W * nb); rc |= dalloc(&S.ubase, (size_t)W * nb);
-    rc |= dalloc(&S.mubin, nb); rc |= dalloc(&S.binwidth, nb);
+    rc |= dalloc(&S.mubin, nb); rc |= dalloc(&S.binwidth, nb); rc |= dalloc(&S.ginv, nb); rc |= dalloc(&S.hinc, nb);
     rc |= dalloc(&c->delta, (size_t)3 * c->NBP);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpy(S.mubin, mu_bin.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(S.binwidth, bw.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
+    {
+        std::vector<double> ginv(nb, 0.0);
+        for (int k = 0; k + 1 < nb; ++k) ginv[k] = 2.0 / (bw[k] + bw[k + 1]);
+        CUDA_TRY(cudaMemcpy(S.ginv, ginv.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
+        for (int k = 0; k < nb; ++k) ginv[k] = av_bw / bw[k];
+        CUDA_TRY(cudaMemcpy(S.hinc, ginv.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
+    }
 
     // ---- per-walker scalars: windows (:659-722), ref_enthalpy (main.f90:146-150), mu (:857-862)
     std::vector<WalkerScalars> h(W);
@@ -889,6 +898,7 @@ extern "C" int mwgpu_mc_init(mwgpu_ctx* c, const mwgpu_mc_params* up, int first_
     P.r_pos = r_pos; P.r_neg = r_neg; P.a_pos = a_pos; P.a_neg = a_neg;
     P.log_r_pos = std::log(r_pos); P.log_r_neg = std::log(r_neg);
     P.inv_log_r_pos = 1.0 / P.log_r_pos; P.inv_log_r_neg = 1.0 / P.log_r_neg;
+    P.c_pos = (1.0 - r_pos) / a_pos; P.c_neg = (1.0 - r_neg) / a_neg;
     P.av_binwidth = av_bw; P.log_unbiased_norm = lun;
     P.mu_min = u.mu_min; P.mu_max = u.mu_max;
     P.orig_wl_factor = orig_wl_factor; P.wl_alpha = u.wl_alpha;
