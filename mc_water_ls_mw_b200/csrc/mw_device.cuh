@@ -266,7 +266,7 @@ struct WalkerView {
     double*   iv;      // [nlat][3][IVC]
     double*   cell;    // [nlat][9]      hmatrix, column-major
     double*   recip;   // [nlat][9]
-    double*   q;       // [4][QC] scratch: tx,ty,tz,r2 -> ux,uy,uz,g
+    double*   q;       // [6][QC] scratch: tx,ty,tz,r2 -> ux,uy,uz,g; row 4 = 1.0; row 5 = [g > GSAFE]
     double*   ti;      // [4][TS] bond tensors of the moved molecule, one per evaluation
     double*   pn;      // [2][3]  trial position of the moved molecule
     double*   tv;      // [2][3]  trial displacement
@@ -290,7 +290,7 @@ struct WalkerView {
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t smem_doubles(int N, int nlat)
 {
-    return (size_t)nlat * 3 * N + (size_t)nlat * 3 * IVC + (size_t)nlat * 18 + 4 * QC + 4 * TS + 12 + 36 + RB + 2;
+    return (size_t)nlat * 3 * N + (size_t)nlat * 3 * IVC + (size_t)nlat * 18 + 6 * QC + 4 * TS + 12 + 36 + RB + 2;
 }
 
 // Layout (every block 16-byte aligned): doubles | scalars | 32-bit words | 16-bit words | bytes
@@ -314,7 +314,7 @@ __device__ __forceinline__ WalkerView carve_walker(unsigned char* base, int N, i
     w.cell   = w.iv + (size_t)nlat * 3 * IVC;
     w.recip  = w.cell + (size_t)nlat * 9;
     w.q      = w.recip + (size_t)nlat * 9;
-    w.ti     = w.q + 4 * QC;
+    w.ti     = w.q + 6 * QC;
     w.pn     = w.ti + 4 * TS;
     w.tv     = w.pn + 6;
     w.save   = w.tv + 6;
@@ -390,10 +390,29 @@ __device__ __forceinline__ int inverse_image(int img, int nv)
 
 // ---------------------------------------------------------------- Verlet list
 // molint.F90:501-559: brute force over (j, image k), emitted in j-ascending,
-// k-ascending order.  Lanes own molecules j; each lane walks the images and
-// keeps a bit mask; entries are then emitted in lane order.  The exact test
-// (tx^2 + ty^2) + tz^2 < rn^2 is monotone in each term, so an image whose
-// tx^2 alone reaches rn^2 is skipped without changing any decision.
+// k-ascending order.  Lanes own molecules j; every lane tests its candidate images and keeps a
+// bit mask; entries are then emitted in lane order.
+//
+// Candidate images: with b_a the reciprocal vectors of the cell (b_a . h_b = delta_ab), the image
+// displaced by n = (n1,n2,n3) cells has |t| >= |b_a.v + n_a| / |b_a| for every axis a, so only
+// n_a with |b_a.v + n_a| < rn |b_a| (widened by 1e-9) can pass the exact test; the box of those
+// n (typically 1-2 of the 27 images) is evaluated with the reference's exact arithmetic.
+__host__ __device__ constexpr uint32_t image_axis_mask(int axis, int n)      // images k (0..26) whose cell offset along `axis` is n
+{
+    uint32_t m = 0;
+    for (int k = 0; k < 27; ++k) {
+        const int f = (k == 0) ? 13 : (k <= 13 ? k - 1 : k);
+        const int c = (axis == 0) ? f / 9 - 1 : (axis == 1) ? (f / 3) % 3 - 1 : f % 3 - 1;
+        if (c == n) m |= 1u << k;
+    }
+    return m;
+}
+
+__device__ __forceinline__ uint32_t axis_candidates(double s, double R, uint32_t mm, uint32_t m0, uint32_t mp)
+{
+    return (fabs(s - 1.0) < R ? mm : 0u) | (fabs(s) < R ? m0 : 0u) | (fabs(s + 1.0) < R ? mp : 0u);
+}
+
 __device__ __noinline__ int compute_neighbours_warp(WalkerRef ref, int lat)
 {
     int err = compute_ivects_warp(ref, lat);                    // molint.F90:518
@@ -404,22 +423,46 @@ __device__ __noinline__ int compute_neighbours_warp(WalkerRef ref, int lat)
     const int nv = w.niv[lat];
     const double* P = w.pos + lat * 3 * N;
     const double* V = w.iv + lat * 3 * IVC;
+    // reciprocal vectors (plain arithmetic: they only select candidates)
+    const double* h = w.cell + 9 * lat;
+    double b[9];
+    b[0] = h[4] * h[8] - h[5] * h[7]; b[1] = h[5] * h[6] - h[3] * h[8]; b[2] = h[3] * h[7] - h[4] * h[6];
+    b[3] = h[7] * h[2] - h[8] * h[1]; b[4] = h[8] * h[0] - h[6] * h[2]; b[5] = h[6] * h[1] - h[7] * h[0];
+    b[6] = h[1] * h[5] - h[2] * h[4]; b[7] = h[2] * h[3] - h[0] * h[5]; b[8] = h[0] * h[4] - h[1] * h[3];
+    const double idet = 1.0 / (h[0] * b[0] + h[1] * b[1] + h[2] * b[2]);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) b[k] *= idet;
+    const double R0 = RN * (1.0 + 1e-9) * sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]) + 1e-12;
+    const double R1 = RN * (1.0 + 1e-9) * sqrt(b[3] * b[3] + b[4] * b[4] + b[5] * b[5]) + 1e-12;
+    const double R2 = RN * (1.0 + 1e-9) * sqrt(b[6] * b[6] + b[7] * b[7] + b[8] * b[8]) + 1e-12;
+    const bool boxed = (nv == 27);                              // always, unless the image set is degenerate
+#pragma unroll 1
     for (int i = 0; i < N; ++i) {
         const double ix = P[i], iy = P[N + i], iz = P[2 * N + i];
         int total = 0;
+#pragma unroll 1
         for (int jb = 0; jb < N; jb += 32) {
             const int j = jb + lane;
             uint32_t m = 0;
             if (j < N) {
                 const double vx = xs(P[j], ix), vy = xs(P[N + j], iy), vz = xs(P[2 * N + j], iz);
-                for (int k = 0; k < nv; ++k) {
-                    const double tx = xa(vx, V[k]);
-                    const double xx = xm(tx, tx);
-                    if (xx < RN2) {
-                        const double ty = xa(vy, V[IVC + k]), tz = xa(vz, V[2 * IVC + k]);
-                        const double r2 = xa(xa(xx, xm(ty, ty)), xm(tz, tz));
-                        if (r2 < RN2) m |= 1u << k;
-                    }
+                uint32_t cand = lowbits(nv);
+                if (boxed) {
+                    // the image k adds n = +cell offset; |b.v + n| < R  (n = -1, 0, +1)
+                    const double s0 = b[0] * vx + b[1] * vy + b[2] * vz;
+                    const double s1 = b[3] * vx + b[4] * vy + b[5] * vz;
+                    const double s2 = b[6] * vx + b[7] * vy + b[8] * vz;
+                    constexpr uint32_t A0 = image_axis_mask(0, -1), A1 = image_axis_mask(0, 0), A2 = image_axis_mask(0, 1);
+                    constexpr uint32_t B0 = image_axis_mask(1, -1), B1 = image_axis_mask(1, 0), B2 = image_axis_mask(1, 1);
+                    constexpr uint32_t C0 = image_axis_mask(2, -1), C1 = image_axis_mask(2, 0), C2 = image_axis_mask(2, 1);
+                    cand = axis_candidates(s0, R0, A0, A1, A2) & axis_candidates(s1, R1, B0, B1, B2) & axis_candidates(s2, R2, C0, C1, C2);
+                }
+#pragma unroll 1
+                while (cand) {
+                    const int k = __ffs(cand) - 1; cand &= cand - 1;
+                    const double tx = xa(vx, V[k]), ty = xa(vy, V[IVC + k]), tz = xa(vz, V[2 * IVC + k]);
+                    const double r2 = xa(xa(xm(tx, tx), xm(ty, ty)), xm(tz, tz));
+                    if (r2 < RN2) m |= 1u << k;
                 }
                 if (j == i) {
                     m &= ~1u;                                   // (k==1).and.(jmol==imol) cycle
@@ -435,6 +478,7 @@ __device__ __noinline__ int compute_neighbours_warp(WalkerRef ref, int lat)
             }
             int off = total + incl - cnt;
             uint16_t* row = w.list + ((size_t)lat * N + i) * LC;
+#pragma unroll 1
             while (m) {
                 const int k = __ffs(m) - 1; m &= m - 1;
                 if (off < LC) row[off] = (uint16_t)((k << 10) | j);
@@ -468,6 +512,7 @@ __device__ __forceinline__ double eval_bond(double* q, int r)
     const double g = e_4 * e_2;
     const double s2 = SS * ir * ir;
     q[r] = tx * ir; q[QC + r] = ty * ir; q[2 * QC + r] = tz * ir; q[3 * QC + r] = g;
+    q[5 * QC + r] = (g > GSAFE) ? 1.0 : 0.0;
     return AEPS * (BIGB * (s2 * s2) - 1.0) * e2;
 }
 
@@ -526,26 +571,26 @@ __device__ __forceinline__ double ten_term(int comp, double ux, double uy, doubl
     return g * a * b;
 }
 
-// The same for lanes that each own one component (comp is lane-dependent): branch-free operand
-// selection by shared-memory row.  TenSel: rows of the two factors (offsets into q; the constant 1
-// is encoded as one = true) and the kind of component.
-struct TenSel { int offa, offb; bool onea, oneb; int mode; };      // mode 0: g*a*b, 1: [g > GSAFE], 2: 0
+// The same for lanes that each own one component (comp is lane-dependent): three shared-memory
+// rows per component, product of their entries.  Rows: 0..2 = ux,uy,uz, 3 = g, 4 = 1, 5 = [g > GSAFE].
+struct TenSel { int offg, offa, offb; };
 __device__ __forceinline__ TenSel ten_sel(int comp)
 {
-    const int ia = (comp < 3 || comp == 6) ? 0 : (comp == 3 || comp == 4 || comp == 7) ? 1 : (comp == 5 || comp == 8) ? 2 : 3;
-    const int ib = (comp == 0) ? 0 : (comp == 1 || comp == 3) ? 1 : (comp == 2 || comp == 4 || comp == 5) ? 2 : 3;
+    const int ia = (comp < 3 || comp == 6) ? 0 : (comp == 3 || comp == 4 || comp == 7) ? 1 : (comp == 5 || comp == 8) ? 2 : 4;
+    const int ib = (comp == 0) ? 0 : (comp == 1 || comp == 3) ? 1 : (comp == 2 || comp == 4 || comp == 5) ? 2 : 4;
     TenSel t;
-    t.onea = ia == 3; t.oneb = ib == 3;
-    t.offa = t.onea ? 0 : ia * QC; t.offb = t.oneb ? 0 : ib * QC;
-    t.mode = (comp < 10) ? 0 : (comp == 10) ? 1 : 2;
+    t.offg = (comp < 10 ? 3 : 5) * QC; t.offa = ia * QC; t.offb = ib * QC;     // comp 11 (pad) repeats comp 10
     return t;
 }
 __device__ __forceinline__ double ten_term_sel(const TenSel& t, const double* q, int c)
 {
-    const double g = q[3 * QC + c];
-    const double a = q[t.offa + c], b = q[t.offb + c];
-    const double v = g * (t.onea ? 1.0 : a) * (t.oneb ? 1.0 : b);
-    return (t.mode == 0) ? v : ((t.mode == 1 && g > GSAFE) ? 1.0 : 0.0);
+    return q[t.offg + c] * q[t.offa + c] * q[t.offb + c];
+}
+// row 4 of q: set once per kernel
+__device__ __forceinline__ void init_ones_row(double* q)
+{
+    for (int c = lane_id(); c < QC; c += 32) q[4 * QC + c] = 1.0;
+    __syncwarp();
 }
 
 struct Ten {

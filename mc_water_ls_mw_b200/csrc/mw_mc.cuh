@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
                         S.disp + (size_t)wi * NLAT * N, N, NLAT};
     const WalkerView w = ref.view();
     load_walker(S, wi, w);
+    init_ones_row(w.q);
     WalkerScalars* sc = w.sc;
     double* wgt = S.weight + (size_t)wi * S.NB;
     double* hist = S.hist + (size_t)wi * S.NB;

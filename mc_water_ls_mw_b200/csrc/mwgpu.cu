@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
                         S.disp + (size_t)wi * NLAT * N, N, NLAT};
     const WalkerView w = ref.view();
     load_walker(S, wi, w);
+    init_ones_row(w.q);
     WalkerScalars* sc = w.sc;
     int err = 0;
 
@@ -677,6 +678,7 @@ __global__ void __launch_bounds__(32) k_model_energy_all(const __grid_constant__
     const uint8_t* gn = S.nn + ((size_t)wi * S.nlat + lat) * N;
     for (int t = lane; t < N; t += 32) w.nn[t] = gn[t];
     __syncwarp();
+    init_ones_row(w.q);
     const double e = full_energy_warp(ref, 0, 1);
     if (lane == 0) {
         S.scal[wi].E[lat] = e;
