@@ -207,7 +207,7 @@ __device__ __forceinline__ void philox_block(uint64_t seed, uint32_t stream, uin
 {
     uint32_t c0 = (uint32_t)block, c1 = (uint32_t)(block >> 32), c2 = stream, c3 = 0u;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
@@ -735,7 +735,7 @@ __device__ __noinline__ double jcentre_enum_warp(WalkerRef ref, int imol, int re
 }
 
 // Inputs in shared memory: w.pn (trial position per lattice, WITH_NEW), w.cxs[CX_DISP..] is written here.
-// tlen0/tlen1: length of the trial displacement per lattice (guard).  Results: eo/en (uniform).
+// tlen0/tlen1: SQUARED length of the trial displacement per lattice, rounded up (guard).  Results: eo/en (uniform).
 // e0/e1: this lane's entry of imol's Verlet row in lattice 1/2 (loaded early by the caller).
 template <int NLAT, bool WITH_NEW>
 __device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerView& w, int imol, uint32_t e0, uint32_t e1,
@@ -804,9 +804,14 @@ __device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerV
     }
 
     // ---- which path?  (uniform over the warp)
+    // guard: rn_eff - disp(imol) - |trial displacement| - dmax > RSAFE, with the trial length squared
     const float margin = (float)(RSAFE * 1.0001);
-    bool guard = sc->rn_eff[0] - disp0 - (WITH_NEW ? tlen0 : 0.f) - sc->dmax[0] > margin;
-    if (NLAT == 2) guard = guard && (sc->rn_eff[1] - disp1 - (WITH_NEW ? tlen1 : 0.f) - sc->dmax[1] > margin);
+    const float room0 = sc->rn_eff[0] - disp0 - sc->dmax[0] - margin;
+    bool guard = room0 > 0.f && (!WITH_NEW || tlen0 < room0 * room0);
+    if (NLAT == 2) {
+        const float room1 = sc->rn_eff[1] - disp1 - sc->dmax[1] - margin;
+        guard = guard && room1 > 0.f && (!WITH_NEW || tlen1 < room1 * room1);
+    }
     const bool forced = sc->force_exact || !sc->tensors_valid;
     const bool fast = guard && !forced;
     cxs[CX_NQ] = nq; cxs[CX_FAST] = fast;
