@@ -177,17 +177,6 @@ int  mwgpu_mc_monitor(mwgpu_ctx *ctx);
 /* mc_check_chain_synchronisation (mc_moves.F90:2217-2416), all walkers */
 int  mwgpu_mc_chain_sync(mwgpu_ctx *ctx);
 
-/* ---- evaluation path of compute_local_real_energy inside the moves (no reference counterpart) ----
- * The kernel evaluates the three-body part of a trial move through cached per-molecule bond tensors
- * whenever that is provably identical to the reference's enumeration, and through
- * the enumeration itself otherwise.  exact != 0 forces the enumeration for every move (walker -1: all). */
-int  mwgpu_mc_set_exact_enumeration(mwgpu_ctx *ctx, int walker, int exact);
-/* local-energy evaluations (trial moves / fine-grained calls) of this walker since mwgpu_mc_init or the
- * last mwgpu_mc_monitor: counts[0] through the tensor path; through the enumeration because of
- * counts[1] (unused), [2] a pair closer than 2.2 Ang near the moved molecule, [3] the displacement
- * guard of stale lists, [4] forced / cache invalid */
-int  mwgpu_mc_get_path_counts(mwgpu_ctx *ctx, int walker, int *counts /* [5] */);
-
 /* ---- comms (comms_mpi.f90:244-277, :461-530): delta-since-last-sync all-reduce ----- */
 /* Sums the increments of weight / histogram / (samplerun) unbiased_hist over all walkers of the
  * context and, when mwgpu_comms_init() was called, over all ranks with one NCCL all-reduce on

@@ -92,8 +92,6 @@ SYMBOLS = {
     "mwgpu_mc_set_active_lattice": (_i, [_vp, _i, _i]),
     "mwgpu_mc_monitor": (_i, [_vp]),
     "mwgpu_mc_chain_sync": (_i, [_vp]),
-    "mwgpu_mc_set_exact_enumeration": (_i, [_vp, _i, _i]),
-    "mwgpu_mc_get_path_counts": (_i, [_vp, _i, _ip]),
     "mwgpu_comms_allreduce_bins": (_i, [_vp]),
     "mwgpu_comms_set_hist_base": (_i, [_vp, _dp, _dp]),
     "mwgpu_comms_get_unique_id": (_i, [_vp]),

@@ -44,22 +44,12 @@ constexpr double AEPS    = BIGA * EPSILON;
 constexpr double LEPS    = LAMBDA * EPSILON;
 constexpr double SS      = SIGMA * SIGMA;
 constexpr double F_HUGE  = 1.7976931348623157e308;
-constexpr double C0SQ    = COS0 * COS0;
-constexpr double OMC0SQ  = (1.0 - COS0) * (1.0 - COS0);
-// Two legs of length <= a*sigma at a common centre can only enclose cos(theta) >= 0.99 (the
-// reference's k==i filter, molint.F90:367) when two of the three molecules are closer than
-// a*sigma/1.98 = 2.175 Ang.  The tensor path is used only while every such pair is provably
-// farther apart than RSAFE; otherwise the exact enumeration decides.
-constexpr double RSAFE   = 2.2 * ANG_TO_BOHR;
-constexpr double RSAFE2  = RSAFE * RSAFE;
-constexpr double GSAFE   = 0.2559113248062053;     // exp(gamma*sigma/(RSAFE - a*sigma)): g > GSAFE <=> r < RSAFE
 
 // ---------------------------------------------------------------- capacities
 constexpr int LC  = 32;    // list slots per molecule held in shared memory (one lane per slot)
 constexpr int IVC = 32;    // image vectors per lattice (27 in every BASELINE config)
 constexpr int QC  = 64;    // bond records per batch (a trial move has ~26; more than QC in-range bonds -> ERR_BOND_OVERFLOW)
-constexpr int MC  = 32;    // molecules per full-energy chunk
-constexpr int TS  = 12;    // doubles per molecule bond tensor: Txx,Txy,Txz,Tyy,Tyz,Tzz, Vx,Vy,Vz, G, nshort, pad
+constexpr int CC  = 64;    // triplet centres per trial move: 2 lattices x LC slots
 constexpr int RB  = 64;    // random numbers buffered per refill
 constexpr int NMAX = 1024; // molecules (10 bits of a packed list entry)
 constexpr unsigned FULL = 0xffffffffu;
@@ -85,9 +75,6 @@ __device__ __forceinline__ double xd(double a, double b) { return __ddiv_rn(a, b
 __device__ __forceinline__ double xsqrt(double a) { return __dsqrt_rn(a); }
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-// register-resident small arrays: select instead of dynamic indexing (which would spill them to local memory)
-__device__ __forceinline__ int pick4(int i, const int* a) { return (i == 0) ? a[0] : (i == 1) ? a[1] : (i == 2) ? a[2] : a[3]; }
-__device__ __forceinline__ uint32_t pick2(int i, const uint32_t* a) { return i ? a[1] : a[0]; }
 __device__ __forceinline__ unsigned lowbits(int n) { return (n >= 32) ? 0xffffffffu : ((1u << n) - 1u); }
 __device__ __forceinline__ unsigned lt_mask() { return (1u << (threadIdx.x & 31)) - 1u; }
 
@@ -247,16 +234,6 @@ struct WalkerScalars {
     int wl_invt_active;
     int wmin_zero;          // invariant "min(weight(window)) == 0" established
     int error;
-    // ---- state of the bond-tensor cache
-    float rn_eff[2];        // lower bound on the separation unlisted pairs had at the last list build,
-                            // shrunk by every accepted volume move since
-    float dmax[2];          // max over molecules of the path length moved since the last list build
-    int tensors_valid;      // gten / close_contact describe the current positions and lists
-    int unused0_;
-    int force_exact;        // always use the exact enumeration (testing aid)
-    int fast_moves;         // trial moves evaluated through the tensor path (diagnostic)
-    int slow_moves[4];      // ... through the enumeration because of: >QC/dup-image, close contact, guard, forced
-    int pad_;
 };
 
 // ---------------------------------------------------------------- shared-memory view of one walker
@@ -266,86 +243,76 @@ struct WalkerView {
     double*   iv;      // [nlat][3][IVC]
     double*   cell;    // [nlat][9]      hmatrix, column-major
     double*   recip;   // [nlat][9]
-    double*   q;       // [6][QC] scratch: tx,ty,tz,r2 -> ux,uy,uz,g; row 4 = 1.0; row 5 = [g > GSAFE]
-    double*   ti;      // [4][TS] bond tensors of the moved molecule, one per evaluation
-    double*   pn;      // [2][3]  trial position of the moved molecule
-    double*   tv;      // [2][3]  trial displacement
+    double*   q;       // [4][QC] scratch: tx,ty,tz,r2 -> ux,uy,uz,g
     double*   save;    // [36]    old cell + recip during a volume move
     double*   rngbuf;  // [RB]    buffered U[0,1) numbers
     double*   lv;      // [2]     log(V1/V2), log(V2/V1)
     WalkerScalars* sc;
     uint64_t* rngbase; // draw index of rngbuf[0]
-    uint32_t* qmeta;   // [QC]   evaluation | slot<<2 | j<<8   (full energy: end of the molecule's segment)
-    uint32_t* qgrp;    // [QC]   slots of imol's list that are bonded images of the same molecule j (incl. own)
-    uint32_t* cxs;     // [16]   per-move uniforms: see CX_* below
+    uint32_t* qmeta;   // [QC]   call | j<<8
+    uint32_t* cmeta;   // [CC]   lat | j<<6
+    uint32_t* bmask;   // [nlat][N] bit s: list slot s currently within the cut-off a*sigma
     int*      niv;     // [2]
-    uint16_t* seg;     // [MC+2] record offsets of the molecules of a full-energy chunk
+    uint16_t* cq;      // [CC][2] bond record of the centre in the old / new variant
+    uint16_t* cpre;    // [CC+2]  exclusive prefix of the per-centre bond counts
+    uint16_t* list;    // [nlat][N][LC] packed entries img<<10 | j   (0-based)
     uint8_t*  nn;      // [nlat][N]
-    // global memory of this walker (L2-resident; read with ld.cg: another SM may have written it)
-    uint16_t* list;    // [nlat][N][LC] packed Verlet entries img<<10 | j   (0-based)
-    double*   gten;    // [nlat][N][TS] per-molecule bond tensors
-    float*    gdisp;   // [nlat][N] path length moved since the last list build
 };
 
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t smem_doubles(int N, int nlat)
 {
-    return (size_t)nlat * 3 * N + (size_t)nlat * 3 * IVC + (size_t)nlat * 18 + 6 * QC + 4 * TS + 12 + 36 + RB + 2;
+    return (size_t)nlat * 3 * N + (size_t)nlat * 3 * IVC + (size_t)nlat * 18 + 4 * QC + 36 + RB + 2;
 }
 
-// Layout (every block 16-byte aligned): doubles | scalars | 32-bit words | 16-bit words | bytes
+// Layout (every block 16-byte aligned): doubles | scalars | list | 32-bit words | 16-bit words | bytes
 __host__ __device__ inline size_t walker_smem_bytes(int N, int nlat)
 {
     size_t b = 0;
     b += align16(sizeof(double) * smem_doubles(N, nlat));
     b += align16(sizeof(WalkerScalars) + sizeof(uint64_t));
-    b += align16(sizeof(uint32_t) * (2 * QC + 16 + 2));                           // qmeta, qgrp, cxs, niv
-    b += align16(sizeof(uint16_t) * (MC + 2));                                    // seg
+    b += align16(sizeof(uint16_t) * (size_t)nlat * N * LC);                       // list
+    b += align16(sizeof(uint32_t) * (QC + CC + (size_t)nlat * N + 2));            // qmeta, cmeta, bmask, niv
+    b += align16(sizeof(uint16_t) * (CC * 2 + CC + 2));                           // cq, cpre
     b += align16((size_t)nlat * N);                                               // nn
     return b;
 }
 
-__device__ __forceinline__ WalkerView carve_walker(unsigned char* base, int N, int nlat, uint16_t* glist, double* gten, float* gdisp)
+__device__ __forceinline__ WalkerView carve_walker(unsigned char* base, int N, int nlat)
 {
-    WalkerView w; w.N = N; w.nlat = nlat; w.list = glist; w.gten = gten; w.gdisp = gdisp;
+    WalkerView w; w.N = N; w.nlat = nlat;
     unsigned char* p = base;
     w.pos    = (double*)p;
     w.iv     = w.pos + (size_t)nlat * 3 * N;
     w.cell   = w.iv + (size_t)nlat * 3 * IVC;
     w.recip  = w.cell + (size_t)nlat * 9;
     w.q      = w.recip + (size_t)nlat * 9;
-    w.ti     = w.q + 6 * QC;
-    w.pn     = w.ti + 4 * TS;
-    w.tv     = w.pn + 6;
-    w.save   = w.tv + 6;
+    w.save   = w.q + 4 * QC;
     w.rngbuf = w.save + 36;
     w.lv     = w.rngbuf + RB;
     p += align16(sizeof(double) * smem_doubles(N, nlat));
     w.sc      = (WalkerScalars*)p;
     w.rngbase = (uint64_t*)(p + sizeof(WalkerScalars));
     p += align16(sizeof(WalkerScalars) + sizeof(uint64_t));
+    w.list  = (uint16_t*)p;
+    p += align16(sizeof(uint16_t) * (size_t)nlat * N * LC);
     w.qmeta = (uint32_t*)p;
-    w.qgrp  = w.qmeta + QC;
-    w.cxs   = w.qgrp + QC;
-    w.niv   = (int*)(w.cxs + 16);
-    p += align16(sizeof(uint32_t) * (2 * QC + 16 + 2));
-    w.seg   = (uint16_t*)p;
-    p += align16(sizeof(uint16_t) * (MC + 2));
+    w.cmeta = w.qmeta + QC;
+    w.bmask = w.cmeta + CC;
+    w.niv   = (int*)(w.bmask + (size_t)nlat * N);
+    p += align16(sizeof(uint32_t) * (QC + CC + (size_t)nlat * N + 2));
+    w.cq    = (uint16_t*)p;
+    w.cpre  = w.cq + CC * 2;
+    p += align16(sizeof(uint16_t) * (CC * 2 + CC + 2));
     w.nn    = (uint8_t*)p;
     return w;
 }
 
-// What the __noinline__ routines need to rebuild a WalkerView (passed in registers)
-struct WalkerRef {
-    unsigned char* smem; uint16_t* glist; double* gten; float* gdisp; int N, nlat;
-    __device__ __forceinline__ WalkerView view() const { return carve_walker(smem, N, nlat, glist, gten, gdisp); }
-};
-
 // ---------------------------------------------------------------- image vectors
 // molint.F90:174-217.  Lane k builds vector k.  Returns error bits.
-__device__ __noinline__ int compute_ivects_warp(WalkerRef ref, int lat)
+__device__ __noinline__ int compute_ivects_warp(unsigned char* smem, int N, int nlat, int lat)
 {
-    const WalkerView w = ref.view();
+    const WalkerView w = carve_walker(smem, N, nlat);
     const double* h = w.cell + 9 * lat;
     const double l1 = xsqrt(xa(xa(xm(h[0], h[0]), xm(h[1], h[1])), xm(h[2], h[2])));
     const double l2 = xsqrt(xa(xa(xm(h[3], h[3]), xm(h[4], h[4])), xm(h[5], h[5])));
@@ -413,12 +380,11 @@ __device__ __forceinline__ uint32_t axis_candidates(double s, double R, uint32_t
     return (fabs(s - 1.0) < R ? mm : 0u) | (fabs(s) < R ? m0 : 0u) | (fabs(s + 1.0) < R ? mp : 0u);
 }
 
-__device__ __noinline__ int compute_neighbours_warp(WalkerRef ref, int lat)
+__device__ __noinline__ int compute_neighbours_warp(unsigned char* smem, int N, int nlat, int lat)
 {
-    int err = compute_ivects_warp(ref, lat);                    // molint.F90:518
+    int err = compute_ivects_warp(smem, N, nlat, lat);          // molint.F90:518
     if (err) return err;
-    const WalkerView w = ref.view();
-    const int N = w.N;
+    const WalkerView w = carve_walker(smem, N, nlat);
     const int lane = lane_id();
     const int nv = w.niv[lat];
     const double* P = w.pos + lat * 3 * N;
@@ -494,6 +460,30 @@ __device__ __noinline__ int compute_neighbours_warp(WalkerRef ref, int lat)
     return err;
 }
 
+// ---------------------------------------------------------------- bond masks
+// bmask[lat][a] bit s <=> slot s of a's list is inside the cut-off (r^2 < rcsq,
+// molint.F90:276/454).  Lanes are the slots.
+__device__ __noinline__ void compute_bond_masks_warp(unsigned char* smem, int N, int nlat, int lat)
+{
+    const WalkerView w = carve_walker(smem, N, nlat);
+    const int lane = lane_id();
+    const double* P = w.pos + lat * 3 * N;
+    const double* V = w.iv + lat * 3 * IVC;
+    for (int a = 0; a < N; ++a) {
+        const int nna = w.nn[lat * N + a];
+        const bool has = lane < nna;
+        const uint32_t e = has ? w.list[((size_t)lat * N + a) * LC + lane] : 0u;
+        const int j = e & 1023, img = e >> 10;
+        const double tx = (P[j] + V[img]) - P[a];
+        const double ty = (P[N + j] + V[IVC + img]) - P[N + a];
+        const double tz = (P[2 * N + j] + V[2 * IVC + img]) - P[2 * N + a];
+        const double r2 = tx * tx + ty * ty + tz * tz;
+        const uint32_t m = __ballot_sync(FULL, has && r2 < RCSQ);
+        if (lane == 0) w.bmask[lat * N + a] = m;
+    }
+    __syncwarp();
+}
+
 // ---------------------------------------------------------------- energy kernels (free-form fp64)
 // Pair record evaluation shared by the local and the full energy:
 //   in : q[0..2][r] = separation vector t, q[3][r] = r^2
@@ -512,7 +502,6 @@ __device__ __forceinline__ double eval_bond(double* q, int r)
     const double g = e_4 * e_2;
     const double s2 = SS * ir * ir;
     q[r] = tx * ir; q[QC + r] = ty * ir; q[2 * QC + r] = tz * ir; q[3 * QC + r] = g;
-    q[5 * QC + r] = (g > GSAFE) ? 1.0 : 0.0;
     return AEPS * (BIGB * (s2 * s2) - 1.0) * e2;
 }
 
@@ -556,80 +545,21 @@ __device__ __forceinline__ double warp_sum(double a)
     return a;
 }
 
-// ---------------------------------------------------------------- bond tensors
-// For every molecule m of a lattice, over the list entries k of m inside the cut-off
-// (unit vector u_mk, radial factor g_mk = exp(gamma*sigma/(r_mk - a*sigma))):
-//     T = sum g u u^T (6 numbers), V = sum g u, G = sum g.
-// The three-body sum over one leg set collapses to a quadratic form:
-//     sum_k g_k (c*u.u_k - cos0)^2 = u^T T u - 2 c cos0 u.V + cos0^2 G,   c = +-1.
-// Component `comp` of the contribution of one bond (g, u):
-__device__ __forceinline__ double ten_term(int comp, double ux, double uy, double uz, double g)
+// position of the (rank+1)-th set bit of m (rank < popc(m))
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int rank)
 {
-    if (comp >= 10) return (comp == 10 && g > GSAFE) ? 1.0 : 0.0;       // number of bonds shorter than RSAFE
-    const double a = (comp < 3 || comp == 6) ? ux : (comp == 3 || comp == 4 || comp == 7) ? uy : (comp == 9) ? 1.0 : uz;
-    const double b = (comp == 0) ? ux : (comp == 1 || comp == 3) ? uy : (comp == 2 || comp == 4 || comp == 5) ? uz : 1.0;
-    return g * a * b;
+    int pos = 0;
+    int c = __popc(m & 0xffffu);
+    if (rank >= c) { rank -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xffu);
+    if (rank >= c) { rank -= c; pos += 8; m >>= 8; }
+    c = __popc(m & 0xfu);
+    if (rank >= c) { rank -= c; pos += 4; m >>= 4; }
+    c = __popc(m & 0x3u);
+    if (rank >= c) { rank -= c; pos += 2; m >>= 2; }
+    if (rank >= (int)(m & 1u)) pos += 1;
+    return pos;
 }
-
-// The same for lanes that each own one component (comp is lane-dependent): three shared-memory
-// rows per component, product of their entries.  Rows: 0..2 = ux,uy,uz, 3 = g, 4 = 1, 5 = [g > GSAFE].
-struct TenSel { int offg, offa, offb; };
-__device__ __forceinline__ TenSel ten_sel(int comp)
-{
-    const int ia = (comp < 3 || comp == 6) ? 0 : (comp == 3 || comp == 4 || comp == 7) ? 1 : (comp == 5 || comp == 8) ? 2 : 4;
-    const int ib = (comp == 0) ? 0 : (comp == 1 || comp == 3) ? 1 : (comp == 2 || comp == 4 || comp == 5) ? 2 : 4;
-    TenSel t;
-    t.offg = (comp < 10 ? 3 : 5) * QC; t.offa = ia * QC; t.offb = ib * QC;     // comp 11 (pad) repeats comp 10
-    return t;
-}
-__device__ __forceinline__ double ten_term_sel(const TenSel& t, const double* q, int c)
-{
-    return q[t.offg + c] * q[t.offa + c] * q[t.offb + c];
-}
-// row 4 of q: set once per kernel
-__device__ __forceinline__ void init_ones_row(double* q)
-{
-    for (int c = lane_id(); c < QC; c += 32) q[4 * QC + c] = 1.0;
-    __syncwarp();
-}
-
-struct Ten {
-    double xx, xy, xz, yy, yz, zz, vx, vy, vz, g, ns;
-    __device__ __forceinline__ void load(const double* p)     // 16-byte aligned, L2 (the same warp updates it)
-    {
-        const double2 a = __ldcg((const double2*)p), b = __ldcg((const double2*)p + 1), c = __ldcg((const double2*)p + 2);
-        const double2 d = __ldcg((const double2*)p + 3), e = __ldcg((const double2*)p + 4);
-        xx = a.x; xy = a.y; xz = b.x; yy = b.y; yz = c.x; zz = c.y; vx = d.x; vy = d.y; vz = e.x; g = e.y;
-        ns = __ldcg(p + 10);
-    }
-    __device__ __forceinline__ void load_shared(const double* p)
-    {
-        xx = p[0]; xy = p[1]; xz = p[2]; yy = p[3]; yz = p[4]; zz = p[5]; vx = p[6]; vy = p[7]; vz = p[8]; g = p[9]; ns = p[10];
-    }
-    __device__ __forceinline__ void store(double* p) const
-    {
-        __stcg((double2*)p, make_double2(xx, xy)); __stcg((double2*)p + 1, make_double2(xz, yy));
-        __stcg((double2*)p + 2, make_double2(yz, zz)); __stcg((double2*)p + 3, make_double2(vx, vy));
-        __stcg((double2*)p + 4, make_double2(vz, g)); __stcg(p + 10, ns);
-    }
-    // add s * (bond with outward unit vector (ux,uy,uz) and radial factor gb)
-    __device__ __forceinline__ void add(double s, double ux, double uy, double uz, double gb)
-    {
-        const double sg = s * gb;
-        const double gx = sg * ux, gy = sg * uy, gz = sg * uz;
-        xx = fma(gx, ux, xx); xy = fma(gx, uy, xy); xz = fma(gx, uz, xz);
-        yy = fma(gy, uy, yy); yz = fma(gy, uz, yz); zz = fma(gz, uz, zz);
-        vx += gx; vy += gy; vz += gz; g += sg;
-        ns += (gb > GSAFE) ? s : 0.0;
-    }
-    // sum_k g_k (c*u.u_k - cos0)^2
-    __device__ __forceinline__ double quad(double ux, double uy, double uz, double c) const
-    {
-        const double t = ux * (xx * ux + 2.0 * (xy * uy + xz * uz)) + uy * (yy * uy + 2.0 * yz * uz) + zz * uz * uz;
-        const double l = ux * vx + uy * vy + uz * vz;
-        return t - (2.0 * COS0 * c) * l + C0SQ * g;
-    }
-};
 
 // ------------------------------------------------------------------------------------------------
 // Local energies of molecule imol in every lattice, for the current ("old")
@@ -637,286 +567,185 @@ struct Ten {
 // (4 evaluations of compute_local_real_energy, molint.F90:220-404, in one
 // flattened pass; mc_moves.F90:1010,1083).
 //
-// Formulation (equal to the reference's sum up to fp64 rounding; DESIGN.md 4.1):
+// Formulation (equal to the reference's sum up to fp64 rounding; DESIGN.md):
 //   E(i) = sum_{b in bonds(i)} phi2(r_ib)
 //        + lam*eps * sum_{b<c in bonds(i)} g_ib g_ic h(u_ib.u_ic) * (j_b==j_c ? 3 : 1)
 //        + lam*eps * sum_{b in bonds(i)} g_ib sum_{k in bonds(j_b), k not an image of i} g_jk h(-u_ib.u_jk)
-// where bonds(x) are the list entries inside the cut-off and h(c) = (c - cos0)^2 for c < 0.99,
-// else 0.  The factor 3 covers the two j-centred triplets whose third body is another periodic
-// image of i (reference: list-B entries with kmol==imol that survive the cos<0.99 filter).
+// where bonds(x) are the list entries inside the cut-off.  The factor 3 covers
+// the two j-centred triplets whose third body is another periodic image of i
+// (reference: list-B entries with kmol==imol that survive the cos<0.99 filter).
+// Bonds of the neighbours j come from the cached bond masks; their geometry
+// does not depend on the position of i, so one item evaluation serves both
+// the old and the new variant.
 //
-// TENSOR path: both triplet sums are quadratic forms in the cached bond tensors (h without the
-// filter).  The filter can only bite (for k != i) when two of the three molecules of a triplet are
-// closer than a*sigma/1.98 (see RSAFE); every centre for which that cannot be excluded -- a bond
-// of imol or of the neighbour shorter than RSAFE -- is re-done by the reference's enumeration.
-// EXACT path: enumeration for every centre; used when forced (testing) or when the
-// displacement guard cannot vouch for molecules missing from the stale Verlet lists.
-// per-move uniforms kept in shared memory (w.cxs): every lane stores the same value
-enum : int {
-    CX_MO = 0,      // [2] in-range slot masks of imol, old position
-    CX_MN = 2,      // [2] ... trial position
-    CX_SEG = 4,     // [4] first bond record of evaluation ev = lat*2 + new
-    CX_NSEG = 8,    // [4] number of bond records of evaluation ev
-    CX_NQ = 12,
-    CX_FAST = 13,   // tensor path (else: enumeration for every centre)
-    CX_DISP = 14,   // [2] float bits: path length of imol since the last list build
-};
-
-struct Acc4 { double a0, a1, a2, a3; };
-
-// exact stage 3: triplets centred on imol: all pairs (b<c) of bond records of one evaluation
-// (lanes = records b, loop over the later records c of the same evaluation).
-__device__ __noinline__ Acc4 icentre_pairs_warp(WalkerRef ref)
-{
-    const WalkerView w = ref.view();
-    const double* q = w.q;
-    const uint32_t* cxs = w.cxs;
-    const int lane = lane_id();
-    const int nq = cxs[CX_NQ];
-    Acc4 acc{0.0, 0.0, 0.0, 0.0};
-#pragma unroll 1
-    for (int b0 = 0; b0 < nq; b0 += 32) {
-        const int r = b0 + lane;
-        const bool act = r < nq;
-        const uint32_t qm = act ? w.qmeta[r] : 0u;
-        const int ev = qm & 3;
-        const int send = act ? (int)(cxs[CX_SEG + ev] + cxs[CX_NSEG + ev]) : 0;
-        const double ux = act ? q[r] : 0.0, uy = act ? q[QC + r] : 0.0, uz = act ? q[2 * QC + r] : 0.0;
-        const double g = act ? q[3 * QC + r] : 0.0;
-        const int maxd = __reduce_max_sync(FULL, act ? send - r - 1 : 0);
-        double tb = 0.0;
-#pragma unroll 1
-        for (int d = 1; d <= maxd; ++d) {
-            const int c = r + d;
-            if (c < send) {
-                const double ct = ux * q[c] + uy * q[QC + c] + uz * q[2 * QC + c];
-                const double mult = ((qm >> 8) == (w.qmeta[c] >> 8)) ? 3.0 : 1.0;   // images of one molecule
-                tb += q[3 * QC + c] * hfun(ct) * mult;
-            }
-        }
-        tb *= LEPS * g;
-        acc.a0 += (ev == 0) ? tb : 0.0; acc.a1 += (ev == 1) ? tb : 0.0;
-        acc.a2 += (ev == 2) ? tb : 0.0; acc.a3 += (ev == 3) ? tb : 0.0;
-    }
-    return acc;
-}
-
-// exact stages 4+5 for ONE centre: triplets centred on the neighbour j of bond record rec
-// (legs j->imol [the record] and j->k, k over j's own list; lanes = slots of that list).  Images of
-// imol are skipped (see above).  Returns this lane's part of lam*eps * g_rec * sum_k g_jk h(-u.u_jk).
-__device__ __noinline__ double jcentre_enum_warp(WalkerRef ref, int imol, int rec)
-{
-    const WalkerView w = ref.view();
-    const int N = w.N, lane = lane_id();
-    const double* q = w.q;
-    const uint32_t qm = w.qmeta[rec];
-    const int lat = (qm & 3) >> 1, j = qm >> 8;
-    const double* P = w.pos + lat * 3 * N;
-    const double* V = w.iv + lat * 3 * IVC;
-    const int nnj = w.nn[lat * N + j];
-    double v = 0.0;
-    if (lane < nnj) {
-        const uint32_t e2 = __ldcg(w.list + ((size_t)lat * N + j) * LC + lane);
-        const int k = e2 & 1023, img = e2 >> 10;
-        if (k != imol) {
-            const double tx = (P[k] + V[img]) - P[j];
-            const double ty = (P[N + k] + V[IVC + img]) - P[N + j];
-            const double tz = (P[2 * N + k] + V[2 * IVC + img]) - P[2 * N + j];
-            const double sq = tx * tx + ty * ty + tz * tz;
-            if (sq < RCSQ) {
-                const double vi = rsqrt_fast(sq);
-                const double ex = LEPS * exp_fast(GS * rcp_fast(sq * vi - RC));
-                const double ct = -(q[rec] * tx + q[QC + rec] * ty + q[2 * QC + rec] * tz) * vi;
-                v = q[3 * QC + rec] * ex * hfun(ct);
-            }
-        }
-    }
-    return v;
-}
-
-// Inputs in shared memory: w.pn (trial position per lattice, WITH_NEW), w.cxs[CX_DISP..] is written here.
-// tlen0/tlen1: SQUARED length of the trial displacement per lattice, rounded up (guard).  Results: eo/en (uniform).
-// e0/e1: this lane's entry of imol's Verlet row in lattice 1/2 (loaded early by the caller).
+// Outputs (uniform over the warp): eo[lat], en[lat]; mo[lat]/mn[lat] = in-range
+// slot masks of imol for the old / new position.
 template <int NLAT, bool WITH_NEW>
-__device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerView& w, int imol, uint32_t e0, uint32_t e1,
-                                                    float tlen0, float tlen1, double* eo, double* en)
+__device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imol, const double (*pnew)[3],
+                                                    double* eo, double* en, uint32_t* mo, uint32_t* mn)
 {
     const int N = w.N, lane = lane_id();
     const unsigned lt = lt_mask();
     double* q = w.q;
-    WalkerScalars* sc = w.sc;
-    uint32_t* cxs = w.cxs;
-    int nq = 0;
-
-    // cached tensor of imol (old position) and its path length: issued early, used after stage 2
-    double told = 0.0;
-    if (lane < NLAT * TS) told = __ldcg(w.gten + ((size_t)(lane / TS) * N + imol) * TS + (lane % TS));
-    const float disp0 = __ldcg(w.gdisp + imol);
-    const float disp1 = (NLAT == 2) ? __ldcg(w.gdisp + N + imol) : 0.f;
+    int nq = 0, nc = 0;
+    int seg_start[4] = {0, 0, 0, 0}, seg_n[4] = {0, 0, 0, 0};
 
     // ---- stage 1: distance tests over imol's own list (lanes = slots), compaction into bond records
-#pragma unroll 1
+#pragma unroll
     for (int lat = 0; lat < NLAT; ++lat) {
         const double* P = w.pos + lat * 3 * N;
         const double* V = w.iv + lat * 3 * IVC;
         const int nni = w.nn[lat * N + imol];
         const bool has = lane < nni;
-        const uint32_t e = has ? (lat ? e1 : e0) : 0u;
+        const uint32_t e = has ? w.list[((size_t)lat * N + imol) * LC + lane] : 0u;
         const int j = e & 1023, img = e >> 10;
         const double pjx = P[j] + V[img], pjy = P[N + j] + V[IVC + img], pjz = P[2 * N + j] + V[2 * IVC + img];
         const double tox = pjx - P[imol], toy = pjy - P[N + imol], toz = pjz - P[2 * N + imol];
         const double r2o = tox * tox + toy * toy + toz * toz;
         const bool fo = has && r2o < RCSQ;
         const uint32_t bo = __ballot_sync(FULL, fo);
+        mo[lat] = bo;
         const int io = nq + __popc(bo & lt);
-        cxs[CX_MO + lat] = bo; cxs[CX_SEG + 2 * lat] = nq; cxs[CX_NSEG + 2 * lat] = __popc(bo);
-        nq += __popc(bo);
+        seg_start[lat * 2] = nq; seg_n[lat * 2] = __popc(bo); nq += __popc(bo);
         bool fn = false; int in_ = 0; uint32_t bn = 0;
         double tnx = 0, tny = 0, tnz = 0, r2n = 0;
         if (WITH_NEW) {
-            tnx = pjx - w.pn[lat * 3]; tny = pjy - w.pn[lat * 3 + 1]; tnz = pjz - w.pn[lat * 3 + 2];
+            tnx = pjx - pnew[lat][0]; tny = pjy - pnew[lat][1]; tnz = pjz - pnew[lat][2];
             r2n = tnx * tnx + tny * tny + tnz * tnz;
             fn = has && r2n < RCSQ;
             bn = __ballot_sync(FULL, fn);
+            mn[lat] = bn;
             in_ = nq + __popc(bn & lt);
+            seg_start[lat * 2 + 1] = nq; seg_n[lat * 2 + 1] = __popc(bn); nq += __popc(bn);
         }
-        cxs[CX_MN + lat] = bn; cxs[CX_SEG + 2 * lat + 1] = nq; cxs[CX_NSEG + 2 * lat + 1] = __popc(bn);
-        nq += __popc(bn);
-        // bonded slots that are images of the same molecule (narrow cells): handled as one group
-        const uint32_t grp = __match_any_sync(FULL, (fo || fn) ? (uint32_t)j : 0x8000u + (uint32_t)lane);
-        // nq may exceed QC only at unphysical densities (flagged below)
+        const uint32_t bu = bo | bn;
+        const int ic = nc + __popc(bu & lt);
+        nc += __popc(bu);
+        // nc <= 2*LC == CC by construction; nq may exceed QC only at unphysical densities (flagged below)
         if (fo && io < QC) {
             q[io] = tox; q[QC + io] = toy; q[2 * QC + io] = toz; q[3 * QC + io] = r2o;
-            w.qmeta[io] = (uint32_t)(lat * 2) | ((uint32_t)lane << 2) | ((uint32_t)j << 8);
-            w.qgrp[io] = grp;
+            w.qmeta[io] = (uint32_t)(lat * 2) | ((uint32_t)j << 8);
         }
         if (WITH_NEW && fn && in_ < QC) {
             q[in_] = tnx; q[QC + in_] = tny; q[2 * QC + in_] = tnz; q[3 * QC + in_] = r2n;
-            w.qmeta[in_] = (uint32_t)(lat * 2 + 1) | ((uint32_t)lane << 2) | ((uint32_t)j << 8);
-            w.qgrp[in_] = grp;
+            w.qmeta[in_] = (uint32_t)(lat * 2 + 1) | ((uint32_t)j << 8);
+        }
+        if (fo || fn) {
+            w.cmeta[ic] = (uint32_t)lat | ((uint32_t)j << 6);
+            w.cq[ic * 2] = (fo && io < QC) ? (uint16_t)io : NONE16;
+            w.cq[ic * 2 + 1] = (fn && in_ < QC) ? (uint16_t)in_ : NONE16;
         }
     }
-    if (NLAT == 1) { cxs[CX_MO + 1] = 0; cxs[CX_MN + 1] = 0; cxs[CX_SEG + 2] = nq; cxs[CX_SEG + 3] = nq; cxs[CX_NSEG + 2] = 0; cxs[CX_NSEG + 3] = 0; }
     if (nq > QC) {                                  // results of this call are invalid; the walker is flagged
-        sc->error |= ERR_BOND_OVERFLOW;
+        w.sc->error |= ERR_BOND_OVERFLOW;
         nq = QC;
-        if (lane < 8) cxs[CX_SEG + lane] = 0;       // all segments empty
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { seg_start[c] = 0; seg_n[c] = 0; }
     }
-
-    // ---- which path?  (uniform over the warp)
-    // guard: rn_eff - disp(imol) - |trial displacement| - dmax > RSAFE, with the trial length squared
-    const float margin = (float)(RSAFE * 1.0001);
-    const float room0 = sc->rn_eff[0] - disp0 - sc->dmax[0] - margin;
-    bool guard = room0 > 0.f && (!WITH_NEW || tlen0 < room0 * room0);
-    if (NLAT == 2) {
-        const float room1 = sc->rn_eff[1] - disp1 - sc->dmax[1] - margin;
-        guard = guard && room1 > 0.f && (!WITH_NEW || tlen1 < room1 * room1);
-    }
-    const bool forced = sc->force_exact || !sc->tensors_valid;
-    const bool fast = guard && !forced;
-    cxs[CX_NQ] = nq; cxs[CX_FAST] = fast;
-    cxs[CX_DISP] = __float_as_uint(disp0); cxs[CX_DISP + 1] = __float_as_uint(disp1);
     __syncwarp();
 
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;     // per-lane partial sums of the 4 evaluations
 
-    // ---- stage 2: bond evaluation (pair energy, g, unit vector); which evaluations own a short bond
-    uint32_t shortev = 0;
-#pragma unroll 1
+    // ---- stage 2: bond evaluation (pair energy, g, unit vector)
     for (int b = 0; b < nq; b += 32) {
         const int r = b + lane;
         if (r < nq) {
             const double pe = eval_bond(q, r);
             const int c = w.qmeta[r] & 3;
-            if (q[3 * QC + r] > GSAFE) shortev |= 1u << c;
             a0 += (c == 0) ? pe : 0.0; a1 += (c == 1) ? pe : 0.0;
             a2 += (c == 2) ? pe : 0.0; a3 += (c == 3) ? pe : 0.0;
         }
     }
-    shortev = __reduce_or_sync(FULL, shortev);
-    __syncwarp();
 
-    // ---- tensors of imol for the 4 evaluations: old = cache, new = sum over the new records
-    if (lane < NLAT * TS) {
-        const int lat = lane / TS, comp = lane - lat * TS;
-        w.ti[(lat * 2) * TS + comp] = told;
-        if (WITH_NEW) {
-            double tn = 0.0;
-            const int s0 = cxs[CX_SEG + 2 * lat + 1], s1 = s0 + cxs[CX_NSEG + 2 * lat + 1];
-            const TenSel sel = ten_sel(comp);
-#pragma unroll 1
-            for (int c = s0; c < s1; ++c) tn += ten_term_sel(sel, q, c);
-            w.ti[(lat * 2 + 1) * TS + comp] = tn;
+    // ---- per-centre bond counts (lanes = centres) -> exclusive prefix in shared memory
+    int ncand = 0;
+    for (int cb = 0; cb < nc; cb += 32) {
+        const int c = cb + lane;
+        int cnt = 0;
+        if (c < nc) {
+            const uint32_t cm = w.cmeta[c];
+            cnt = __popc(w.bmask[(cm & 1) * N + ((cm >> 6) & 1023)]);
         }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (c < nc) w.cpre[c] = (uint16_t)(ncand + incl - cnt);
+        ncand += __shfl_sync(FULL, incl, 31);
     }
+    if (lane == 0) w.cpre[nc] = (uint16_t)ncand;
     __syncwarp();
 
-    bool anybad = !fast;
-    double i0 = 0.0, i1 = 0.0, i2 = 0.0, i3 = 0.0;     // i-centred sums through the tensors of imol
-    // ---- lanes = bond records: i-centred and j-centred triplet sums as quadratic forms
-#pragma unroll 1
-    for (int b = 0; b < nq; b += 32) {
-        const int r = b + lane;
-        bool bad = false;
-        if (r < nq) {
-            const uint32_t qm = w.qmeta[r];
-            const int ev = qm & 3, lat = ev >> 1, s = (qm >> 2) & 31, j = qm >> 8;
-            const double ux = q[r], uy = q[QC + r], uz = q[2 * QC + r], g = q[3 * QC + r];
-            bad = !fast || ((shortev >> ev) & 1u);
-            if (fast) {
-                Ten T;
-                T.load(w.gten + ((size_t)lat * N + j) * TS);
-                // the bonds of j to (images of) imol at its OLD position leave the sum (outward vector -u_c):
-                // they are the old records of the slots of this record's group
-                const uint32_t bo = cxs[CX_MO + lat], grp = w.qgrp[r];
-                const int so = cxs[CX_SEG + 2 * lat], se = cxs[CX_SEG + ev];
-                uint32_t m = grp & bo;
-#pragma unroll 1
-                while (m) {
-                    const int s2 = __ffs(m) - 1; m &= m - 1;
-                    const int c = so + __popc(bo & ((1u << s2) - 1u));
-                    T.add(-1.0, -q[c], -q[QC + c], -q[2 * QC + c], q[3 * QC + c]);
-                }
-                bad = bad || fabs(T.ns) > 0.5;                               // j keeps a bond shorter than RSAFE
-                double tj = bad ? 0.0 : T.quad(ux, uy, uz, -1.0);            // centre j: cos = -u.u_jk
-                T.load_shared(w.ti + ev * TS);
-                double ti = 0.5 * (T.quad(ux, uy, uz, 1.0) - g * OMC0SQ);    // centre i: ordered pairs, minus c == b
-                // two bonds to different images of the same j: the reference counts that pair 3 times
-                const uint32_t be = (ev & 1) ? cxs[CX_MN + lat] : bo;
-                m = grp & be & ~(1u << s);
-#pragma unroll 1
-                while (m) {
-                    const int s2 = __ffs(m) - 1; m &= m - 1;
-                    const int c = se + __popc(be & ((1u << s2) - 1u));
-                    const double ct = ux * q[c] + uy * q[QC + c] + uz * q[2 * QC + c];
-                    ti += q[3 * QC + c] * hfun(ct);
-                }
-                tj *= LEPS * g; ti *= LEPS * g;
-                a0 += (ev == 0) ? tj : 0.0; a1 += (ev == 1) ? tj : 0.0;
-                a2 += (ev == 2) ? tj : 0.0; a3 += (ev == 3) ? tj : 0.0;
-                i0 += (ev == 0) ? ti : 0.0; i1 += (ev == 1) ? ti : 0.0;
-                i2 += (ev == 2) ? ti : 0.0; i3 += (ev == 3) ? ti : 0.0;
+    // ---- stage 3: triplets centred on imol: all pairs (a<b) of bond records of the same evaluation,
+    // flattened over the 4 evaluations (lanes = pairs)
+    {
+        const int p0 = seg_n[0] * (seg_n[0] - 1) / 2, p1 = p0 + seg_n[1] * (seg_n[1] - 1) / 2;
+        const int p2 = p1 + seg_n[2] * (seg_n[2] - 1) / 2, p3 = p2 + seg_n[3] * (seg_n[3] - 1) / 2;
+        for (int pb = 0; pb < p3; pb += 32) {
+            const int p = pb + lane;
+            if (p < p3) {
+                const int c = (p >= p2) ? 3 : (p >= p1) ? 2 : (p >= p0) ? 1 : 0;
+                const int m = p - ((c == 3) ? p2 : (c == 2) ? p1 : (c == 1) ? p0 : 0);
+                const int s0 = (c == 3) ? seg_start[3] : (c == 2) ? seg_start[2] : (c == 1) ? seg_start[1] : seg_start[0];
+                // m = b(b-1)/2 + a with a < b
+                int bb = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)m)) * 0.5f);
+                if (bb * (bb - 1) / 2 > m) --bb;
+                if ((bb + 1) * bb / 2 <= m) ++bb;
+                const int ra = s0 + (m - bb * (bb - 1) / 2), rb = s0 + bb;
+                const double ct = q[ra] * q[rb] + q[QC + ra] * q[QC + rb] + q[2 * QC + ra] * q[2 * QC + rb];
+                const double mult = ((w.qmeta[ra] >> 8) == (w.qmeta[rb] >> 8)) ? 3.0 * LEPS : LEPS;
+                const double tb = q[3 * QC + ra] * q[3 * QC + rb] * hfun(ct) * mult;
+                a0 += (c == 0) ? tb : 0.0; a1 += (c == 1) ? tb : 0.0;
+                a2 += (c == 2) ? tb : 0.0; a3 += (c == 3) ? tb : 0.0;
             }
         }
-        // ---- centres that need the reference's enumeration (rare): one pass over j's list each
-        uint32_t badm = __ballot_sync(FULL, bad);
-        anybad = anybad || badm;
-#pragma unroll 1
-        while (badm) {
-            const int c = __ffs(badm) - 1; badm &= badm - 1;
-            const int ev = w.qmeta[b + c] & 3;
-            const double v = jcentre_enum_warp(ref, imol, b + c);
-            a0 += (ev == 0) ? v : 0.0; a1 += (ev == 1) ? v : 0.0;
-            a2 += (ev == 2) ? v : 0.0; a3 += (ev == 3) ? v : 0.0;
-        }
     }
-    if (anybad) {                                   // a close contact somewhere near imol: i-centred pairs one by one
-        const Acc4 p = icentre_pairs_warp(ref);
-        a0 += p.a0; a1 += p.a1; a2 += p.a2; a3 += p.a3;
-        sc->slow_moves[!fast ? (forced ? 3 : 2) : 1] += 1;
-    } else {
-        a0 += i0; a1 += i1; a2 += i2; a3 += i3;
-        sc->fast_moves += 1;
+
+    // ---- stages 4+5: j-centred triplets, lanes = (centre, bond of the centre) candidates.  The
+    // centre of a candidate is found by binary search in the prefix table, its list slot as the
+    // rank-th set bit of the centre's bond mask.  Images of imol are skipped (see above).  One
+    // evaluation of (j,k) serves both variants.
+    for (int tb0 = 0; tb0 < ncand; tb0 += 32) {
+        const int t = tb0 + lane;
+        if (t < ncand) {
+            int lo = 0, hi = nc;                       // largest c with cpre[c] <= t
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if ((int)w.cpre[mid] <= t) lo = mid; else hi = mid;
+            }
+            const int c = lo;
+            const uint32_t cm = w.cmeta[c];
+            const int lat = cm & 1, j = (cm >> 6) & 1023;
+            const int s2 = nth_set_bit(w.bmask[lat * N + j], t - (int)w.cpre[c]);
+            const uint32_t e2 = w.list[((size_t)lat * N + j) * LC + s2];
+            const int k = e2 & 1023, img = e2 >> 10;
+            if (k != imol) {
+                const double* P = w.pos + lat * 3 * N;
+                const double* V = w.iv + lat * 3 * IVC;
+                const double tx = (P[k] + V[img]) - P[j];
+                const double ty = (P[N + k] + V[IVC + img]) - P[N + j];
+                const double tz = (P[2 * N + k] + V[2 * IVC + img]) - P[2 * N + j];
+                const double sq = tx * tx + ty * ty + tz * tz;
+                if (sq < RCSQ) {
+                    const double vi = rsqrt_fast(sq);
+                    const double ex = LEPS * exp_fast(GS * rcp_fast(sq * vi - RC));
+                    const double ux = tx * vi, uy = ty * vi, uz = tz * vi;
+                    const uint16_t qo = w.cq[c * 2], qn = w.cq[c * 2 + 1];
+                    double vo = 0.0, vn = 0.0;
+                    if (qo != NONE16) {
+                        const double ct = -(q[qo] * ux + q[QC + qo] * uy + q[2 * QC + qo] * uz);
+                        vo = q[3 * QC + qo] * ex * hfun(ct);
+                    }
+                    if (WITH_NEW && qn != NONE16) {
+                        const double ct = -(q[qn] * ux + q[QC + qn] * uy + q[2 * QC + qn] * uz);
+                        vn = q[3 * QC + qn] * ex * hfun(ct);
+                    }
+                    if (lat == 0) { a0 += vo; a1 += vn; } else { a2 += vo; a3 += vn; }
+                }
+            }
+        }
     }
 
     reduce4(a0, a1, a2, a3);
@@ -928,13 +757,11 @@ __device__ __forceinline__ void local_energies_warp(WalkerRef ref, const WalkerV
 // ------------------------------------------------------------------------------------------------
 // Full energy of one lattice (compute_model_energy, molint.F90:407-499), molecule-
 // chunked: bonds of a chunk of molecules are compacted (stage 1), evaluated
-// (stage 2) and combined into i-centred triplets (stage 3).
-//   what & 1: return the energy;  what & 2: refresh the bond tensors of the lattice from the same
-//   bond records.
-__device__ __noinline__ double full_energy_warp(WalkerRef ref, int lat, int what)
+// (stage 2) and combined into i-centred triplets (stage 3).  Also refreshes the
+// bond masks of the lattice.  Returns E (uniform).
+__device__ __noinline__ double full_energy_warp(unsigned char* smem, int N, int nlat, int lat)
 {
-    const WalkerView w = ref.view();
-    const int N = w.N;
+    const WalkerView w = carve_walker(smem, N, nlat);
     const int lane = lane_id();
     const unsigned lt = lt_mask();
     const double* P = w.pos + lat * 3 * N;
@@ -946,10 +773,10 @@ __device__ __noinline__ double full_energy_warp(WalkerRef ref, int lat, int what
         // ---- gather bonds of molecules a.. while they fit in the record buffer
         int nq = 0;
         int a1 = a;
-        for (; a1 < N && a1 - a < MC; ++a1) {
+        for (; a1 < N; ++a1) {
             const int nna = w.nn[lat * N + a1];
             const bool has = lane < nna;
-            const uint32_t e = has ? (uint32_t)__ldcg(w.list + ((size_t)lat * N + a1) * LC + lane) : 0u;
+            const uint32_t e = has ? w.list[((size_t)lat * N + a1) * LC + lane] : 0u;
             const int j = e & 1023, img = e >> 10;
             const double tx = (P[j] + V[img]) - P[a1];
             const double ty = (P[N + j] + V[IVC + img]) - P[N + a1];
@@ -958,8 +785,8 @@ __device__ __noinline__ double full_energy_warp(WalkerRef ref, int lat, int what
             const bool f = has && r2 < RCSQ;
             const uint32_t bm = __ballot_sync(FULL, f);
             const int cnt = __popc(bm);
-            if (nq + cnt > QC) break;                 // cnt <= LC <= QC: a chunk always holds >= 1 molecule
-            if (lane == 0) w.seg[a1 - a] = (uint16_t)nq;
+            if (nq + cnt > QC) break;                 // cnt <= LC < QC: a chunk always holds >= 1 molecule
+            if (lane == 0) w.bmask[lat * N + a1] = bm;
             if (f) {
                 const int io = nq + __popc(bm & lt);
                 q[io] = tx; q[QC + io] = ty; q[2 * QC + io] = tz; q[3 * QC + io] = r2;
@@ -967,7 +794,6 @@ __device__ __noinline__ double full_energy_warp(WalkerRef ref, int lat, int what
             }
             nq += cnt;
         }
-        if (lane == 0) w.seg[a1 - a] = (uint16_t)nq;
         __syncwarp();
         // ---- bond evaluation: 0.5 * pair energy (molint.F90:464)
         for (int b = 0; b < nq; b += 32) {
@@ -975,59 +801,32 @@ __device__ __noinline__ double full_energy_warp(WalkerRef ref, int lat, int what
             if (r < nq) acc += 0.5 * eval_bond(q, r);
         }
         __syncwarp();
-        if (what & 1) {
-            // ---- triplets centred on each molecule of the chunk (lanes = records, loop over later
-            // records of the same molecule)
-            for (int b = 0; b < nq; b += 32) {
-                const int r = b + lane;
-                const bool act = r < nq;
-                const int send = act ? (int)w.qmeta[r] : 0;
-                const double ux = act ? q[r] : 0.0, uy = act ? q[QC + r] : 0.0, uz = act ? q[2 * QC + r] : 0.0;
-                const double g = act ? q[3 * QC + r] : 0.0;
-                double tb = 0.0;
-                const int more = act ? send - r - 1 : 0;
-                const int maxd = __reduce_max_sync(FULL, more);
-                for (int d = 1; d <= maxd; ++d) {
-                    const int r2i = r + d;
-                    if (act && r2i < send) {
-                        const double ct = ux * q[r2i] + uy * q[QC + r2i] + uz * q[2 * QC + r2i];
-                        // no k==i filter here: compute_model_energy has none (molint.F90:480-483)
-                        const double dd = ct - COS0;
-                        tb += g * q[3 * QC + r2i] * dd * dd;
-                    }
-                }
-                acc += LEPS * tb;
-            }
-        }
-        if (what & 2) {
-            // ---- bond tensors: lanes = (molecule of the chunk, component)
-            const int ntask = (a1 - a) * TS;
-            for (int t0 = 0; t0 < ntask; t0 += 32) {
-                const int t = t0 + lane;
-                if (t < ntask) {
-                    const int m = t / TS, comp = t - m * TS;
-                    const int s0 = w.seg[m], s1 = w.seg[m + 1];
-                    double tn = 0.0;
-                    const TenSel sel = ten_sel(comp);
-                    for (int c = s0; c < s1; ++c) tn += ten_term_sel(sel, q, c);
-                    __stcg(w.gten + ((size_t)lat * N + a + m) * TS + comp, tn);
+        // ---- triplets centred on each molecule of the chunk (lanes = records, loop over later
+        // records of the same molecule)
+        for (int b = 0; b < nq; b += 32) {
+            const int r = b + lane;
+            const bool act = r < nq;
+            const int send = act ? (int)w.qmeta[r] : 0;
+            const double ux = act ? q[r] : 0.0, uy = act ? q[QC + r] : 0.0, uz = act ? q[2 * QC + r] : 0.0;
+            const double g = act ? q[3 * QC + r] : 0.0;
+            double tb = 0.0;
+            const int more = act ? send - r - 1 : 0;
+            const int maxd = __reduce_max_sync(FULL, more);
+            for (int d = 1; d <= maxd; ++d) {
+                const int r2i = r + d;
+                if (act && r2i < send) {
+                    const double ct = ux * q[r2i] + uy * q[QC + r2i] + uz * q[2 * QC + r2i];
+                    // no k==i filter here: compute_model_energy has none (molint.F90:480-483)
+                    const double dd = ct - COS0;
+                    tb += g * q[3 * QC + r2i] * dd * dd;
                 }
             }
+            acc += LEPS * tb;
         }
         __syncwarp();
         a = a1;
     }
     return warp_sum(acc);
-}
-
-// after a list build: unlisted pairs are at least rn apart, nothing has moved yet
-__device__ __forceinline__ void reset_guard(const WalkerView& w, int lat)
-{
-    const int N = w.N;
-    for (int i = lane_id(); i < N; i += 32) __stcg(w.gdisp + lat * N + i, 0.f);
-    w.sc->rn_eff[lat] = (float)(RN * 0.9999);
-    w.sc->dmax[lat] = 0.f;
-    __syncwarp();
 }
 
 }  // namespace mw

@@ -41,8 +41,6 @@ struct DeviceState {
     int*    niv;        // [W][2]
     uint16_t* list;     // [W][nlat][N][LC]
     uint8_t*  nn;       // [W][nlat][N]
-    double* ten;        // [W][nlat][N][TS]  per-molecule bond tensors (cache, rebuilt on demand)
-    float*  disp;       // [W][nlat][N]      path length moved since the last list build
     WalkerScalars* scal;// [W]
     double* weight;     // [W][NB]
     double* hist;       // [W][NB]
@@ -60,30 +58,32 @@ struct DeviceState {
 };
 
 // ---------------------------------------------------------------- staging
-// Global -> shared at the start of a work unit and back at its end.  Loads bypass L1 (ld.cg): the
-// previous unit of this walker may have run on another SM during the same launch.
 __device__ __forceinline__ void load_walker(const DeviceState& S, int wi, const WalkerView& w)
 {
     const int N = S.N, nlat = S.nlat, lane = lane_id();
     const double* gp = S.pos + (size_t)wi * nlat * 3 * N;
-    for (int t = lane; t < nlat * 3 * N; t += 32) w.pos[t] = __ldcg(gp + t);
+    for (int t = lane; t < nlat * 3 * N; t += 32) w.pos[t] = gp[t];
     const double* gi = S.iv + (size_t)wi * nlat * 3 * IVC;
-    for (int t = lane; t < nlat * 3 * IVC; t += 32) w.iv[t] = __ldcg(gi + t);
+    for (int t = lane; t < nlat * 3 * IVC; t += 32) w.iv[t] = gi[t];
     if (lane < nlat * 9) {
-        w.cell[lane] = __ldcg(S.cell + (size_t)wi * nlat * 9 + lane);
-        w.recip[lane] = __ldcg(S.recip + (size_t)wi * nlat * 9 + lane);
+        w.cell[lane] = S.cell[(size_t)wi * nlat * 9 + lane];
+        w.recip[lane] = S.recip[(size_t)wi * nlat * 9 + lane];
     }
-    if (lane < 2) w.niv[lane] = __ldcg(S.niv + wi * 2 + lane);
+    if (lane < 2) w.niv[lane] = S.niv[wi * 2 + lane];
+    // lists: 16-byte vector copies (N*LC*2 bytes per lattice is a multiple of 16)
+    const uint4* gl = (const uint4*)(S.list + (size_t)wi * nlat * N * LC);
+    uint4* sl = (uint4*)w.list;
+    for (int t = lane; t < nlat * N * LC / 8; t += 32) sl[t] = gl[t];
     const uint8_t* gn = S.nn + (size_t)wi * nlat * N;
-    for (int t = lane; t < nlat * N; t += 32) w.nn[t] = __ldcg(gn + t);
+    for (int t = lane; t < nlat * N; t += 32) w.nn[t] = gn[t];
     // scalars: word-wise copy
     const uint32_t* gs = (const uint32_t*)(S.scal + wi);
     uint32_t* ss = (uint32_t*)w.sc;
-    for (int t = lane; t < (int)(sizeof(WalkerScalars) / 4); t += 32) ss[t] = __ldcg(gs + t);
+    for (int t = lane; t < (int)(sizeof(WalkerScalars) / 4); t += 32) ss[t] = gs[t];
     __syncwarp();
 }
 
-__device__ __forceinline__ void store_walker(const DeviceState& S, int wi, const WalkerView& w)
+__device__ __forceinline__ void store_walker(const DeviceState& S, int wi, const WalkerView& w, bool lists)
 {
     const int N = S.N, nlat = S.nlat, lane = lane_id();
     __syncwarp();
@@ -96,8 +96,13 @@ __device__ __forceinline__ void store_walker(const DeviceState& S, int wi, const
         S.recip[(size_t)wi * nlat * 9 + lane] = w.recip[lane];
     }
     if (lane < 2) S.niv[wi * 2 + lane] = w.niv[lane];
-    uint8_t* gn = S.nn + (size_t)wi * nlat * N;
-    for (int t = lane; t < nlat * N; t += 32) gn[t] = w.nn[t];
+    if (lists) {
+        uint4* gl = (uint4*)(S.list + (size_t)wi * nlat * N * LC);
+        const uint4* sl = (const uint4*)w.list;
+        for (int t = lane; t < nlat * N * LC / 8; t += 32) gl[t] = sl[t];
+        uint8_t* gn = S.nn + (size_t)wi * nlat * N;
+        for (int t = lane; t < nlat * N; t += 32) gn[t] = w.nn[t];
+    }
     uint32_t* gs = (uint32_t*)(S.scal + wi);
     const uint32_t* ss = (const uint32_t*)w.sc;
     for (int t = lane; t < (int)(sizeof(WalkerScalars) / 4); t += 32) gs[t] = ss[t];
@@ -107,9 +112,9 @@ __device__ __forceinline__ void store_walker(const DeviceState& S, int wi, const
 // Per-walker stream of U[0,1) numbers (random.f90:87-102), buffered RB at a time in shared
 // memory.  mode 0: Philox (draw n = half n&1 of block n>>1); mode 1: host FIFO (draw n = fifo[n]).
 // `pos` (index of the next draw inside the buffer) is carried in a register by the caller.
-__device__ __noinline__ void rng_refill(WalkerRef ref, const DeviceState& S, const McParams& p, int wi)
+__device__ __noinline__ void rng_refill(unsigned char* smem, int N, int nlat, const DeviceState& S, const McParams& p, int wi)
 {
-    const WalkerView w = ref.view();
+    const WalkerView w = carve_walker(smem, N, nlat);
     const int lane = lane_id();
     const uint64_t base = *w.rngbase;
     __syncwarp();
@@ -126,7 +131,7 @@ __device__ __noinline__ void rng_refill(WalkerRef ref, const DeviceState& S, con
 }
 
 struct Rng {
-    WalkerRef ref; int wi;
+    unsigned char* smem; int N, nlat, wi;
     const DeviceState* S; const McParams* p;
     double* buf; uint64_t* base;
     int pos;
@@ -139,16 +144,12 @@ struct Rng {
             const uint64_t next = *base + (uint64_t)pos;
             __syncwarp();
             *base = next & ~(uint64_t)1;      // every lane stores the same value
-            rng_refill(ref, *S, *p, wi);
+            rng_refill(smem, N, nlat, *S, *p, wi);
             pos = (int)(next & 1);
         }
     }
     __device__ __forceinline__ double draw() { return buf[pos++]; }
 };
-#ifndef MWGPU_MC_BLOCKS
-#define MWGPU_MC_BLOCKS 16
-#endif
-constexpr int MC_BLOCKS_PER_SM = MWGPU_MC_BLOCKS;   // register budget of k_mc_run: 65536 / (32 * blocks) per thread
 constexpr int DRAWS_PER_MOVE = 8;            // at most 8 draws per trial move (+ switch)
 
 // ---------------------------------------------------------------- order parameter / weights
@@ -231,12 +232,13 @@ __device__ __forceinline__ double switch_arg(const McParams& p, const WalkerView
 }
 
 // mc_lattice_switch (mc_moves.F90:1536-1594), stand-alone form (cold paths)
-__device__ __noinline__ int lattice_switch_cold(WalkerRef ref, const DeviceState& S, const McParams& p, int wi, int rng_pos)
+__device__ __noinline__ int lattice_switch_cold(unsigned char* smem, const DeviceState& S, const McParams& p, int wi,
+                                                int nlat, int rng_pos)
 {
     const int N = S.N;
-    const WalkerView w = ref.view();
+    const WalkerView w = carve_walker(smem, N, nlat);
     WalkerScalars* sc = w.sc;
-    Rng rng{ref, wi, &S, &p, w.rngbuf, w.rngbase, rng_pos};
+    Rng rng{smem, N, nlat, wi, &S, &p, w.rngbuf, w.rngbase, rng_pos};
     const double eta = eta_bin(p, S.mubin, S.ginv, sc, S.weight + (size_t)wi * S.NB, sc->mu).eta;
     const double arg = switch_arg(p, w, sc->E[0], sc->E[1], sc->ls == 1, eta, (double)N);
     const double compare = (arg > 0.0) ? 1.0 : exp_fast(arg);
@@ -252,11 +254,10 @@ __device__ __noinline__ int lattice_switch_cold(WalkerRef ref, const DeviceState
 
 // mc_moves.F90:1597-1689 for the weight-generation case (not samplerun): the histogram increment
 // is done by the caller; this updates wl_factor (Swetnam / 1-over-t variants) and the weights.
-__device__ __noinline__ void update_weights(WalkerRef ref, const McParams& p,
+__device__ __noinline__ void update_weights(unsigned char* smem, int N, int nlat, const McParams& p,
                                             const double* __restrict__ binwidth, double* wgt, const double* hist, int k)
 {
-    const WalkerView w = ref.view();
-    const int N = w.N;
+    const WalkerView w = carve_walker(smem, N, nlat);
     WalkerScalars* sc = w.sc;
     const int nb = p.nbins, lane = lane_id();
     if (p.wl_swetnam) {
@@ -313,10 +314,9 @@ __device__ __forceinline__ void rescale_pos(double& x, double& y, double& z, con
     x = xa(x, t0); y = xa(y, t1); z = xa(z, t2);
 }
 
-__device__ __noinline__ void rescale_all(WalkerRef ref, double* refpos, int lat)
+__device__ __noinline__ void rescale_all(unsigned char* smem, int N, int nlat, double* refpos, int lat)
 {
-    const WalkerView w = ref.view();
-    const int N = w.N;
+    const WalkerView w = carve_walker(smem, N, nlat);
     const int lane = lane_id();
     double rm[9], hm[9];
 #pragma unroll
@@ -327,7 +327,7 @@ __device__ __noinline__ void rescale_all(WalkerRef ref, double* refpos, int lat)
         double x = P[i], y = P[N + i], z = P[2 * N + i];
         rescale_pos(x, y, z, rm, hm);
         P[i] = x; P[N + i] = y; P[2 * N + i] = z;
-        x = __ldcg(R + i); y = __ldcg(R + N + i); z = __ldcg(R + 2 * N + i);
+        x = R[i]; y = R[N + i]; z = R[2 * N + i];
         rescale_pos(x, y, z, rm, hm);
         R[i] = x; R[N + i] = y; R[2 * N + i] = z;
     }
@@ -335,9 +335,9 @@ __device__ __noinline__ void rescale_all(WalkerRef ref, double* refpos, int lat)
 }
 
 // recip matrix of the cell in shared memory -> shared memory (uniform stores)
-__device__ __noinline__ void refresh_recip(WalkerRef ref, int lat)
+__device__ __noinline__ void refresh_recip(unsigned char* smem, int N, int nlat, int lat)
 {
-    const WalkerView w = ref.view();
+    const WalkerView w = carve_walker(smem, N, nlat);
     double hm[9], rm[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) hm[k] = w.cell[lat * 9 + k];
@@ -356,24 +356,15 @@ __device__ __forceinline__ double cell_volume(const WalkerView& w, int lat)
     return fabs(determinant3(hm));
 }
 
-// (Re)build the bond-tensor cache of every lattice from the current positions and lists.
-__device__ __noinline__ void rebuild_tensors_all(WalkerRef ref)
-{
-    const WalkerView w = ref.view();
-    for (int lat = 0; lat < w.nlat; ++lat) full_energy_warp(ref, lat, 2);
-    w.sc->tensors_valid = 1;
-    __syncwarp();
-}
-
 // mc_moves.F90:1216-1534.  Cold path (0.26 % of the moves): not inlined.  Returns the new
 // position in the random-number buffer.
 template <int NLAT>
-__device__ __noinline__ int volume_move(WalkerRef ref, const DeviceState& S, const McParams& p, int wi, int rng_pos)
+__device__ __noinline__ int volume_move(unsigned char* smem, const DeviceState& S, const McParams& p, int wi, int rng_pos)
 {
     const int N = S.N;
-    const WalkerView w = ref.view();
+    const WalkerView w = carve_walker(smem, N, NLAT);
     WalkerScalars* sc = w.sc;
-    Rng rng{ref, wi, &S, &p, w.rngbuf, w.rngbase, rng_pos};
+    Rng rng{smem, N, NLAT, wi, &S, &p, w.rngbuf, w.rngbase, rng_pos};
     const int lane = lane_id();
     const double Nd = (double)N;
     const double* wgt = S.weight + (size_t)wi * S.NB;
@@ -385,7 +376,7 @@ __device__ __noinline__ int volume_move(WalkerRef ref, const DeviceState& S, con
     for (int lat = 0; lat < NLAT; ++lat) {
         backupE[lat] = sc->E[lat];
         old_vol[lat] = sc->vol[lat];
-        refresh_recip(ref, lat);                           // :1260-1262
+        refresh_recip(smem, N, NLAT, lat);                 // :1260-1262
     }
     if (lane < NLAT * 9) { save[lane] = w.cell[lane]; save[18 + lane] = w.recip[lane]; }
     __syncwarp();
@@ -405,11 +396,11 @@ __device__ __noinline__ int volume_move(WalkerRef ref, const DeviceState& S, con
     double* refpos = S.ref + (size_t)wi * NLAT * 3 * N;
 #pragma unroll
     for (int lat = 0; lat < NLAT; ++lat) {
-        rescale_all(ref, refpos, lat);                     // recip = old cell's, h = new cell
+        rescale_all(smem, N, NLAT, refpos, lat);           // recip = old cell's, h = new cell
         sc->vol[lat] = cell_volume(w, lat);
-        refresh_recip(ref, lat);
-        err |= compute_ivects_warp(ref, lat);
-        newE[lat] = full_energy_warp(ref, lat, 3);         // energy + bond tensors of the trial cell
+        refresh_recip(smem, N, NLAT, lat);
+        err |= compute_ivects_warp(smem, N, NLAT, lat);
+        newE[lat] = full_energy_warp(smem, N, NLAT, lat);
         sc->E[lat] = newE[lat];
     }
     double old_eta = 0.0, new_eta = 0.0, old_mu = 0.0;
@@ -435,16 +426,6 @@ __device__ __noinline__ int volume_move(WalkerRef ref, const DeviceState& S, con
             if (dmu > sc->max_dmu) sc->max_dmu = dmu;
         }
         w.lv[0] = nlv12; w.lv[1] = nlv21;
-        // every separation was multiplied by at least 1 - |dh| * sqrt(2) * ||h_old^-1||_F : shrink the
-        // bound on the distance of unlisted pairs accordingly (guard of the tensor path)
-#pragma unroll
-        for (int lat = 0; lat < NLAT; ++lat) {
-            double f2 = 0.0;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) f2 += save[18 + lat * 9 + k] * save[18 + lat * 9 + k];
-            const float eps = (float)(fabs(dh) * 1.4143 * sqrt(f2) * (0.5 * INV_PI)) * 1.001f;
-            sc->rn_eff[lat] = sc->rn_eff[lat] * fmaxf(0.f, 1.f - eps);
-        }
     } else {
         // :1434-1528: V,h <- old; rescale with recip(NEW) and h(OLD); recip <- old; ivects; E <- backup
         __syncwarp();
@@ -453,15 +434,15 @@ __device__ __noinline__ int volume_move(WalkerRef ref, const DeviceState& S, con
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {
             sc->vol[lat] = old_vol[lat];
-            rescale_all(ref, refpos, lat);
+            rescale_all(smem, N, NLAT, refpos, lat);
         }
         if (lane < NLAT * 9) w.recip[lane] = save[18 + lane];
         __syncwarp();
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {
-            err |= compute_ivects_warp(ref, lat);
+            err |= compute_ivects_warp(smem, N, NLAT, lat);
             sc->E[lat] = backupE[lat];
-            full_energy_warp(ref, lat, 2);                 // bond tensors of the restored positions
+            compute_bond_masks_warp(smem, N, NLAT, lat);   // positions moved by rounding; keep masks fresh
         }
         if (NLAT == 2) sc->mu = mu_paren(p, sc, Nd, w.lv[0]);
     }
@@ -469,122 +450,75 @@ __device__ __noinline__ int volume_move(WalkerRef ref, const DeviceState& S, con
     return rng.pos;
 }
 
-// commit of an accepted translation: new position, and the bond-tensor cache follows the move
+// commit of an accepted translation: new position, own bond mask, and the reverse bits of the
+// bonds that formed / broke (rare)
 template <int NLAT>
-__device__ __forceinline__ void commit_translation(const WalkerView& w, int imol, float tlen0, float tlen1)
+__device__ __forceinline__ void commit_translation(const WalkerView& w, int imol, const double (*pnew)[3],
+                                                   const uint32_t* mo, const uint32_t* mn)
 {
     const int N = w.N, lane = lane_id();
-    WalkerScalars* sc = w.sc;
-    const uint32_t* cxs = w.cxs;
-    const double* q = w.q;
     __syncwarp();
-    if (lane < NLAT * 3) w.pos[(lane / 3) * 3 * N + (lane % 3) * N + imol] = w.pn[lane];
-    {
-        const float d0 = __uint_as_float(cxs[CX_DISP]) + tlen0;
-        sc->dmax[0] = fmaxf(sc->dmax[0], d0);
-        if (lane == 0) __stcg(w.gdisp + imol, d0);
-        if (NLAT == 2) {
-            const float d1 = __uint_as_float(cxs[CX_DISP + 1]) + tlen1;
-            sc->dmax[1] = fmaxf(sc->dmax[1], d1);
-            if (lane == 0) __stcg(w.gdisp + N + imol, d1);
-        }
-    }
-    if (!sc->tensors_valid) { __syncwarp(); return; }
-    // tensor of imol at its new position
-    if (lane < NLAT * TS) {
-        const int lat = lane / TS, comp = lane - lat * TS;
-        __stcg(w.gten + ((size_t)lat * N + imol) * TS + comp, w.ti[(lat * 2 + 1) * TS + comp]);
-    }
-    // neighbours (lanes = list slots of imol): T_j loses the old bonds to imol and gains the new ones;
-    // the lowest slot of a group of images of one molecule applies the whole group's change
-#pragma unroll 1
+#pragma unroll
     for (int lat = 0; lat < NLAT; ++lat) {
-        const uint32_t bo = cxs[CX_MO + lat], bn = cxs[CX_MN + lat];
-        const bool mine = ((bo | bn) >> lane) & 1u;
-        const int j = mine ? (__ldcg(w.list + ((size_t)lat * N + imol) * LC + lane) & 1023) : 0;
-        const uint32_t grp = __match_any_sync(FULL, mine ? (uint32_t)j : 0x8000u + (uint32_t)lane);
-        if (mine && (int)(__ffs(grp) - 1) == lane) {
-            double* gp = w.gten + ((size_t)lat * N + j) * TS;
-            Ten T;
-            T.load(gp);
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                const uint32_t bm = pass ? bn : bo;
-                const int s0 = cxs[CX_SEG + 2 * lat + pass];
-                const double sign = pass ? 1.0 : -1.0;
-                uint32_t m = grp & bm;
-#pragma unroll 1
-                while (m) {
-                    const int s2 = __ffs(m) - 1; m &= m - 1;
-                    const int c = s0 + __popc(bm & ((1u << s2) - 1u));
-                    T.add(sign, -q[c], -q[QC + c], -q[2 * QC + c], q[3 * QC + c]);
-                }
+        double* P = w.pos + lat * 3 * N;
+        if (lane < 3) P[lane * N + imol] = (lane == 0) ? pnew[lat][0] : (lane == 1) ? pnew[lat][1] : pnew[lat][2];
+        uint32_t changed = mo[lat] ^ mn[lat];
+        if (lane == 0) w.bmask[lat * N + imol] = mn[lat];
+        const int nv = w.niv[lat];
+        while (changed) {
+            const int s = __ffs(changed) - 1; changed &= changed - 1;
+            const uint32_t e = w.list[((size_t)lat * N + imol) * LC + s];
+            const int j = e & 1023, img = e >> 10;
+            const uint32_t target = ((uint32_t)inverse_image(img, nv) << 10) | (uint32_t)imol;
+            const int nnj = w.nn[lat * N + j];
+            const uint32_t e2 = (lane < nnj) ? w.list[((size_t)lat * N + j) * LC + lane] : 0xffffffffu;
+            const uint32_t hit = __ballot_sync(FULL, e2 == target);
+            if (hit && lane == 0) {
+                const int s2 = __ffs(hit) - 1;
+                const uint32_t bit = (mn[lat] >> s) & 1u;
+                w.bmask[lat * N + j] = (w.bmask[lat * N + j] & ~(1u << s2)) | (bit << s2);
             }
-            T.store(gp);
+            __syncwarp();
         }
     }
     __syncwarp();
 }
 
 // ---------------------------------------------------------------- the walker kernel
-// Persistent kernel: one warp (= one CTA of 32 threads) per resident slot; every slot claims work
-// units (chunk c of `chunk` MC cycles of walker wi) from a global counter in chunk-major order and
-// advances that walker through the hot part of mc_cycle (mc_moves.F90:117-255).  Chunk c of a
-// walker starts only after its chunk c-1 was published (sched[1 + wi] >= c); since units are
-// claimed in order and every claimed unit is resident, the wait cannot deadlock.  The tail of a
-// launch is then at most one chunk long, whatever the ratio of walkers to resident slots.
-struct Sched { int ncycles, chunk, nchunks; int* state; };     // state[0] = next unit, state[1 + w] = chunks done
-
+// One warp (= one CTA of 32 threads) per walker; ncycles MC cycles of the hot
+// part of mc_cycle (mc_moves.F90:117-255).
 template <int NLAT>
-__global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_constant__ DeviceState S,
-                                                             const __grid_constant__ McParams p,
-                                                             const __grid_constant__ Sched sd)
+__global__ void __launch_bounds__(32) k_mc_run(const __grid_constant__ DeviceState S,
+                                               const __grid_constant__ McParams p, int ncycles)
 {
     extern __shared__ __align__(16) unsigned char smem[];
+    const int wi = blockIdx.x;
+    if (wi >= S.W) return;
     const int lane = lane_id();
     const int N = S.N;
-    const double Nd = (double)N;
-    const int nunits = sd.nchunks * S.W;
-  for (;;) {
-    int unit = 0;
-    if (lane == 0) unit = atomicAdd(sd.state, 1);
-    unit = __shfl_sync(FULL, unit, 0);
-    if (unit >= nunits) break;
-    const int chunk_id = unit / S.W;
-    const int wi = unit - chunk_id * S.W;
-    const int ncycles = min(sd.chunk, sd.ncycles - chunk_id * sd.chunk);
-    if (chunk_id > 0) {
-        if (lane == 0) {
-            volatile int* done = sd.state + 1 + wi;
-            while (*done < chunk_id) __nanosleep(256);
-        }
-        __syncwarp();
-        __threadfence();
-    }
-    const WalkerRef ref{smem, S.list + (size_t)wi * NLAT * N * LC, S.ten + (size_t)wi * NLAT * N * TS,
-                        S.disp + (size_t)wi * NLAT * N, N, NLAT};
-    const WalkerView w = ref.view();
+    const WalkerView w = carve_walker(smem, N, NLAT);
     load_walker(S, wi, w);
-    init_ones_row(w.q);
     WalkerScalars* sc = w.sc;
+    const double Nd = (double)N;
     double* wgt = S.weight + (size_t)wi * S.NB;
     double* hist = S.hist + (size_t)wi * S.NB;
     double* uhist = S.uhist + (size_t)wi * S.NB;
     int err = 0;
     if (p.prob_error) err |= ERR_PROB;
 
-    if (!sc->tensors_valid) rebuild_tensors_all(ref);
+#pragma unroll
+    for (int lat = 0; lat < NLAT; ++lat) compute_bond_masks_warp(smem, N, NLAT, lat);
 
-    Rng rng{ref, wi, &S, &p, w.rngbuf, w.rngbase, 0};
+    Rng rng{smem, N, NLAT, wi, &S, &p, w.rngbuf, w.rngbase, 0};
     {
         const uint64_t idx = sc->rng_index;
         *w.rngbase = idx & ~(uint64_t)1;
         rng.pos = (int)(idx & 1);
-        rng_refill(ref, S, p, wi);
+        rng_refill(smem, N, NLAT, S, p, wi);
     }
     if (NLAT == 2) { w.lv[0] = log(sc->vol[0] / sc->vol[1]); w.lv[1] = log(sc->vol[1] / sc->vol[0]); }
 
-    for (int cyc = 0; cyc < ncycles && !((err | sc->error) & (ERR_WINDOW | ERR_PROB)); ++cyc) {
+    for (int cyc = 0; cyc < ncycles && !(err & (ERR_WINDOW | ERR_PROB)); ++cyc) {
         const int cycle = sc->cycle + 1;
         sc->cycle = cycle;
         if (p.dd) {                                            // mc_moves.F90:181-210
@@ -595,10 +529,9 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
         if (cycle % p.list_update_int == 0) {                  // :218-222
 #pragma unroll
             for (int lat = 0; lat < NLAT; ++lat) {
-                err |= compute_neighbours_warp(ref, lat);
-                reset_guard(w, lat);
+                err |= compute_neighbours_warp(smem, N, NLAT, lat);
+                compute_bond_masks_warp(smem, N, NLAT, lat);
             }
-            rebuild_tensors_all(ref);
         }
         const bool dd_eq = p.dd && (cycle < p.eq_mc_cycles);
         const bool bins_on = !(cycle < p.eq_mc_cycles);        // mc_update_wl_bins: :1615
@@ -616,9 +549,6 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
                 if (imol > N) imol = N;
                 imol -= 1;
                 if (lane == 0) atomicAdd(S.transcount + (size_t)wi * N + imol, 1);
-                // this lane's entries of imol's Verlet rows: in flight while the displacement is generated
-                const uint32_t e0 = __ldcg(w.list + (size_t)imol * LC + lane);
-                const uint32_t e1 = (NLAT == 2) ? (uint32_t)__ldcg(w.list + ((size_t)N + imol) * LC + lane) : 0u;
                 x = rng.draw();
                 double y = rng.draw();
                 double z = rng.draw();
@@ -642,25 +572,20 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
                     by = xa(xa(xm(MW_H(hm,2,1), sx), xm(MW_H(hm,2,2), sy)), xm(MW_H(hm,2,3), sz));
                     bz = xa(xa(xm(MW_H(hm,3,1), sx), xm(MW_H(hm,3,2), sy)), xm(MW_H(hm,3,3), sz));
                 }
-                // trial displacement tv[lat][d] and trial position pn[lat][d] live in shared memory
-                // (uniform values): lane l < 6 owns component l
-                float tlen0, tlen1 = 0.f;                      // displacement lengths, rounded up (guard)
-                {
-                    const float fa = sqrtf((float)(x * x + y * y + z * z)) * 1.0001f;
-                    const float fb = sqrtf((float)(bx * bx + by * by + bz * bz)) * 1.0001f;
-                    tlen0 = one ? fa : fb; tlen1 = one ? fb : fa;
-                    __syncwarp();
-                    if (lane < NLAT * 3) {
-                        const int lat = lane / 3, d = lane - lat * 3;
-                        const bool act = (lat == 0) == one;    // this lattice is the active one
-                        const double t = (d == 0) ? (act ? x : bx) : (d == 1) ? (act ? y : by) : (act ? z : bz);
-                        w.tv[lane] = t;
-                        w.pn[lane] = xa(w.pos[lat * 3 * N + d * N + imol], t);
-                    }
-                    __syncwarp();
+                double tv[2][3];
+                tv[0][0] = one ? x : bx; tv[0][1] = one ? y : by; tv[0][2] = one ? z : bz;
+                tv[1][0] = one ? bx : x; tv[1][1] = one ? by : y; tv[1][2] = one ? bz : z;
+                double pnew[2][3];
+#pragma unroll
+                for (int lat = 0; lat < NLAT; ++lat) {
+                    const double* P = w.pos + lat * 3 * N;
+                    pnew[lat][0] = xa(P[imol], tv[lat][0]);
+                    pnew[lat][1] = xa(P[N + imol], tv[lat][1]);
+                    pnew[lat][2] = xa(P[2 * N + imol], tv[lat][2]);
                 }
                 double eo[2] = {0.0, 0.0}, en[2] = {0.0, 0.0};
-                local_energies_warp<NLAT, true>(ref, w, imol, e0, e1, tlen0, tlen1, eo, en);
+                uint32_t mo[2] = {0, 0}, mn[2] = {0, 0};
+                local_energies_warp<NLAT, true>(w, imol, pnew, eo, en, mo, mn);
 
                 // model_energy bookkeeping exactly as :1013-1016, :1087-1090
                 const double Eb0 = sc->E[0], Eb1 = sc->E[1];
@@ -711,11 +636,17 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
                     if (dmu > sc->max_dmu) sc->max_dmu = dmu;
                     sc->E[0] = Ea0;
                     if (NLAT == 2) { sc->E[1] = Ea1; sc->mu = mu_acc; }
-                    commit_translation<NLAT>(w, imol, tlen0, tlen1);
+                    commit_translation<NLAT>(w, imol, pnew, mo, mn);
                 } else {
                     // reject: the reference restores by (x+t)-t, not by copy (mc_moves.F90:1186)
                     __syncwarp();
-                    if (lane < NLAT * 3) w.pos[(lane / 3) * 3 * N + (lane % 3) * N + imol] = xs(w.pn[lane], w.tv[lane]);
+#pragma unroll
+                    for (int lat = 0; lat < NLAT; ++lat) {
+                        double* P = w.pos + lat * 3 * N;
+                        const double pn = (lane == 0) ? pnew[lat][0] : (lane == 1) ? pnew[lat][1] : pnew[lat][2];
+                        const double tt = (lane == 0) ? tv[lat][0] : (lane == 1) ? tv[lat][1] : tv[lat][2];
+                        if (lane < 3) P[lane * N + imol] = xs(pn, tt);
+                    }
                     if (NLAT == 2) sc->mu = mu_rej;
                     __syncwarp();
                 }
@@ -729,7 +660,7 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
                         const double uf = __shfl_sync(FULL, ex, accepted ? 3 : 4);
                         if (lane == 0) atomicAdd(uhist + kb - 1, c * uf);
                     } else {
-                        update_weights(ref, p, S.binwidth, wgt, hist, kb);
+                        update_weights(smem, N, NLAT, p, S.binwidth, wgt, hist, kb);
                     }
                 }
                 // ====================== mc_lattice_switch (mc_moves.F90:1536-1594) ======================
@@ -744,13 +675,13 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
                     sc->att_s += 1;
                 } else if (do_switch) {
                     // weights may have moved in update_weights: the reference looks eta up again
-                    rng.pos = lattice_switch_cold(ref, S, p, wi, rng.pos);
+                    rng.pos = lattice_switch_cold(smem, S, p, wi, NLAT, rng.pos);
                 }
                 continue;
             }
             // ---------------- rare move types ----------------
             if (xi < p.volP) {
-                rng.pos = volume_move<NLAT>(ref, S, p, wi, rng.pos);
+                rng.pos = volume_move<NLAT>(smem, S, p, wi, rng.pos);
                 const EtaBin eb = eta_bin(p, S.mubin, S.ginv, sc, wgt, sc->mu);
                 if (bins_on && eb.k >= 1 && eb.k <= p.nbins) {
                     const double c = __ldg(S.hinc + eb.k - 1);
@@ -758,14 +689,14 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
                     if (p.samplerun) {
                         if (lane == 0) atomicAdd(uhist + eb.k - 1, c * exp(eb.eta - p.log_unbiased_norm));
                     } else {
-                        update_weights(ref, p, S.binwidth, wgt, hist, eb.k);
+                        update_weights(smem, N, NLAT, p, S.binwidth, wgt, hist, eb.k);
                     }
                 }
                 sc->att_v += 1;
             } else if (xi < p.swP) {
-                if (NLAT == 2 && !dd_eq) rng.pos = lattice_switch_cold(ref, S, p, wi, rng.pos);
+                if (NLAT == 2 && !dd_eq) rng.pos = lattice_switch_cold(smem, S, p, wi, NLAT, rng.pos);
             }
-            if (do_switch) rng.pos = lattice_switch_cold(ref, S, p, wi, rng.pos);
+            if (do_switch) rng.pos = lattice_switch_cold(smem, S, p, wi, NLAT, rng.pos);
         }
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {                 // :253-255
@@ -779,12 +710,7 @@ __global__ void __launch_bounds__(32, MC_BLOCKS_PER_SM) k_mc_run(const __grid_co
     sc->rng_index = idx;
     sc->error |= err;
     __syncwarp();
-    store_walker(S, wi, w);
-    // publish: this walker's next chunk may start (on any SM)
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) atomicExch(sd.state + 1 + wi, chunk_id + 1);
-  }
+    store_walker(S, wi, w, true);
 }
 
 }  // namespace mw

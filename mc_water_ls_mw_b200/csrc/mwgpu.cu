@@ -12,7 +12,6 @@
 #include <cstring>
 #include <string>
 #include <vector>
-#include <algorithm>
 #include <dlfcn.h>
 
 using namespace mw;
@@ -59,8 +58,6 @@ struct mwgpu_ctx {
     size_t iout_ints = 0;
     double* delta = nullptr;       // [3][NBP] summed increments
     double* fifo = nullptr;
-    int* sched = nullptr;          // [1 + W] unit counter + per-walker chunks done (k_mc_run)
-    int mc_grid = 0;               // resident slots of k_mc_run on this device
     int64_t launches = 0;
     float last_ms = 0.f;
     std::vector<double> h_mubin, h_binwidth;
@@ -121,11 +118,8 @@ extern "C" int mwgpu_create(int nwater, int nlat, int nwalkers, int device, mwgp
     rc |= dalloc(&S.niv, W * 2);
     rc |= dalloc(&S.list, W * L * N * LC);
     rc |= dalloc(&S.nn, W * L * N);
-    rc |= dalloc(&S.ten, W * L * N * TS);
-    rc |= dalloc(&S.disp, W * L * N);
     rc |= dalloc(&S.scal, W);
     rc |= dalloc(&S.transcount, W * N);
-    rc |= dalloc(&c->sched, W + 1);
     c->stage_doubles = W * L * (2 * 3 * N + 9);
     rc |= dalloc(&c->stage, c->stage_doubles);
     c->out_doubles = W * 2 > N ? W * 2 : N;
@@ -151,9 +145,9 @@ extern "C" void mwgpu_destroy(mwgpu_ctx* c)
     cudaSetDevice(c->device);
     nccl_destroy(c);
     DeviceState& S = c->S;
-    void* ptrs[] = {S.pos, S.ref, S.cell, S.recip, S.refcell, S.iv, S.niv, S.list, S.nn, S.ten, S.disp, S.scal,
+    void* ptrs[] = {S.pos, S.ref, S.cell, S.recip, S.refcell, S.iv, S.niv, S.list, S.nn, S.scal,
                     S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.transcount, S.mubin,
-                    S.binwidth, S.ginv, S.hinc, c->stage, c->out, c->iout, c->delta, c->fifo, c->sched};
+                    S.binwidth, S.ginv, S.hinc, c->stage, c->out, c->iout, c->delta, c->fifo};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -249,7 +243,6 @@ __global__ void k_unpack(DeviceState S, const double* __restrict__ ljr, const do
         const double v = hm[(bcast ? 0 : (size_t)w * L * 9) + rem];
         S.cell[(size_t)(w0 + w) * L * 9 + rem] = v;
         S.refcell[(size_t)(w0 + w) * L * 9 + rem] = v;
-        if (rem == 0) S.scal[w0 + w].tensors_valid = 0;      // positions changed under the bond-tensor cache
     }
 }
 
@@ -366,65 +359,61 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
     const int wi = a.w0 + blockIdx.x;
     if (wi >= S.W) return;
     const int lane = lane_id(), N = S.N;
-    const WalkerRef ref{smem, S.list + (size_t)wi * NLAT * N * LC, S.ten + (size_t)wi * NLAT * N * TS,
-                        S.disp + (size_t)wi * NLAT * N, N, NLAT};
-    const WalkerView w = ref.view();
+    const WalkerView w = carve_walker(smem, N, NLAT);
     load_walker(S, wi, w);
-    init_ones_row(w.q);
     WalkerScalars* sc = w.sc;
     int err = 0;
+    bool store_lists = false;
 
     switch (a.op) {
     case OP_ENERGY_INIT: {
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {
             sc->vol[lat] = cell_volume(w, lat);                         // molint.F90:125
-            refresh_recip(ref, lat);                                    // init.f90:90
+            refresh_recip(smem, N, NLAT, lat);                          // init.f90:90
         }
         sc->error = 0;
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat) {
-            err |= compute_neighbours_warp(ref, lat);                   // includes compute_ivects
-            reset_guard(w, lat);
-            sc->E[lat] = full_energy_warp(ref, lat, 3);
+            err |= compute_neighbours_warp(smem, N, NLAT, lat);         // includes compute_ivects
+            sc->E[lat] = full_energy_warp(smem, N, NLAT, lat);
         }
-        sc->tensors_valid = 1;
         if (NLAT == 2 && a.refresh_mu) {      // mc_moves.F90:857-862 (left-to-right association)
             double mu = sc->E[0] + a.pressure * sc->vol[0] - sc->E[1] - a.pressure * sc->vol[1];
             if (a.leshift) mu = mu - sc->refH[0] + sc->refH[1];
             sc->mu = mu * a.beta - (double)N * log(sc->vol[0] / sc->vol[1]);
         }
+        store_lists = true;
         break;
     }
     case OP_IVECTS:
-        err |= compute_ivects_warp(ref, a.lat);
-        sc->tensors_valid = 0;
+        err |= compute_ivects_warp(smem, N, NLAT, a.lat);
         break;
     case OP_NEIGHBOURS:
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat)
-            if (a.lat < 0 || a.lat == lat) { err |= compute_neighbours_warp(ref, lat); reset_guard(w, lat); }
-        sc->tensors_valid = 0;
+            if (a.lat < 0 || a.lat == lat) err |= compute_neighbours_warp(smem, N, NLAT, lat);
+        store_lists = true;
         break;
     case OP_MODEL_ENERGY:
 #pragma unroll
         for (int lat = 0; lat < NLAT; ++lat)
             if (a.lat < 0 || a.lat == lat) {
-                const double e = full_energy_warp(ref, lat, 1);
+                const double e = full_energy_warp(smem, N, NLAT, lat);
                 sc->E[lat] = e;
                 if (a.out && lane == 0) a.out[(size_t)(wi - a.w0) * NLAT + lat] = e;
             }
         break;
     case OP_LOCAL_ONE:
     case OP_LOCAL_ALL: {
-        if (!sc->tensors_valid) rebuild_tensors_all(ref);
+#pragma unroll
+        for (int lat = 0; lat < NLAT; ++lat) compute_bond_masks_warp(smem, N, NLAT, lat);
         const int i0 = (a.op == OP_LOCAL_ONE) ? a.imol : 0;
         const int i1 = (a.op == OP_LOCAL_ONE) ? a.imol + 1 : N;
         for (int i = i0; i < i1; ++i) {
             double eo[2] = {0, 0}, en[2] = {0, 0};
-            const uint32_t e0 = __ldcg(w.list + (size_t)i * LC + lane);
-            const uint32_t e1 = (NLAT == 2) ? (uint32_t)__ldcg(w.list + ((size_t)N + i) * LC + lane) : 0u;
-            local_energies_warp<NLAT, false>(ref, w, i, e0, e1, 0.f, 0.f, eo, en);
+            uint32_t mo[2], mn[2];
+            local_energies_warp<NLAT, false>(w, i, nullptr, eo, en, mo, mn);
             if (lane == 0) a.out[i - i0] = (a.lat == 0) ? eo[0] : eo[1];
         }
         break;
@@ -438,9 +427,7 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
             sc->dv_max = fmax(xd(xm(sc->dv_max, avr), a.target_ratio), 0.0001);
         }
 #pragma unroll
-        for (int lat = 0; lat < NLAT; ++lat) sc->E[lat] = full_energy_warp(ref, lat, 3);   // :1786-1792
-        sc->tensors_valid = 1;
-        sc->fast_moves = 0; sc->slow_moves[0] = sc->slow_moves[1] = sc->slow_moves[2] = sc->slow_moves[3] = 0;
+        for (int lat = 0; lat < NLAT; ++lat) sc->E[lat] = full_energy_warp(smem, N, NLAT, lat);   // :1786-1792
         sc->acc_r = 0; sc->acc_v = 0; sc->acc_s = 0; sc->att_r = 0; sc->att_v = 0; sc->att_s = 0; // :1797-1810
         for (int i = lane; i < N; i += 32) S.transcount[(size_t)wi * N + i] = 0;
         sc->avgE[0] = 0.0; sc->avgE[1] = 0.0;
@@ -450,13 +437,13 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
     case OP_CHAIN_SYNC: {
         // mc_moves.F90:2217-2416 (two lattices only)
         if (NLAT == 2) {
-            sc->E[0] = full_energy_warp(ref, 0, 1);
-            sc->E[1] = full_energy_warp(ref, 1, 1);
+            sc->E[0] = full_energy_warp(smem, N, NLAT, 0);
+            sc->E[1] = full_energy_warp(smem, N, NLAT, 1);
             const double* rh = S.refcell + (size_t)wi * NLAT * 9;
             if (lane < 9) w.cell[9 + lane] = xa(rh[9 + lane], xs(w.cell[lane], rh[lane]));     // :2262,2277
             __syncwarp();
-            refresh_recip(ref, 0);
-            refresh_recip(ref, 1);
+            refresh_recip(smem, N, NLAT, 0);
+            refresh_recip(smem, N, NLAT, 1);
             const double* R = S.ref + (size_t)wi * NLAT * 3 * N;
             for (int i = lane; i < N; i += 32) {
                 double sv[2][3], rsv[2][3];
@@ -492,13 +479,10 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
 #pragma unroll
             for (int lat = 0; lat < 2; ++lat) {
                 sc->vol[lat] = cell_volume(w, lat);
-                err |= compute_ivects_warp(ref, lat);
+                err |= compute_ivects_warp(smem, N, NLAT, lat);
             }
-            sc->E[0] = full_energy_warp(ref, 0, 3);
-            sc->E[1] = full_energy_warp(ref, 1, 3);
-            sc->tensors_valid = 1;
-            // lattice 2 was moved by an unbounded amount relative to its lists: no tensor path until the next list build
-            sc->rn_eff[1] = 0.f;
+            sc->E[0] = full_energy_warp(smem, N, NLAT, 0);
+            sc->E[1] = full_energy_warp(smem, N, NLAT, 1);
             // left-to-right association (:2400-2402)
             double mu = sc->E[0] + a.pressure * sc->vol[0] - sc->E[1] - a.pressure * sc->vol[1];
             if (a.leshift) mu = mu - sc->refH[0] + sc->refH[1];
@@ -510,7 +494,7 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
     }
     sc->error |= err;
     __syncwarp();
-    store_walker(S, wi, w);
+    store_walker(S, wi, w, store_lists);
 }
 
 static int launch_op(mwgpu_ctx* c, OpArgs a, int nw, bool sync = true)
@@ -669,17 +653,18 @@ __global__ void __launch_bounds__(32) k_model_energy_all(const __grid_constant__
     const int wi = unit / S.nlat, lat = unit % S.nlat;
     const int lane = lane_id(), N = S.N;
     // a one-lattice view: lattice `lat` of the walker is staged as lattice 0
-    const WalkerRef ref{smem, S.list + ((size_t)wi * S.nlat + lat) * N * LC, nullptr, nullptr, N, 1};
-    const WalkerView w = ref.view();
+    const WalkerView w = carve_walker(smem, N, 1);
     const double* gp = S.pos + ((size_t)wi * S.nlat + lat) * 3 * N;
     for (int t = lane; t < 3 * N; t += 32) w.pos[t] = gp[t];
     const double* gi = S.iv + ((size_t)wi * S.nlat + lat) * 3 * IVC;
     for (int t = lane; t < 3 * IVC; t += 32) w.iv[t] = gi[t];
+    const uint4* gl = (const uint4*)(S.list + ((size_t)wi * S.nlat + lat) * N * LC);
+    uint4* sl = (uint4*)w.list;
+    for (int t = lane; t < N * LC / 8; t += 32) sl[t] = gl[t];
     const uint8_t* gn = S.nn + ((size_t)wi * S.nlat + lat) * N;
     for (int t = lane; t < N; t += 32) w.nn[t] = gn[t];
     __syncwarp();
-    init_ones_row(w.q);
-    const double e = full_energy_warp(ref, 0, 1);
+    const double e = full_energy_warp(smem, N, 1, 0);
     if (lane == 0) {
         S.scal[wi].E[lat] = e;
         if (out) out[unit] = e;
@@ -811,11 +796,11 @@ extern "C" int mwgpu_mc_init(mwgpu_ctx* c, const mwgpu_mc_params* up, int first_
     CUDA_TRY(cudaMemcpy(S.mubin, mu_bin.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(S.binwidth, bw.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
     {
-        std::vector<double> ginv(nb, 0.0);
-        for (int k = 0; k + 1 < nb; ++k) ginv[k] = 2.0 / (bw[k] + bw[k + 1]);
-        CUDA_TRY(cudaMemcpy(S.ginv, ginv.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
-        for (int k = 0; k < nb; ++k) ginv[k] = av_bw / bw[k];
-        CUDA_TRY(cudaMemcpy(S.hinc, ginv.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
+        std::vector<double> tab(nb, 0.0);
+        for (int k = 0; k + 1 < nb; ++k) tab[k] = 2.0 / (bw[k] + bw[k + 1]);
+        CUDA_TRY(cudaMemcpy(S.ginv, tab.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
+        for (int k = 0; k < nb; ++k) tab[k] = av_bw / bw[k];
+        CUDA_TRY(cudaMemcpy(S.hinc, tab.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
     }
 
     // ---- per-walker scalars: windows (:659-722), ref_enthalpy (main.f90:146-150), mu (:857-862)
@@ -869,8 +854,7 @@ extern "C" int mwgpu_mc_init(mwgpu_ctx* c, const mwgpu_mc_params* up, int first_
         sc.rng_index = 0; sc.cycle = 0;
         sc.acc_r = sc.acc_v = sc.acc_s = sc.att_r = sc.att_v = sc.att_s = 0;
         sc.in_window = u.dd ? 0 : 1;
-        sc.wl_invt_active = 0; sc.wmin_zero = 0; sc.error = 0; sc.fast_moves = 0;
-        sc.slow_moves[0] = sc.slow_moves[1] = sc.slow_moves[2] = sc.slow_moves[3] = 0;
+        sc.wl_invt_active = 0; sc.wmin_zero = 0; sc.error = 0;
         for (int i = 0; i < nb; ++i) {
             hb[(size_t)w * nb + i] = weight[i];                            // eta_last_sync = weight (:776)
             double v = weight[i];
@@ -946,40 +930,22 @@ extern "C" int mwgpu_mc_set_rng_fifo(mwgpu_ctx* c, const double* u, int64_t n)
 // ------------------------------------------------------------------------------------------------
 // the hot loop
 // ------------------------------------------------------------------------------------------------
-template <int NLAT>
-static int launch_mc(mwgpu_ctx* c, int ncycles)
-{
-    const size_t smem = walker_smem_bytes(c->N, c->nlat);
-    if (!c->mc_grid) {
-        CUDA_TRY(cudaFuncSetAttribute(k_mc_run<NLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0, sms = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mc_run<NLAT>, 32, smem));
-        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-        if (per_sm < 1) return fail("mwgpu_mc_run: the walker kernel does not fit on this device");
-        c->mc_grid = per_sm * sms;                  // every block of the grid is resident: units may wait on each other
-    }
-    Sched sd;
-    sd.ncycles = ncycles;
-    sd.chunk = 1;                                   // work unit = one MC cycle of one walker
-    sd.nchunks = (ncycles + sd.chunk - 1) / sd.chunk;
-    sd.state = c->sched;
-    const long long nunits = (long long)sd.nchunks * c->W;
-    if (nunits > 0x7fffffffLL) return fail("mwgpu_mc_run: too many work units in one launch");
-    CUDA_TRY(cudaMemsetAsync(c->sched, 0, sizeof(int) * (c->W + 1), c->stream));
-    const int grid = (int)std::min<long long>(nunits, c->mc_grid);
-    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    if (grid > 0) k_mc_run<NLAT><<<grid, 32, smem, c->stream>>>(c->S, c->P, sd);
-    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
-    c->launches++;
-    return 0;
-}
-
 static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
 {
     if (int rc = check_ctx(c, 0, false)) return rc;
     if (!c->mc_ready) return fail("mwgpu_mc_run: call mwgpu_mc_init first");
     if (ncycles < 0) return fail("mwgpu_mc_run: ncycles must be >= 0");
-    if (int rc = (c->nlat == 2) ? launch_mc<2>(c, ncycles) : launch_mc<1>(c, ncycles)) return rc;
+    const size_t smem = walker_smem_bytes(c->N, c->nlat);
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    if (c->nlat == 2) {
+        CUDA_TRY(cudaFuncSetAttribute(k_mc_run<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_mc_run<2><<<c->W, 32, smem, c->stream>>>(c->S, c->P, ncycles);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_mc_run<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_mc_run<1><<<c->W, 32, smem, c->stream>>>(c->S, c->P, ncycles);
+    }
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->launches++;
     if (int rc = finish(c, sync)) return rc;
     if (sync) return collect_errors(c, "mwgpu_mc_run");
     return 0;
@@ -1098,29 +1064,6 @@ extern "C" int mwgpu_mc_set_active_lattice(mwgpu_ctx* c, int walker, int ls)
     CUDA_TRY(cudaMemcpy(h.data(), c->S.scal, sizeof(WalkerScalars) * c->W, cudaMemcpyDeviceToHost));
     for (int w = 0; w < c->W; ++w) if (walker < 0 || walker == w) h[w].ls = ls;
     CUDA_TRY(cudaMemcpy(c->S.scal, h.data(), sizeof(WalkerScalars) * c->W, cudaMemcpyHostToDevice));
-    return 0;
-}
-
-extern "C" int mwgpu_mc_set_exact_enumeration(mwgpu_ctx* c, int walker, int exact)
-{
-    if (int rc = check_ctx(c, walker, true)) return rc;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    std::vector<WalkerScalars> h(c->W);
-    CUDA_TRY(cudaMemcpy(h.data(), c->S.scal, sizeof(WalkerScalars) * c->W, cudaMemcpyDeviceToHost));
-    for (int w = 0; w < c->W; ++w) if (walker < 0 || walker == w) h[w].force_exact = exact ? 1 : 0;
-    CUDA_TRY(cudaMemcpy(c->S.scal, h.data(), sizeof(WalkerScalars) * c->W, cudaMemcpyHostToDevice));
-    return 0;
-}
-
-extern "C" int mwgpu_mc_get_path_counts(mwgpu_ctx* c, int walker, int* counts)
-{
-    if (int rc = check_ctx(c, walker, false)) return rc;
-    if (!counts) return fail("mwgpu_mc_get_path_counts: NULL");
-    WalkerScalars s;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaMemcpy(&s, c->S.scal + walker, sizeof(s), cudaMemcpyDeviceToHost));
-    counts[0] = s.fast_moves;
-    for (int k = 0; k < 4; ++k) counts[1 + k] = s.slow_moves[k];
     return 0;
 }
 

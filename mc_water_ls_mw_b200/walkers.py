@@ -208,19 +208,6 @@ class WalkerBatch:
     def set_active_lattice(self, ls: int, walker: int = -1) -> None:
         check(self.L.mwgpu_mc_set_active_lattice(self.h, walker, int(ls)))
 
-    def set_exact_enumeration(self, exact: bool, walker: int = -1) -> None:
-        """Force the reference's triplet enumeration (True) instead of the bond-tensor path."""
-        check(self.L.mwgpu_mc_set_exact_enumeration(self.h, walker, 1 if exact else 0))
-
-    def path_counts(self, walker: int = 0):
-        """[tensor path, enumeration: image pair, close contact, stale-list guard, forced]."""
-        n = (C.c_int * 5)()
-        check(self.L.mwgpu_mc_get_path_counts(self.h, walker, n))
-        return list(n)
-
-    def fast_moves(self, walker: int = 0) -> int:
-        return self.path_counts(walker)[0]
-
     def mc_monitor(self) -> None:
         check(self.L.mwgpu_mc_monitor(self.h))
 

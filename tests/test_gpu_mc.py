@@ -229,54 +229,3 @@ def test_full_size_properties_4096_walkers():
     o.set_rng_philox(SEED, 1234, 1000000)
     assert o.mc_run(20) == 0
     np.testing.assert_array_equal(g.download(1234)[0], o.ljr)
-
-
-@pytest.mark.parametrize("ex", ["ice1_sample", "single_box", "ice1_gen_weights"])
-def test_tensor_path_equals_exact_enumeration(ex):
-    """The bond-tensor evaluation of the triplet sums and the reference's enumeration
-    must drive the same Markov chain: identical accept/reject history and positions, energies 1e-11."""
-    ov = {"eq_mc_cycles": 5, "mc_max_trans": 0.3 / 0.5291772108}       # a tuned step size (~50 % acceptance)
-    nw = 8
-    fast, up = make_gpu_walkers(ex, nwalkers=nw, overrides=ov)
-    exact, _ = make_gpu_walkers(ex, nwalkers=nw, overrides=ov)
-    exact.set_exact_enumeration(True)
-    for g in (fast, exact):
-        g.set_rng_philox(SEED, 0, 1000000)
-    for chunk in (25, 25, 35):
-        fast.mc_run(chunk); exact.mc_run(chunk)
-        fast.mc_monitor(); exact.mc_monitor()          # equilibration step-size tuning in between
-    fast.mc_run(40); exact.mc_run(40)
-    lf, rf, hf = fast.download_all(); le, re_, he = exact.download_all()
-    np.testing.assert_array_equal(lf, le); np.testing.assert_array_equal(hf, he); np.testing.assert_array_equal(rf, re_)
-    nl = up.num_lattices
-    tot_fast = tot_att = 0
-    reasons = np.zeros(5, dtype=np.int64)
-    for w in range(nw):
-        reasons += np.array(fast.path_counts(w))
-        sf, se = fast.state(w), exact.state(w)
-        assert list(sf.accepted) == list(se.accepted) and list(sf.attempted) == list(se.attempted)
-        assert sf.rng_index == se.rng_index
-        assert rel_err(list(sf.model_energy)[:nl], list(se.model_energy)[:nl]) < TOL
-        assert exact.fast_moves(w) == 0
-        tot_fast += fast.fast_moves(w); tot_att += sf.attempted[0]
-    # with tuned step sizes nearly every trial move qualifies for the tensor path
-    # (reasons[2] = tensor path with some centres re-done by enumeration because of a close contact)
-    assert tot_fast + reasons[2] > 0.9 * tot_att and tot_fast > 0.5 * tot_att, (tot_fast, tot_att, reasons.tolist())
-
-
-def test_local_energy_api_tensor_vs_exact():
-    """Fine-grained compute_local_real_energy on thermalised configurations: tensor path vs enumeration vs oracle."""
-    ov = {"eq_mc_cycles": 5}
-    g, up = make_gpu_walkers("ice1_sample", overrides=ov)
-    o, _ = make_oracle_walker("ice1_sample", overrides=ov)
-    g.set_rng_philox(SEED, 0, 1000000); o.set_rng_philox(SEED, 0, 1000000)
-    g.mc_run(37); assert o.mc_run(37) == 0
-    for l in (1, 2):
-        want = np.array([o.compute_local_real_energy(i + 1, l) for i in range(up.nwater)])
-        n0 = g.fast_moves()
-        got_fast = g.compute_local_real_energy_all(l)
-        assert g.fast_moves() - n0 > 0
-        g.set_exact_enumeration(True)
-        got_exact = g.compute_local_real_energy_all(l)
-        g.set_exact_enumeration(False)
-        assert rel_err(got_fast, want) < TOL and rel_err(got_exact, want) < TOL
