@@ -51,6 +51,7 @@ constexpr int IVC = 32;    // image vectors per lattice (27 in every BASELINE co
 constexpr int QC  = 64;    // bond records per batch (a trial move has ~26; more than QC in-range bonds -> ERR_BOND_OVERFLOW)
 constexpr int CC  = 64;    // triplet centres per trial move: 2 lattices x LC slots
 constexpr int RB  = 64;    // random numbers buffered per refill
+constexpr int KC  = 256;   // (centre, bond) candidates of the j-centred triplets of one trial move (~90)
 constexpr int NMAX = 1024; // molecules (10 bits of a packed list entry)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint16_t NONE16 = 0xffffu;
@@ -60,7 +61,7 @@ enum : int {
     ERR_LIST_OVERFLOW  = 1,    // a molecule has more than LC list neighbours
     ERR_IVECT_OVERFLOW = 2,    // more than IVC image vectors (cell shrank below the cut-off)
     ERR_BOND_OVERFLOW  = 4,    // more than QC bonds inside the cut-off in one trial move (unphysical density)
-    ERR_ITEM_OVERFLOW  = 8,    // (unused)
+    ERR_ITEM_OVERFLOW  = 8,    // more than KC neighbour bonds around one trial move (unphysical density)
     ERR_SELF_IMAGE     = 16,   // a molecule is its own list neighbour (cell narrower than 1.18*a*sigma)
     ERR_RNG_UNDERRUN   = 32,   // host FIFO ran dry
     ERR_WINDOW         = 64,   // dd: walker not in its window at eq_mc_cycles (mc_moves.F90:191-201)
@@ -255,6 +256,7 @@ struct WalkerView {
     int*      niv;     // [2]
     uint16_t* cq;      // [CC][2] bond record of the centre in the old / new variant
     uint16_t* cpre;    // [CC+2]  exclusive prefix of the per-centre bond counts
+    uint16_t* cand;    // [KC]    centre<<5 | list slot of every bond of every centre
     uint16_t* list;    // [nlat][N][LC] packed entries img<<10 | j   (0-based)
     uint8_t*  nn;      // [nlat][N]
 };
@@ -273,7 +275,7 @@ __host__ __device__ inline size_t walker_smem_bytes(int N, int nlat)
     b += align16(sizeof(WalkerScalars) + sizeof(uint64_t));
     b += align16(sizeof(uint16_t) * (size_t)nlat * N * LC);                       // list
     b += align16(sizeof(uint32_t) * (QC + CC + (size_t)nlat * N + 2));            // qmeta, cmeta, bmask, niv
-    b += align16(sizeof(uint16_t) * (CC * 2 + CC + 2));                           // cq, cpre
+    b += align16(sizeof(uint16_t) * (CC * 2 + CC + 2 + KC));                      // cq, cpre, cand
     b += align16((size_t)nlat * N);                                               // nn
     return b;
 }
@@ -303,7 +305,8 @@ __device__ __forceinline__ WalkerView carve_walker(unsigned char* base, int N, i
     p += align16(sizeof(uint32_t) * (QC + CC + (size_t)nlat * N + 2));
     w.cq    = (uint16_t*)p;
     w.cpre  = w.cq + CC * 2;
-    p += align16(sizeof(uint16_t) * (CC * 2 + CC + 2));
+    w.cand  = w.cpre + CC + 2;
+    p += align16(sizeof(uint16_t) * (CC * 2 + CC + 2 + KC));
     w.nn    = (uint8_t*)p;
     return w;
 }
@@ -656,26 +659,6 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
             a2 += (c == 2) ? pe : 0.0; a3 += (c == 3) ? pe : 0.0;
         }
     }
-
-    // ---- per-centre bond counts (lanes = centres) -> exclusive prefix in shared memory
-    int ncand = 0;
-    for (int cb = 0; cb < nc; cb += 32) {
-        const int c = cb + lane;
-        int cnt = 0;
-        if (c < nc) {
-            const uint32_t cm = w.cmeta[c];
-            cnt = __popc(w.bmask[(cm & 1) * N + ((cm >> 6) & 1023)]);
-        }
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (c < nc) w.cpre[c] = (uint16_t)(ncand + incl - cnt);
-        ncand += __shfl_sync(FULL, incl, 31);
-    }
-    if (lane == 0) w.cpre[nc] = (uint16_t)ncand;
     __syncwarp();
 
     // ---- stage 3: triplets centred on imol: all pairs (a<b) of bond records of the same evaluation,
@@ -703,49 +686,87 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
         }
     }
 
-    // ---- stages 4+5: j-centred triplets, lanes = (centre, bond of the centre) candidates.  The
-    // centre of a candidate is found by binary search in the prefix table, its list slot as the
-    // rank-th set bit of the centre's bond mask.  Images of imol are skipped (see above).  One
-    // evaluation of (j,k) serves both variants.
-    for (int tb0 = 0; tb0 < ncand; tb0 += 32) {
-        const int t = tb0 + lane;
-        if (t < ncand) {
-            int lo = 0, hi = nc;                       // largest c with cpre[c] <= t
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if ((int)w.cpre[mid] <= t) lo = mid; else hi = mid;
+    // ---- stages 4+5: j-centred triplets.  Centres are taken in groups (all of them, or 8 at a time
+    // when their bonds would not fit the candidate table); per group: bond counts (lanes = centres),
+    // exclusive prefix, expansion of every bond into the table as centre<<5 | list slot; then
+    // lanes = candidates.  Images of imol are skipped (see above).  One evaluation of (j,k) serves
+    // both variants.
+#pragma unroll 1
+    for (int cb = 0; cb < nc;) {
+        const int c0 = cb + lane;
+        int cnt = 0;
+        uint32_t bm0 = 0;
+        if (c0 < nc) {
+            const uint32_t cm = w.cmeta[c0];
+            bm0 = w.bmask[(cm & 1) * N + ((cm >> 6) & 1023)];
+            cnt = __popc(bm0);
+        }
+        int take = 32;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (__shfl_sync(FULL, incl, 31) > KC) {        // unusually crowded: 8 centres (<= 256 bonds) at a time
+            take = 8;
+            if (lane >= 8) { cnt = 0; bm0 = 0; }
+            incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
             }
-            const int c = lo;
-            const uint32_t cm = w.cmeta[c];
-            const int lat = cm & 1, j = (cm >> 6) & 1023;
-            const int s2 = nth_set_bit(w.bmask[lat * N + j], t - (int)w.cpre[c]);
-            const uint32_t e2 = w.list[((size_t)lat * N + j) * LC + s2];
-            const int k = e2 & 1023, img = e2 >> 10;
-            if (k != imol) {
-                const double* P = w.pos + lat * 3 * N;
-                const double* V = w.iv + lat * 3 * IVC;
-                const double tx = (P[k] + V[img]) - P[j];
-                const double ty = (P[N + k] + V[IVC + img]) - P[N + j];
-                const double tz = (P[2 * N + k] + V[2 * IVC + img]) - P[2 * N + j];
-                const double sq = tx * tx + ty * ty + tz * tz;
-                if (sq < RCSQ) {
-                    const double vi = rsqrt_fast(sq);
-                    const double ex = LEPS * exp_fast(GS * rcp_fast(sq * vi - RC));
-                    const double ux = tx * vi, uy = ty * vi, uz = tz * vi;
-                    const uint16_t qo = w.cq[c * 2], qn = w.cq[c * 2 + 1];
-                    double vo = 0.0, vn = 0.0;
-                    if (qo != NONE16) {
-                        const double ct = -(q[qo] * ux + q[QC + qo] * uy + q[2 * QC + qo] * uz);
-                        vo = q[3 * QC + qo] * ex * hfun(ct);
+            const int tot8 = __shfl_sync(FULL, incl, 7);
+            incl = (lane < 8) ? incl : tot8;
+        }
+        const int ncand = __shfl_sync(FULL, incl, 31);
+        {
+            int pos = incl - cnt;
+#pragma unroll 1
+            while (bm0) {
+                const int s2 = __ffs(bm0) - 1; bm0 &= bm0 - 1;
+                w.cand[pos++] = (uint16_t)(((c0 - cb) << 5) | s2);
+            }
+        }
+        __syncwarp();
+        for (int tb0 = 0; tb0 < ncand; tb0 += 32) {
+            const int t = tb0 + lane;
+            if (t < ncand) {
+                const uint32_t ce = w.cand[t];
+                const int c = cb + (int)(ce >> 5), s2 = ce & 31;
+                const uint32_t cm = w.cmeta[c];
+                const int lat = cm & 1, j = (cm >> 6) & 1023;
+                const uint32_t e2 = w.list[((size_t)lat * N + j) * LC + s2];
+                const int k = e2 & 1023, img = e2 >> 10;
+                if (k != imol) {
+                    const double* P = w.pos + lat * 3 * N;
+                    const double* V = w.iv + lat * 3 * IVC;
+                    const double tx = (P[k] + V[img]) - P[j];
+                    const double ty = (P[N + k] + V[IVC + img]) - P[N + j];
+                    const double tz = (P[2 * N + k] + V[2 * IVC + img]) - P[2 * N + j];
+                    const double sq = tx * tx + ty * ty + tz * tz;
+                    if (sq < RCSQ) {
+                        const double vi = rsqrt_fast(sq);
+                        const double ex = LEPS * exp_fast(GS * rcp_fast(sq * vi - RC));
+                        const double ux = tx * vi, uy = ty * vi, uz = tz * vi;
+                        const uint16_t qo = w.cq[c * 2], qn = w.cq[c * 2 + 1];
+                        double vo = 0.0, vn = 0.0;
+                        if (qo != NONE16) {
+                            const double ct = -(q[qo] * ux + q[QC + qo] * uy + q[2 * QC + qo] * uz);
+                            vo = q[3 * QC + qo] * ex * hfun(ct);
+                        }
+                        if (WITH_NEW && qn != NONE16) {
+                            const double ct = -(q[qn] * ux + q[QC + qn] * uy + q[2 * QC + qn] * uz);
+                            vn = q[3 * QC + qn] * ex * hfun(ct);
+                        }
+                        if (lat == 0) { a0 += vo; a1 += vn; } else { a2 += vo; a3 += vn; }
                     }
-                    if (WITH_NEW && qn != NONE16) {
-                        const double ct = -(q[qn] * ux + q[QC + qn] * uy + q[2 * QC + qn] * uz);
-                        vn = q[3 * QC + qn] * ex * hfun(ct);
-                    }
-                    if (lat == 0) { a0 += vo; a1 += vn; } else { a2 += vo; a3 += vn; }
                 }
             }
         }
+        __syncwarp();
+        cb += take;
     }
 
     reduce4(a0, a1, a2, a3);
