@@ -152,3 +152,31 @@ def test_error_behaviour():
     g2.upload(r * 0.3, h * 0.3)
     with pytest.raises(MwgpuError):
         g2.energy_init()
+
+
+@pytest.mark.parametrize("scale", [0.94, 0.92])
+def test_compressed_lattices_crowded_neighbourhoods(scale):
+    """Both example lattices compressed until the second shell (12 molecules) is inside the cut-off:
+    16 bonds per molecule, 28 list entries, > 256 (centre, bond) candidates per local energy -- the
+    kernel then walks the triplet centres in groups of 8 (mw_device.cuh, stages 4+5)."""
+    from mc_water_ls_mw_b200 import walkers as W
+    from oracle import orc
+    up, h, r, _, _ = load_example("ice1_sample")
+    rng = np.random.default_rng(11)
+    ljr = np.asarray(r) * scale + rng.normal(0.0, 0.02, np.asarray(r).shape)
+    hm = np.asarray(h) * scale
+    o = orc.System(up.nwater, up.num_lattices)
+    o.set_config(ljr, hm)
+    o.energy_init()
+    g = W.WalkerBatch(up.nwater, up.num_lattices, 1)
+    g.upload(ljr, hm)
+    g.energy_init()
+    for l in (1, 2):
+        nn, jn, vn = g.get_neighbours(l)
+        onn, ojn, ovn = used_lists(o.nn[l - 1], o.jn[l - 1], o.vn[l - 1])
+        np.testing.assert_array_equal(nn, onn); np.testing.assert_array_equal(jn, ojn); np.testing.assert_array_equal(vn, ovn)
+        assert nn.max() >= 26
+        assert rel_err(g.compute_model_energy(l), o.compute_model_energy(l)) < TOL
+        loc = g.compute_local_real_energy_all(l)
+        oloc = [o.compute_local_real_energy(i + 1, l) for i in range(up.nwater)]
+        assert rel_err(loc, oloc) < TOL
