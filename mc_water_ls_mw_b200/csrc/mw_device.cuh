@@ -661,29 +661,32 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
     }
     __syncwarp();
 
-    // ---- stage 3: triplets centred on imol: all pairs (a<b) of bond records of the same evaluation,
-    // flattened over the 4 evaluations (lanes = pairs)
-    {
-        const int p0 = seg_n[0] * (seg_n[0] - 1) / 2, p1 = p0 + seg_n[1] * (seg_n[1] - 1) / 2;
-        const int p2 = p1 + seg_n[2] * (seg_n[2] - 1) / 2, p3 = p2 + seg_n[3] * (seg_n[3] - 1) / 2;
-        for (int pb = 0; pb < p3; pb += 32) {
-            const int p = pb + lane;
-            if (p < p3) {
-                const int c = (p >= p2) ? 3 : (p >= p1) ? 2 : (p >= p0) ? 1 : 0;
-                const int m = p - ((c == 3) ? p2 : (c == 2) ? p1 : (c == 1) ? p0 : 0);
-                const int s0 = (c == 3) ? seg_start[3] : (c == 2) ? seg_start[2] : (c == 1) ? seg_start[1] : seg_start[0];
-                // m = b(b-1)/2 + a with a < b
-                int bb = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)m)) * 0.5f);
-                if (bb * (bb - 1) / 2 > m) --bb;
-                if ((bb + 1) * bb / 2 <= m) ++bb;
-                const int ra = s0 + (m - bb * (bb - 1) / 2), rb = s0 + bb;
-                const double ct = q[ra] * q[rb] + q[QC + ra] * q[QC + rb] + q[2 * QC + ra] * q[2 * QC + rb];
-                const double mult = ((w.qmeta[ra] >> 8) == (w.qmeta[rb] >> 8)) ? 3.0 * LEPS : LEPS;
-                const double tb = q[3 * QC + ra] * q[3 * QC + rb] * hfun(ct) * mult;
-                a0 += (c == 0) ? tb : 0.0; a1 += (c == 1) ? tb : 0.0;
-                a2 += (c == 2) ? tb : 0.0; a3 += (c == 3) ? tb : 0.0;
+    // ---- stage 3: triplets centred on imol: all pairs (b<c) of bond records of one evaluation
+    // (lanes = records b, loop over the later records c of the same evaluation)
+#pragma unroll 1
+    for (int b0 = 0; b0 < nq; b0 += 32) {
+        const int r = b0 + lane;
+        const bool act = r < nq;
+        const uint32_t qm = act ? w.qmeta[r] : 0u;
+        const int ev = qm & 3;
+        const int send = act ? ((ev == 0) ? seg_start[0] + seg_n[0] : (ev == 1) ? seg_start[1] + seg_n[1]
+                                : (ev == 2) ? seg_start[2] + seg_n[2] : seg_start[3] + seg_n[3]) : 0;
+        const double ux = act ? q[r] : 0.0, uy = act ? q[QC + r] : 0.0, uz = act ? q[2 * QC + r] : 0.0;
+        const double g = act ? q[3 * QC + r] : 0.0;
+        const int maxd = __reduce_max_sync(FULL, act ? send - r - 1 : 0);
+        double tb = 0.0;
+#pragma unroll 1
+        for (int d = 1; d <= maxd; ++d) {
+            const int c = r + d;
+            if (c < send) {
+                const double ct = ux * q[c] + uy * q[QC + c] + uz * q[2 * QC + c];
+                const double mult = ((qm >> 8) == (w.qmeta[c] >> 8)) ? 3.0 : 1.0;   // images of one molecule
+                tb += q[3 * QC + c] * hfun(ct) * mult;
             }
         }
+        tb *= LEPS * g;
+        a0 += (ev == 0) ? tb : 0.0; a1 += (ev == 1) ? tb : 0.0;
+        a2 += (ev == 2) ? tb : 0.0; a3 += (ev == 3) ? tb : 0.0;
     }
 
     // ---- stages 4+5: j-centred triplets.  Centres are taken in groups (all of them, or 8 at a time
