@@ -115,26 +115,33 @@ __device__ __forceinline__ void recipmatrix3(const double* h, double* r)
 __device__ __forceinline__ double rcp_fast(double x)
 {
     double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));       // MUFU.RCP64H seed
-    double e = fma(-x, y, 1.0);                                  // 2 Newton steps: 2^-23 -> 2^-46 -> 2^-92
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));       // MUFU.RCP64H seed (20 mantissa bits of x), e ~ 2^-20
+    const double e = fma(-x, y, 1.0);                            // 1/x = y/(1 - e) = y (1 + e)(1 + e^2) + O(e^4)
+    const double a = fma(y, e, y);                               // a and e*e are independent: 3 deep after the seed
+    return fma(a, e * e, a);
 }
 
 __device__ __forceinline__ double rsqrt_fast(double x)
 {
     double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));     // MUFU.RSQ64H seed
-    double e = fma(-(x * y), y, 1.0);                            // 3 Newton steps (second-order each)
-    y = fma(0.5 * y, e, y);
-    e = fma(-(x * y), y, 1.0);
-    y = fma(0.5 * y, e, y);
-    e = fma(-(x * y), y, 1.0);
-    return fma(0.5 * y, e, y);
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));     // MUFU.RSQ64H seed (20 mantissa bits of x), e = 1 - x y^2 ~ 2^-19
+    const double e = fma(-(x * y), y, 1.0);                      // x^-1/2 = y (1 - e)^-1/2 = y (1 + e/2 + 3e^2/8 + 5e^3/16 + O(e^4))
+    const double p = fma(fma(0.3125, e, 0.375), e, 0.5);         // one quartic step (error 35/128 e^4); p and y*e are independent
+    return fma(y * e, p, y);
 }
 
-// exp(x) for x <= ~700; returns 0 below -708 (the SW terms vanish at the cut-off: x -> -inf)
+// 1/r and 1/(r - a*sigma) = (r + a*sigma)/(r^2 - (a*sigma)^2) of a squared bond length: written so that the
+// reciprocal does not wait for the square root (two independent MUFU + Newton chains)
+__device__ __forceinline__ void bond_radial(double r2, double& ir, double& isr)
+{
+    ir = rsqrt_fast(r2);
+    const double id = rcp_fast(r2 - RC * RC);
+    isr = fma(r2, ir, RC) * id;
+}
+
+// exp(x) for x <= ~700; returns 0 below -708 (the SW terms vanish at the cut-off: x -> -inf).
+// Degree-13 Taylor polynomial on |r| <= ln2/2 in Estrin form (dependency depth 4 after r instead of 13:
+// the walker kernel is bound by latency and instruction supply, not by fp64 throughput).
 __device__ __forceinline__ double exp_fast(double x)
 {
     const double xc = fmax(x, -708.0);
@@ -143,20 +150,22 @@ __device__ __forceinline__ double exp_fast(double x)
     const double fn = t - 6755399441055744.0;
     double r = fma(-fn, 6.93147180369123816490e-01, xc);
     r = fma(-fn, 1.90821492927058770002e-10, r);                           // |r| <= ln2/2
-    double p = 1.6059043836821613e-10;                                     // Taylor, 1/13! ... 1
-    p = fma(p, r, 2.08767569878681e-09);
-    p = fma(p, r, 2.505210838544172e-08);
-    p = fma(p, r, 2.755731922398589e-07);
-    p = fma(p, r, 2.755731922398589e-06);
-    p = fma(p, r, 2.48015873015873e-05);
-    p = fma(p, r, 1.984126984126984e-04);
-    p = fma(p, r, 1.388888888888889e-03);
-    p = fma(p, r, 8.333333333333333e-03);
-    p = fma(p, r, 4.1666666666666664e-02);
-    p = fma(p, r, 1.6666666666666666e-01);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    const double r2 = r * r;
+    const double a0 = 1.0 + r;                                             // 1/0! + r/1!
+    const double a1 = fma(1.6666666666666666e-01, r, 0.5);                 // 1/2! + r/3!
+    const double a2 = fma(8.333333333333333e-03, r, 4.1666666666666664e-02);
+    const double a3 = fma(1.984126984126984e-04, r, 1.388888888888889e-03);
+    const double a4 = fma(2.755731922398589e-06, r, 2.48015873015873e-05);
+    const double a5 = fma(2.505210838544172e-08, r, 2.755731922398589e-07);
+    const double a6 = fma(1.6059043836821613e-10, r, 2.08767569878681e-09);
+    const double r4 = r2 * r2;
+    const double b0 = fma(a1, r2, a0);
+    const double b1 = fma(a3, r2, a2);
+    const double b2 = fma(a5, r2, a4);
+    const double r8 = r4 * r4;
+    const double c0 = fma(b1, r4, b0);
+    const double c1 = fma(a6, r4, b2);
+    const double p = fma(c1, r8, c0);
     const double s = __hiloint2double((n + 1023) << 20, 0);               // 2^n, n in [-1022, 1023]
     return (x < -708.0) ? 0.0 : p * s;
 }
@@ -495,9 +504,8 @@ __device__ __noinline__ void compute_bond_masks_warp(unsigned char* smem, int N,
 __device__ __forceinline__ double eval_bond(double* q, int r)
 {
     const double tx = q[r], ty = q[QC + r], tz = q[2 * QC + r], r2 = q[3 * QC + r];
-    const double ir = rsqrt_fast(r2);
-    const double r1 = ir * r2;
-    const double isr = rcp_fast(r1 - RC);
+    double ir, isr;
+    bond_radial(r2, ir, isr);
     // exp(sigma*isr) = e^5 and exp(gamma*sigma*isr) = e^6 with e = exp(0.2*sigma*isr)  (gamma = 1.2)
     const double e1 = exp_fast((0.2 * SIGMA) * isr);
     const double e_2 = e1 * e1, e_4 = e_2 * e_2;
@@ -750,8 +758,9 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
                     const double tz = (P[2 * N + k] + V[2 * IVC + img]) - P[2 * N + j];
                     const double sq = tx * tx + ty * ty + tz * tz;
                     if (sq < RCSQ) {
-                        const double vi = rsqrt_fast(sq);
-                        const double ex = LEPS * exp_fast(GS * rcp_fast(sq * vi - RC));
+                        double vi, isr;
+                        bond_radial(sq, vi, isr);
+                        const double ex = LEPS * exp_fast(GS * isr);
                         const double ux = tx * vi, uy = ty * vi, uz = tz * vi;
                         const uint16_t qo = w.cq[c * 2], qn = w.cq[c * 2 + 1];
                         double vo = 0.0, vn = 0.0;
