@@ -11,13 +11,15 @@ samplerun, nbins 101, list_update_int 10).  Weak scaling: every rank owns 4096
 walkers; the only exchange is the delta all-reduce of weights / histograms every
 mpi_sync_int = 250 cycles (NCCL).
 
-A *step* = one call of the hot path over the whole batch: `mc_run(10 cycles)` =
-4096 x 48 x 10 attempted moves per GPU, including the in-kernel neighbour-list
-rebuild that falls into every 10th cycle.  `value` is device-timed with inputs
-resident in HBM; `e2e` is the same step through the C ABI with HOST buffers
-(pinned host -> device upload of every walker's positions / reference positions /
-cells, list + energy re-initialisation as after a checkpoint load, the 10 cycles,
-and the device -> host read of positions and observables) inside the timed region.
+A *step* = one call of the hot path over the whole batch between two exchanges of
+the reference: `mc_run(mpi_sync_int = 250 cycles)` = 4096 x 48 x 250 attempted moves
+per GPU, including the in-kernel neighbour-list rebuilds (every 10th cycle), followed
+by the delta all-reduce of weights / histograms (comms_mpi.f90:244-277).  `value` is
+device-timed with inputs resident in HBM; `e2e` is the same step through the C ABI
+with HOST buffers (pinned host -> device upload of every walker's positions /
+reference positions / cells, list + energy re-initialisation as after a checkpoint
+load, the 250 cycles, and the device -> host read of positions and observables)
+inside the timed region.
 
 `--impl reference`: the reference cannot be compiled here (no Fortran compiler, no
 MPI in this image or on the GPU box); the arm times the CPU oracle (C restatement of
@@ -38,7 +40,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 WALKERS_PER_GPU = 4096
-CYCLES_PER_STEP = 10
+CYCLES_PER_STEP = 250            # = mpi_sync_int of the example decks: one step ends with the delta all-reduce
 FLOP_PER_MOVE = 10730.0          # BASELINE.md section 3 / SURVEY.md 8(d): average attempted LS move
 FLOP_PER_EVAL = 35424.0          # one lattice full energy (mean of 34560 / 36288)
 BYTES_PER_EVAL = 8336.0          # one lattice, reference int32 list layout (mean of 8144 / 8528)
@@ -48,7 +50,7 @@ SEED = 20141211
 
 def _example():
     from mc_water_ls_mw_b200 import decks
-    d = os.path.join(ROOT, "tests", "golden", "examples", EXAMPLE)
+    d = os.path.join(ROOT, "tests", "golden", "examples", os.environ.get("MW_BENCH_EXAMPLE", EXAMPLE))
     up = decks.read_input(os.path.join(d, "ice.input"))
     h, r = decks.read_config(d, up)
     wl, _, w = decks.read_eta_weights(os.path.join(d, "eta_weights.dat"))
@@ -139,6 +141,14 @@ def _decorrelate_oracle(ws, nthreads):
             s.mc_monitor()
 
 
+def _oracle_step(ws, nsync, nthreads):
+    """nsync x (mpi_sync_int cycles on all host threads + the delta merge of comms_mpi.f90:244-277)."""
+    from oracle import orc
+    for _ in range(nsync):
+        assert orc.mc_run_many(ws, CYCLES_PER_STEP, nthreads) == 0
+        orc.allreduce_bins(ws)
+
+
 def cpu_baseline(target_seconds: float = 12.0):
     """Oracle timed on all host cores on a bounded sample of the same workload."""
     from oracle import orc
@@ -146,9 +156,10 @@ def cpu_baseline(target_seconds: float = 12.0):
     nthreads = orc.max_threads()
     ws = _oracle_walkers(nthreads * 2, up, h, r, w, wl)
     _decorrelate_oracle(ws, nthreads)
-    t0 = time.perf_counter(); assert orc.mc_run_many(ws, CYCLES_PER_STEP, nthreads) == 0; dt = time.perf_counter() - t0
-    ncyc = max(CYCLES_PER_STEP, int(target_seconds / max(dt, 1e-6)) * CYCLES_PER_STEP)
-    t0 = time.perf_counter(); assert orc.mc_run_many(ws, ncyc, nthreads) == 0; dt = time.perf_counter() - t0
+    t0 = time.perf_counter(); _oracle_step(ws, 1, nthreads); dt = time.perf_counter() - t0
+    nsync = max(1, int(target_seconds / max(dt, 1e-6)))
+    t0 = time.perf_counter(); _oracle_step(ws, nsync, nthreads); dt = time.perf_counter() - t0
+    ncyc = nsync * CYCLES_PER_STEP
     moves = len(ws) * up.nwater * ncyc
     # energy evaluations (single lattice evals / s)
     t0 = time.perf_counter(); reps = 0
@@ -157,8 +168,8 @@ def cpu_baseline(target_seconds: float = 12.0):
     evals = reps * len(ws) * 2 / (time.perf_counter() - t0)
     return {
         "value": moves / dt, "unit": "attempted MC moves/s", "cores": nthreads, "kind": "port",
-        "sample": f"{len(ws)} walkers x {ncyc} cycles of {EXAMPLE} (oracle restatement, not the Fortran binary; "
-                  f"{dt:.1f} s on {nthreads} threads)",
+        "sample": f"{len(ws)} walkers x {ncyc} cycles of {EXAMPLE}, bins merged every {CYCLES_PER_STEP} cycles (oracle "
+                  f"restatement, not the Fortran binary; {dt:.1f} s on {nthreads} threads)",
         "energy_evals_per_s": evals,
     }
 
@@ -173,18 +184,20 @@ def run_reference(args):
     ws = _oracle_walkers(nthreads * 2, up, h, r, w, wl)
     _decorrelate_oracle(ws, nthreads)
     # size one step to ~3 s so that K+W steps end within minutes
-    t0 = time.perf_counter(); assert orc.mc_run_many(ws, CYCLES_PER_STEP, nthreads) == 0; dt = time.perf_counter() - t0
-    per_step = max(1, int(3.0 / max(dt, 1e-6))) * CYCLES_PER_STEP
+    t0 = time.perf_counter(); _oracle_step(ws, 1, nthreads); dt = time.perf_counter() - t0
+    nsync = max(1, int(3.0 / max(dt, 1e-6)))
+    per_step = nsync * CYCLES_PER_STEP
     for _ in range(args.warmup):
-        assert orc.mc_run_many(ws, per_step, nthreads) == 0
+        _oracle_step(ws, nsync, nthreads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        assert orc.mc_run_many(ws, per_step, nthreads) == 0
+        _oracle_step(ws, nsync, nthreads)
     dt = time.perf_counter() - t0
     moves = len(ws) * up.nwater * per_step * args.steps
     val = moves / dt
     unit = "attempted MC moves/s"
-    sample = f"{len(ws)} walkers x {per_step} cycles per step of {EXAMPLE} on {nthreads} host threads (CPU oracle)"
+    sample = (f"{len(ws)} walkers x {per_step} cycles per step of {EXAMPLE} on {nthreads} host threads, bins merged every "
+              f"{CYCLES_PER_STEP} cycles (CPU oracle)")
     print(json.dumps({
         "impl": "reference", "metric": "attempted MC moves/sec (whole box)", "value": val, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -232,6 +245,8 @@ def run_ours(args):
 
     C = args.cycles
     sync_every = max(1, up.mpi_sync_int // C)
+    if world > 1:
+        g.comms_allreduce_bins()        # untimed: the first NCCL collective sets up its channels
 
     def barrier():
         g.synchronize()
@@ -333,7 +348,8 @@ def run_ours(args):
                 "workload": f"synthetic scale-out (BASELINE configs[4]): {nw} independent lattice-switch walkers per GPU, "
                             f"{EXAMPLE} deck (48 mW molecules per lattice, cubic<->hexagonal ice, 200 K, 1 atm, fixed weights)",
                 "walkers_per_gpu": nw, "walkers_total": total, "cycles_per_step": C, "moves_per_step": moves_per_step,
-                "l2_policy": "walker state (~19 MB) is re-read from HBM once per step; the hot loop runs out of shared memory",
+                "l2_policy": "walker state (~75 MB for 4096 walkers) is read from and written back to global memory once per step; "
+                             "the hot loop runs out of shared memory, so cache state between steps does not matter",
                 "rng": "Philox-4x32-10, one stream per walker",
             },
             "energy_evals_per_s": evals_per_s,

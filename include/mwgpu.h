@@ -192,6 +192,34 @@ int  mwgpu_comms_init(mwgpu_ctx *ctx, int nranks, int rank, const void *id128);
 int  mwgpu_comms_reduce_local(mwgpu_ctx *ctx, void **dev_ptr, int *count);
 int  mwgpu_comms_apply(mwgpu_ctx *ctx);
 
+/* ---- periodic bookkeeping on the reduced arrays, device side ---- */
+typedef struct mwgpu_flat_params {     /* userparams.f90:33-36 */
+    int    wl_schedule;                /* 0: every bin within tol of the mean, 1: min visits, 2: above (1-tol) of the mean */
+    int    wl_minhist;
+    double wl_flattol;
+    int    wl_useinvt;
+} mwgpu_flat_params;
+typedef struct mwgpu_flat_report {     /* what mc_check_flatness logs, for walker 0 of the context */
+    int    checked;                    /* 0: returned at the samplerun / empty-histogram guard (:1961) */
+    int    hist_reset;                 /* the one-off histogram reset of :1973-1980 happened in this call */
+    int    flat;
+    int    invt_switched;              /* switched to the 1/t increment (:2134-2142) */
+    double mean, max_pct, min_pct;     /* window mean; most / least populated bin in % of it */
+    double wl_factor;                  /* after the call */
+} mwgpu_flat_report;
+/* mc_check_flatness (mc_moves.F90:1936-2185), state effects for every walker: histogram delta
+ * all-reduce ('mw'), one-off histogram reset, flatness test by wl_schedule, weight shift, histogram
+ * reset + re-base, wl_factor halving, switch to 1/t.  The files of :2067-2101 stay with the caller
+ * (mwgpu_mc_get_bins gives the arrays). */
+int  mwgpu_mc_check_flatness(mwgpu_ctx *ctx, const mwgpu_flat_params *p, mwgpu_flat_report *report);
+/* mc_compute_deltaG_from_hist (mc_moves.F90:2498-2621): all-reduces ('mw') or joins ('dd') the
+ * unbiased histogram, returns G(lattice2)-G(lattice1) in kT for the whole box and normP(nbins). */
+int  mwgpu_mc_deltag_from_hist(mwgpu_ctx *ctx, double *deltaG_kT, double *normP);
+/* comms_join_uhist / comms_join_eta (comms_mpi.f90:299-375, :377-459): stitch the windows of a
+ * 'dd' run (walker = window, rank order; NCCL all-gather when the windows span several GPUs) */
+int  mwgpu_comms_join_uhist(mwgpu_ctx *ctx, int overlap, double *joined /* nbins */);
+int  mwgpu_comms_join_eta(mwgpu_ctx *ctx, int overlap, double *joined /* nbins */);
+
 /* ---- measurement helpers ------------------------------------------------------------ */
 /* elapsed milliseconds of the last mwgpu_mc_run / mwgpu_compute_model_energy_all kernel
  * (CUDA events on the context's stream) */

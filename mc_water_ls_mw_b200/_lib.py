@@ -55,6 +55,19 @@ class WalkerState(C.Structure):
     ]
 
 
+class FlatParams(C.Structure):
+    """mwgpu_flat_params (include/mwgpu.h): userparams.f90:33-36."""
+
+    _fields_ = [("wl_schedule", C.c_int), ("wl_minhist", C.c_int), ("wl_flattol", C.c_double), ("wl_useinvt", C.c_int)]
+
+
+class FlatReport(C.Structure):
+    """mwgpu_flat_report (include/mwgpu.h)."""
+
+    _fields_ = [("checked", C.c_int), ("hist_reset", C.c_int), ("flat", C.c_int), ("invt_switched", C.c_int),
+                ("mean", C.c_double), ("max_pct", C.c_double), ("min_pct", C.c_double), ("wl_factor", C.c_double)]
+
+
 # every symbol include/mwgpu.h declares: name -> (restype, argtypes)
 _vp, _i, _d, _dp, _ip = C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)
 SYMBOLS = {
@@ -98,6 +111,10 @@ SYMBOLS = {
     "mwgpu_comms_init": (_i, [_vp, _i, _i, _vp]),
     "mwgpu_comms_reduce_local": (_i, [_vp, C.POINTER(_vp), _ip]),
     "mwgpu_comms_apply": (_i, [_vp]),
+    "mwgpu_mc_check_flatness": (_i, [_vp, C.POINTER(FlatParams), C.POINTER(FlatReport)]),
+    "mwgpu_mc_deltag_from_hist": (_i, [_vp, _dp, _dp]),
+    "mwgpu_comms_join_uhist": (_i, [_vp, _i, _dp]),
+    "mwgpu_comms_join_eta": (_i, [_vp, _i, _dp]),
     "mwgpu_timer_start": (_i, [_vp]),
     "mwgpu_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
     "mwgpu_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),

@@ -46,12 +46,24 @@ constexpr double SS      = SIGMA * SIGMA;
 constexpr double F_HUGE  = 1.7976931348623157e308;
 
 // ---------------------------------------------------------------- capacities
-constexpr int LC  = 32;    // list slots per molecule held in shared memory (one lane per slot)
+#ifndef MW_LC
+#define MW_LC 32
+#endif
+#ifndef MW_QC
+#define MW_QC 64
+#endif
+#ifndef MW_RB
+#define MW_RB 64
+#endif
+#ifndef MW_KC
+#define MW_KC 256
+#endif
+constexpr int LC  = MW_LC;    // list slots per molecule held in shared memory (one lane per slot)
 constexpr int IVC = 32;    // image vectors per lattice (27 in every BASELINE config)
-constexpr int QC  = 64;    // bond records per batch (a trial move has ~26; more than QC in-range bonds -> ERR_BOND_OVERFLOW)
+constexpr int QC  = MW_QC;    // bond records per batch (a trial move has ~26; more than QC in-range bonds -> ERR_BOND_OVERFLOW)
 constexpr int CC  = 64;    // triplet centres per trial move: 2 lattices x LC slots
-constexpr int RB  = 64;    // random numbers buffered per refill
-constexpr int KC  = 256;   // (centre, bond) candidates of the j-centred triplets of one trial move (~90)
+constexpr int RB  = MW_RB;    // random numbers buffered per refill
+constexpr int KC  = MW_KC;   // (centre, bond) candidates of the j-centred triplets of one trial move (~90)
 constexpr int NMAX = 1024; // molecules (10 bits of a packed list entry)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint16_t NONE16 = 0xffffu;
@@ -244,6 +256,8 @@ struct WalkerScalars {
     int wl_invt_active;
     int wmin_zero;          // invariant "min(weight(window)) == 0" established
     int error;
+    int firstcycle;         // mc_moves.F90:85: wl_factor is still the original one
+    int hist_reset;         // mc_moves.F90:1957: the one-off histogram reset of mc_check_flatness happened
 };
 
 // ---------------------------------------------------------------- shared-memory view of one walker

@@ -9,6 +9,10 @@
 #pragma once
 #include "mw_device.cuh"
 
+#ifndef MW_MC_BLOCKS
+#define MW_MC_BLOCKS 14      // resident walkers (1-warp CTAs) per SM the register allocation is bounded for
+#endif
+
 namespace mw {
 
 // Run parameters shared by all walkers (kernel argument, by value).
@@ -488,7 +492,7 @@ __device__ __forceinline__ void commit_translation(const WalkerView& w, int imol
 // One warp (= one CTA of 32 threads) per walker; ncycles MC cycles of the hot
 // part of mc_cycle (mc_moves.F90:117-255).
 template <int NLAT>
-__global__ void __launch_bounds__(32, 14) k_mc_run(const __grid_constant__ DeviceState S,
+__global__ void __launch_bounds__(32, MW_MC_BLOCKS) k_mc_run(const __grid_constant__ DeviceState S,
                                                const __grid_constant__ McParams p, int ncycles)
 {
     extern __shared__ __align__(16) unsigned char smem[];

@@ -58,6 +58,10 @@ struct mwgpu_ctx {
     size_t iout_ints = 0;
     double* delta = nullptr;       // [3][NBP] summed increments
     double* fifo = nullptr;
+    double* book = nullptr;        // scratch of the periodic bookkeeping kernels: report | joined | normP
+    int* skip = nullptr;           // [W] guard flags of mc_check_flatness
+    double* gather = nullptr;      // [size][NB] windows of all ranks (dd joins over several GPUs)
+    size_t gather_doubles = 0;
     int64_t launches = 0;
     float last_ms = 0.f;
     std::vector<double> h_mubin, h_binwidth;
@@ -147,7 +151,8 @@ extern "C" void mwgpu_destroy(mwgpu_ctx* c)
     DeviceState& S = c->S;
     void* ptrs[] = {S.pos, S.ref, S.cell, S.recip, S.refcell, S.iv, S.niv, S.list, S.nn, S.scal,
                     S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.transcount, S.mubin,
-                    S.binwidth, S.ginv, S.hinc, c->stage, c->out, c->iout, c->delta, c->fifo};
+                    S.binwidth, S.ginv, S.hinc, c->stage, c->out, c->iout, c->delta, c->fifo,
+                    c->book, c->skip, c->gather};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -855,6 +860,8 @@ extern "C" int mwgpu_mc_init(mwgpu_ctx* c, const mwgpu_mc_params* up, int first_
         sc.acc_r = sc.acc_v = sc.acc_s = sc.att_r = sc.att_v = sc.att_s = 0;
         sc.in_window = u.dd ? 0 : 1;
         sc.wl_invt_active = 0; sc.wmin_zero = 0; sc.error = 0;
+        sc.firstcycle = !(c->nlat == 2 && wl_factor < orig_wl_factor);       // :817-821
+        sc.hist_reset = 0;
         for (int i = 0; i < nb; ++i) {
             hb[(size_t)w * nb + i] = weight[i];                            // eta_last_sync = weight (:776)
             double v = weight[i];
@@ -1089,10 +1096,11 @@ extern "C" int mwgpu_mc_chain_sync(mwgpu_ctx* c)
 // (comms_mpi.f90:244-277, :461-530)
 // ------------------------------------------------------------------------------------------------
 // delta[a][k] = sum over walkers (in walker order) of arr_a[w][k] - base_a[w][k]
-__global__ void k_reduce_bins(DeviceState S, double* __restrict__ delta, int NBP, int narr)
+__global__ void k_reduce_bins(DeviceState S, double* __restrict__ delta, int NBP, int first, int narr)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= narr * NBP) return;
+    t += first * NBP;
     const int a = t / NBP, k = t % NBP;
     double s = 0.0;
     if (k < S.NB) {
@@ -1104,12 +1112,12 @@ __global__ void k_reduce_bins(DeviceState S, double* __restrict__ delta, int NBP
 }
 
 // arr = total + base ; base = arr
-__global__ void k_apply_bins(DeviceState S, const double* __restrict__ delta, int NBP, int narr)
+__global__ void k_apply_bins(DeviceState S, const double* __restrict__ delta, int NBP, int first, int narr)
 {
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t per = (size_t)S.W * S.NB;
     if (t >= per * narr) return;
-    const int a = (int)(t / per);
+    const int a = first + (int)(t / per);
     const size_t r = t % per;
     const int k = (int)(r % S.NB);
     double* arr = (a == 0) ? S.weight : (a == 1) ? S.hist : S.uhist;
@@ -1131,7 +1139,7 @@ extern "C" int mwgpu_comms_reduce_local(mwgpu_ctx* c, void** dev_ptr, int* count
     if (int rc = check_ctx(c, 0, false)) return rc;
     if (!c->mc_ready) return fail("mwgpu_comms_reduce_local: call mwgpu_mc_init first");
     const int narr = narr_of(c), n = narr * c->NBP;
-    k_reduce_bins<<<(n + 127) / 128, 128, 0, c->stream>>>(c->S, c->delta, c->NBP, narr);
+    k_reduce_bins<<<(n + 127) / 128, 128, 0, c->stream>>>(c->S, c->delta, c->NBP, 0, narr);
     c->launches++;
     if (dev_ptr) *dev_ptr = c->delta;
     if (count) *count = n;
@@ -1144,7 +1152,7 @@ extern "C" int mwgpu_comms_apply(mwgpu_ctx* c)
     if (!c->mc_ready) return fail("mwgpu_comms_apply: call mwgpu_mc_init first");
     const int narr = narr_of(c);
     const size_t n = (size_t)c->W * c->NB * narr;
-    k_apply_bins<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->S, c->delta, c->NBP, narr);
+    k_apply_bins<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->S, c->delta, c->NBP, 0, narr);
     k_clear_wmin<<<(c->W + 127) / 128, 128, 0, c->stream>>>(c->S);
     c->launches += 2;
     return finish(c, true);
@@ -1169,6 +1177,7 @@ struct NcclApi {
     int (*GetUniqueId)(nccl_unique_id*) = nullptr;
     int (*CommInitRank)(void**, int, nccl_unique_id, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -1183,6 +1192,7 @@ static int nccl_load()
     g_nccl.GetUniqueId = (int (*)(nccl_unique_id*))dlsym(g_nccl.handle, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(void**, int, nccl_unique_id, int))dlsym(g_nccl.handle, "ncclCommInitRank");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.handle, "ncclAllReduce");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.handle, "ncclAllGather");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.handle, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.handle, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
@@ -1235,6 +1245,281 @@ extern "C" int mwgpu_comms_allreduce_bins(mwgpu_ctx* c)
         if (r) return nccl_fail("ncclAllReduce", r);
     }
     return mwgpu_comms_apply(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Periodic bookkeeping that consumes the reduced arrays, on the device:
+// mc_check_flatness (mc_moves.F90:1936-2185), mc_compute_deltaG_from_hist (:2498-2621),
+// comms_join_uhist / comms_join_eta (comms_mpi.f90:299-459).  All sums run in the reference's
+// order with explicit round-to-nearest operations (no FMA contraction), so the decisions and the
+// new weights / histograms are bit-identical to the oracle; only log/exp differ by an ulp.
+// ------------------------------------------------------------------------------------------------
+// delta all-reduce of the arrays [first, first+narr) (0 weight, 1 histogram, 2 unbiased_hist)
+static int allreduce_arrays(mwgpu_ctx* c, int first, int narr)
+{
+    const int n = narr * c->NBP;
+    k_reduce_bins<<<(n + 127) / 128, 128, 0, c->stream>>>(c->S, c->delta, c->NBP, first, narr);
+    c->launches++;
+    if (c->nccl_comm && c->nranks > 1) {
+        double* d = c->delta + (size_t)first * c->NBP;
+        const int r = g_nccl.AllReduce(d, d, (size_t)n, 8, 0, c->nccl_comm, c->stream);
+        if (r) return nccl_fail("ncclAllReduce", r);
+    }
+    const size_t m = (size_t)c->W * c->NB * narr;
+    k_apply_bins<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(c->S, c->delta, c->NBP, first, narr);
+    c->launches++;
+    if (first == 0) { k_clear_wmin<<<(c->W + 127) / 128, 128, 0, c->stream>>>(c->S); c->launches++; }
+    return finish(c, false);
+}
+
+struct FlatArgs {
+    int wl_schedule, wl_minhist, wl_useinvt;
+    double wl_flattol;
+    int dd, wl_swetnam, nwater;
+};
+
+// :1961 guard of every walker (= rank) on its own histogram
+__global__ void k_flat_guard(DeviceState S, int samplerun, int* __restrict__ skip)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= S.W) return;
+    const double* hist = S.hist + (size_t)w * S.NB;
+    double sum = 0.0;
+    for (int k = 0; k < S.NB; ++k) sum = __dadd_rn(sum, hist[k]);
+    skip[w] = samplerun || (sum < DBL_MIN);
+}
+
+__device__ __forceinline__ long long nint_dev(double x) { return (long long)(x < 0.0 ? __dadd_rn(x, -0.5) : __dadd_rn(x, 0.5)); }
+
+// :1968-2142, one thread per walker.  In 'mw' runs every walker holds the same reduced histogram and
+// the same window, so the flatness decision is identical on all of them (the reference broadcasts
+// rank 0's, comms_bcastlog :2042).
+__global__ void k_flat_decide(DeviceState S, FlatArgs a, const int* __restrict__ skip, mwgpu_flat_report* __restrict__ rep)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= S.W) return;
+    const int nb = S.NB;
+    WalkerScalars& sc = S.scal[w];
+    double* hist = S.hist + (size_t)w * nb;
+    double* hbase = S.hbase + (size_t)w * nb;
+    double* wgt = S.weight + (size_t)w * nb;
+    mwgpu_flat_report rr;
+    rr.checked = 0; rr.hist_reset = 0; rr.flat = 0; rr.invt_switched = 0;
+    rr.mean = 0.0; rr.max_pct = 0.0; rr.min_pct = 0.0; rr.wl_factor = sc.wl_factor;
+    if (skip[w]) { if (w == 0) *rep = rr; return; }
+    rr.checked = 1;
+    double mn = hist[0], mx = hist[0];
+    for (int k = 1; k < nb; ++k) { const double h = hist[k]; if (h < mn) mn = h; if (h > mx) mx = h; }
+    if (sc.firstcycle && !sc.hist_reset && nint_dev(mn) > (long long)a.wl_minhist) {      // :1973-1980
+        sc.hist_reset = 1;
+        for (int k = 0; k < nb; ++k) { hist[k] = 0.0; hbase[k] = 0.0; }
+        rr.hist_reset = 1;
+        if (w == 0) *rep = rr;
+        return;
+    }
+    const int sb = sc.start_bin, eb = sc.end_bin;
+    double av = 0.0;
+    for (int k = sb; k <= eb; ++k) av = __dadd_rn(av, hist[k - 1]);                       // :1983-1989
+    av = __ddiv_rn(av, (double)(eb - sb + 1));
+    rr.mean = av;
+    rr.max_pct = __ddiv_rn(__dmul_rn(100.0, mx), av);
+    rr.min_pct = __ddiv_rn(__dmul_rn(100.0, mn), av);
+    if (!(sc.wl_invt_active || a.wl_swetnam)) {
+        bool flat = true;
+        if (a.wl_schedule == 0) {
+            for (int k = sb; k <= eb; ++k)
+                if (__ddiv_rn(fabs(__dsub_rn(hist[k - 1], av)), av) > a.wl_flattol) flat = false;
+        } else if (a.wl_schedule == 1) {
+            double m2 = hist[sb - 1];
+            for (int k = sb; k <= eb; ++k) if (hist[k - 1] < m2) m2 = hist[k - 1];
+            if (nint_dev(m2) < (long long)a.wl_minhist) flat = false;
+        } else {
+            const double thr = __dmul_rn(__dsub_rn(1.0, a.wl_flattol), av);
+            for (int k = sb; k <= eb; ++k) if (hist[k - 1] < thr) flat = false;
+        }
+        if (flat) {
+            if (!a.dd) {
+                const double mid = wgt[nb / 2];                                           // weight(nbins/2+1)
+                for (int k = 0; k < nb; ++k) wgt[k] = __dsub_rn(wgt[k], mid);
+                for (int k = 0; k < nb; ++k) { hist[k] = 0.0; hbase[k] = 0.0; }
+                sc.wmin_zero = 0;
+            } else {
+                for (int k = 0; k < nb; ++k) hist[k] = 0.0;
+            }
+            sc.wl_factor = __dmul_rn(sc.wl_factor, 0.5);
+            sc.firstcycle = 0;
+        }
+        rr.flat = flat ? 1 : 0;
+        const double wl_invt = __ddiv_rn((double)nb, (double)(sc.cycle * a.nwater));     // :2134-2142
+        if (sc.wl_factor < wl_invt && sc.wl_factor > DBL_MIN && a.wl_useinvt) {
+            sc.wl_invt_active = 1; sc.wl_factor = wl_invt; rr.invt_switched = 1;
+        }
+    }
+    rr.wl_factor = sc.wl_factor;
+    if (w == 0) *rep = rr;
+}
+
+static int book_alloc(mwgpu_ctx* c)
+{
+    if (!c->book) if (int rc = dalloc(&c->book, (size_t)4 * c->NBP + 64)) return rc;
+    if (!c->skip) if (int rc = dalloc(&c->skip, (size_t)c->W)) return rc;
+    return 0;
+}
+
+extern "C" int mwgpu_mc_check_flatness(mwgpu_ctx* c, const mwgpu_flat_params* fp, mwgpu_flat_report* rep)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_mc_check_flatness: call mwgpu_mc_init first");
+    if (!fp) return fail("mwgpu_mc_check_flatness: params is NULL");
+    if (fp->wl_schedule < 0 || fp->wl_schedule > 2) return fail("Error - unknown wl_schedule value");   // :2036
+    mwgpu_flat_report r0; memset(&r0, 0, sizeof(r0));
+    if (c->nlat != 2 || c->user.samplerun) {                           // :293 (two lattices only), :1961
+        if (rep) *rep = r0;
+        return 0;
+    }
+    if (int rc = book_alloc(c)) return rc;
+    k_flat_guard<<<(c->W + 127) / 128, 128, 0, c->stream>>>(c->S, c->user.samplerun, c->skip);
+    c->launches++;
+    int skip0 = 0;
+    CUDA_TRY(cudaMemcpyAsync(&skip0, c->skip, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (!c->user.dd && !skip0)                                          // :1964-1966 comms_allreduce_hist
+        if (int rc = allreduce_arrays(c, 1, 1)) return rc;
+    FlatArgs a;
+    a.wl_schedule = fp->wl_schedule; a.wl_minhist = fp->wl_minhist; a.wl_useinvt = fp->wl_useinvt;
+    a.wl_flattol = fp->wl_flattol; a.dd = c->user.dd; a.wl_swetnam = c->user.wl_swetnam; a.nwater = c->N;
+    mwgpu_flat_report* drep = (mwgpu_flat_report*)c->book;
+    k_flat_decide<<<(c->W + 63) / 64, 64, 0, c->stream>>>(c->S, a, c->skip, drep);
+    c->launches++;
+    if (int rc = finish(c, false)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(&r0, drep, sizeof(r0), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (rep) *rep = r0;
+    return 0;
+}
+
+// comms_join_uhist (is_eta = 0, comms_mpi.f90:299-375) / comms_join_eta (is_eta = 1, :377-459): rank 0's
+// sequential stitch of the windows, one thread (size - 1 seams of 2*overlap+1 bins, nbins ~ 100)
+__global__ void k_join_windows(const double* __restrict__ arrs, int size, int nb, int overlap, int is_eta,
+                               double* __restrict__ joined)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int bpw = nb / size;
+    for (int k = 0; k < nb; ++k) joined[k] = arrs[k];
+    for (int ir = 1; ir < size; ++ir) {
+        const double* recv = arrs + (size_t)ir * nb;
+        const int my_end = ir * bpw;
+        const int lo = max(my_end - overlap, 1), hi = min(my_end + overlap, nb);      // memory safety only
+        double myave = 0.0, nextav = 0.0;
+        for (int k = lo; k <= hi; ++k) myave = __dadd_rn(myave, is_eta ? joined[k - 1] : log(joined[k - 1]));
+        myave = __ddiv_rn(myave, (double)(2 * overlap + 1));
+        for (int k = lo; k <= hi; ++k) nextav = __dadd_rn(nextav, is_eta ? recv[k - 1] : log(recv[k - 1]));
+        nextav = __ddiv_rn(nextav, (double)(2 * overlap + 1));
+        double shift = __dsub_rn(myave, nextav);
+        if (is_eta) {
+            for (int k = my_end + 1; k <= nb; ++k) joined[k - 1] = __dadd_rn(recv[k - 1], shift);
+        } else {
+            if (isnan(shift)) shift = 0.0;
+            const double f = exp(shift);
+            for (int k = my_end + 1; k <= nb; ++k) joined[k - 1] = __dmul_rn(recv[k - 1], f);
+        }
+    }
+    if (is_eta) {
+        const double mid = joined[nb / 2];
+        for (int k = 0; k < nb; ++k) joined[k] = __dsub_rn(joined[k], mid);
+    }
+}
+
+// windows of all ranks as one [size][NB] array: the context's own array on one GPU, an NCCL
+// all-gather (rank order = window order) over several
+static int gather_windows(mwgpu_ctx* c, const double* mine, const double** all, int* size)
+{
+    *all = mine; *size = c->W;
+    if (!(c->nccl_comm && c->nranks > 1)) return 0;
+    if (!g_nccl.AllGather) return fail("mwgpu_comms_join: ncclAllGather missing");
+    const size_t per = (size_t)c->W * c->NB, need = per * c->nranks;
+    if (c->gather_doubles < need) {
+        if (c->gather) cudaFree(c->gather);
+        c->gather = nullptr; c->gather_doubles = 0;
+        if (int rc = dalloc(&c->gather, need)) return rc;
+        c->gather_doubles = need;
+    }
+    const int r = g_nccl.AllGather(mine, c->gather, per, 8, c->nccl_comm, c->stream);
+    if (r) return nccl_fail("ncclAllGather", r);
+    *all = c->gather; *size = c->W * c->nranks;
+    return 0;
+}
+
+static int join_common(mwgpu_ctx* c, int overlap, int is_eta, double* d_joined)
+{
+    const double* all = nullptr; int size = 0;
+    if (int rc = gather_windows(c, is_eta ? c->S.weight : c->S.uhist, &all, &size)) return rc;
+    if (overlap < 0 || size < 1 || c->NB / size - overlap < 1 || (size - 1) * (c->NB / size) + overlap > c->NB)
+        return fail("mwgpu_comms_join: windows too narrow for this overlap (bins_per_window = nbins/size)");
+    k_join_windows<<<1, 32, 0, c->stream>>>(all, size, c->NB, overlap, is_eta, d_joined);
+    c->launches++;
+    return finish(c, false);
+}
+
+static int join_entry(mwgpu_ctx* c, int overlap, int is_eta, double* joined)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_comms_join: call mwgpu_mc_init first");
+    if (!joined) return fail("mwgpu_comms_join: joined is NULL");
+    if (int rc = book_alloc(c)) return rc;
+    double* dj = c->book + 64;
+    if (int rc = join_common(c, overlap, is_eta, dj)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(joined, dj, sizeof(double) * c->NB, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int mwgpu_comms_join_uhist(mwgpu_ctx* c, int overlap, double* joined) { return join_entry(c, overlap, 0, joined); }
+extern "C" int mwgpu_comms_join_eta(mwgpu_ctx* c, int overlap, double* joined) { return join_entry(c, overlap, 1, joined); }
+
+// :2540-2577 on the joined unbiased histogram; out[0] = deltaG (kT), out[1..nb] = normP
+__global__ void k_deltaG(const double* __restrict__ joined, const double* __restrict__ binwidth, int nb,
+                         int leshift, double beta, const WalkerScalars* __restrict__ sc0, double* __restrict__ out)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double Pnorm = 0.0;
+    for (int i = 0; i < nb; ++i) Pnorm = __dadd_rn(Pnorm, __dmul_rn(joined[i], binwidth[i]));
+    double* normP = out + 1;
+    for (int i = 0; i < nb; ++i) normP[i] = __ddiv_rn(joined[i], Pnorm);
+    double pA = 0.0, pB = 0.0;
+    for (int i = 0; i < nb / 2; ++i) pA = __dadd_rn(pA, __dmul_rn(normP[i], binwidth[i]));
+    for (int i = nb / 2; i < nb; ++i) pB = __dadd_rn(pB, __dmul_rn(normP[i], binwidth[i]));
+    double dG = log(__ddiv_rn(pA, pB));
+    if (leshift) dG = __dsub_rn(__dadd_rn(dG, __dmul_rn(beta, sc0->refH[1])), __dmul_rn(beta, sc0->refH[0]));
+    out[0] = dG;
+}
+
+extern "C" int mwgpu_mc_deltag_from_hist(mwgpu_ctx* c, double* deltaG, double* normP)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_mc_deltag_from_hist: call mwgpu_mc_init first");
+    if (c->nlat != 2 || !c->user.samplerun)                              // :293, :305
+        return fail("mwgpu_mc_deltag_from_hist: needs a two-lattice sample run (mc_moves.F90:305)");
+    if (int rc = book_alloc(c)) return rc;
+    const double* joined = c->S.uhist;                                   // walker 0 after the all-reduce
+    if (!c->user.dd) {
+        if (int rc = allreduce_arrays(c, 2, 1)) return rc;              // :2530 comms_allreduce_uhist
+    } else {
+        double* dj = c->book + 64;
+        if (int rc = join_common(c, c->user.window_overlap, 0, dj)) return rc;   // :2533 comms_join_uhist
+        joined = dj;
+    }
+    double* out = c->book + 64 + c->NBP;
+    const double beta = 1.0 / (KB * c->user.temperature);
+    k_deltaG<<<1, 32, 0, c->stream>>>(joined, c->S.binwidth, c->NB, c->user.leshift, beta, c->S.scal, out);
+    c->launches++;
+    if (int rc = finish(c, false)) return rc;
+    std::vector<double> h((size_t)c->NB + 1);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), out, sizeof(double) * (c->NB + 1), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (deltaG) *deltaG = h[0];
+    if (normP) memcpy(normP, h.data() + 1, sizeof(double) * c->NB);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

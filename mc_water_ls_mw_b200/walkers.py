@@ -20,7 +20,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import McParams, MwgpuError, WalkerState, check, lib
+from ._lib import FlatParams, FlatReport, McParams, MwgpuError, WalkerState, check, lib
 
 
 def _dp(a: Optional[np.ndarray]):
@@ -230,6 +230,34 @@ class WalkerBatch:
 
     def comms_apply(self) -> None:
         check(self.L.mwgpu_comms_apply(self.h))
+
+    def comms_join_uhist(self, overlap: int) -> np.ndarray:
+        """comms_join_uhist (comms_mpi.f90:299-375): unbiased histograms of the dd windows stitched."""
+        out = np.zeros(self.nbins, dtype=np.float64)
+        check(self.L.mwgpu_comms_join_uhist(self.h, int(overlap), _dp(out)))
+        return out
+
+    def comms_join_eta(self, overlap: int) -> np.ndarray:
+        """comms_join_eta (comms_mpi.f90:377-459)."""
+        out = np.zeros(self.nbins, dtype=np.float64)
+        check(self.L.mwgpu_comms_join_eta(self.h, int(overlap), _dp(out)))
+        return out
+
+    # ------------------------------------------------------------------ bookkeeping on the reduced arrays
+    def mc_check_flatness(self, wl_schedule: int = 0, wl_minhist: int = 20,
+                          wl_flattol: float = float(np.float32(0.05)), wl_useinvt: bool = False) -> FlatReport:
+        """mc_check_flatness (mc_moves.F90:1936-2185) for every walker; the report is walker 0's."""
+        fp = FlatParams(int(wl_schedule), int(wl_minhist), float(wl_flattol), int(wl_useinvt))
+        rep = FlatReport()
+        check(self.L.mwgpu_mc_check_flatness(self.h, C.byref(fp), C.byref(rep)))
+        return rep
+
+    def mc_compute_deltaG_from_hist(self):
+        """mc_compute_deltaG_from_hist (mc_moves.F90:2498-2621): (deltaG in kT for the box, normP)."""
+        dG = C.c_double(0.0)
+        normP = np.zeros(self.nbins, dtype=np.float64)
+        check(self.L.mwgpu_mc_deltag_from_hist(self.h, C.byref(dG), _dp(normP)))
+        return float(dG.value), normP
 
     def comms_init_nccl(self, nranks: int, rank: int, unique_id: bytes) -> None:
         buf = C.create_string_buffer(unique_id, 128)

@@ -654,6 +654,9 @@ int orc_mc_init(orc_system *s, const orc_params *pin, int rank, int size,
     s->average_energy[0] = s->average_energy[1] = 0.0;
     s->max_dmu = 0.0; s->min_dmu = F_HUGE;
     s->wl_invt_active = 0;
+    /* firstcycle (:85) is cleared when a smaller increment came from eta_weights.dat (:817-821) */
+    s->firstcycle = !(s->nlat == 2 && s->wl_factor < s->orig_wl_factor);
+    s->histogram_reset = 0;
     s->sumhist = 0.0;
     s->firstpass = 1;
     s->error = 0;
@@ -1116,6 +1119,156 @@ void orc_allreduce_bins(orc_system **w, int n)
 }
 
 /* ------------------------------------------------------------------ */
+/* periodic bookkeeping on the reduced arrays                          */
+/* ------------------------------------------------------------------ */
+static long nint_d(double x) { return (long)(x < 0.0 ? x - 0.5 : x + 0.5); }    /* Fortran nint */
+
+/* mc_moves.F90:1936-2185 */
+int orc_mc_check_flatness(orc_system **w, int n, const orc_flat_params *fp, orc_flat_report *rep)
+{
+    orc_flat_report r0; memset(&r0, 0, sizeof(r0));
+    if (n < 1) { if (rep) *rep = r0; return 0; }
+    const int nb = w[0]->p.nbins;
+    const int dd = w[0]->p.dd;
+    int rc = 0;
+    /* :1961 guard, evaluated per rank on its own histogram (all ranks agree in a valid run) */
+    int *skip = (int *)calloc(n, sizeof(int));
+    for (int r = 0; r < n; ++r) {
+        double sum = 0.0;
+        for (int k = 0; k < nb; ++k) sum = sum + w[r]->histogram[k];
+        skip[r] = w[r]->p.samplerun || (sum < F_TINY);
+    }
+    /* :1964-1966 */
+    if (!dd && !skip[0]) allreduce_one(w, n, nb, offsetof(orc_system, histogram), offsetof(orc_system, hist_last_sync));
+    int flat0 = 0;
+    for (int r = 0; r < n; ++r) {
+        orc_system *s = w[r];
+        orc_flat_report rr; memset(&rr, 0, sizeof(rr));
+        rr.wl_factor = s->wl_factor;
+        if (skip[r]) { if (r == 0) r0 = rr; continue; }
+        rr.checked = 1;
+        double mn = s->histogram[0], mx = s->histogram[0];
+        for (int k = 1; k < nb; ++k) { if (s->histogram[k] < mn) mn = s->histogram[k]; if (s->histogram[k] > mx) mx = s->histogram[k]; }
+        long mini = nint_d(mn);
+        if (s->firstcycle && !s->histogram_reset && mini > fp->wl_minhist) {          /* :1973-1980 */
+            s->histogram_reset = 1;
+            for (int k = 0; k < nb; ++k) { s->histogram[k] = 0.0; s->hist_last_sync[k] = 0.0; }
+            rr.hist_reset = 1;
+            if (r == 0) r0 = rr;
+            continue;
+        }
+        double av = 0.0; int count = 0;                                               /* :1983-1989 */
+        for (int k = s->my_start_bin; k <= s->my_end_bin; ++k) { av = av + s->histogram[k - 1]; count += 1; }
+        av = av / (double)count;
+        rr.mean = av; rr.max_pct = 100.0 * mx / av; rr.min_pct = 100.0 * mn / av;
+        if (!(s->wl_invt_active || s->p.wl_swetnam)) {
+            int flat = 1;
+            if (fp->wl_schedule == 0) {
+                for (int k = s->my_start_bin; k <= s->my_end_bin; ++k)
+                    if (fabs(s->histogram[k - 1] - av) / av > fp->wl_flattol) flat = 0;
+            } else if (fp->wl_schedule == 1) {
+                double m2 = s->histogram[s->my_start_bin - 1];
+                for (int k = s->my_start_bin; k <= s->my_end_bin; ++k) if (s->histogram[k - 1] < m2) m2 = s->histogram[k - 1];
+                if (nint_d(m2) < fp->wl_minhist) flat = 0;
+            } else if (fp->wl_schedule == 2) {
+                for (int k = s->my_start_bin; k <= s->my_end_bin; ++k)
+                    if (s->histogram[k - 1] < (1.0 - fp->wl_flattol) * av) flat = 0;
+            } else { rc = 40; flat = 0; }                                             /* stop 'unknown wl_schedule' */
+            if (!dd) { if (r == 0) flat0 = flat; else flat = flat0; }                 /* comms_bcastlog(flat): rank 0 decides */
+            if (flat) {
+                if (!dd) {
+                    const double mid = s->weight[nb / 2];                             /* weight(nbins/2+1) */
+                    for (int k = 0; k < nb; ++k) s->weight[k] = s->weight[k] - mid;
+                    for (int k = 0; k < nb; ++k) { s->histogram[k] = 0.0; s->hist_last_sync[k] = 0.0; }
+                } else {
+                    for (int k = 0; k < nb; ++k) s->histogram[k] = 0.0;
+                }
+                s->wl_factor = s->wl_factor * 0.5;
+                s->firstcycle = 0;
+            }
+            rr.flat = flat;
+            const double wl_invt = (double)nb / (double)(s->mc_cycle_num * s->nwater); /* :2134-2142 */
+            if (s->wl_factor < wl_invt && s->wl_factor > F_TINY) {
+                if (fp->wl_useinvt) { s->wl_invt_active = 1; s->wl_factor = wl_invt; rr.invt_switched = 1; }
+            }
+        }
+        rr.wl_factor = s->wl_factor;
+        if (r == 0) r0 = rr;
+    }
+    free(skip);
+    if (rep) *rep = r0;
+    return rc;
+}
+
+/* comms_mpi.f90:299-375: rank 0 stitches the windows in rank order, scaling each new window so that
+ * the mean log of the 2*overlap+1 bins around the seam agrees */
+void orc_join_uhist(orc_system **w, int n, int overlap, double *joined)
+{
+    const int nb = w[0]->p.nbins;
+    const int bpw = nb / n;
+    for (int k = 0; k < nb; ++k) joined[k] = w[0]->unbiased_hist[k];
+    for (int ir = 1; ir < n; ++ir) {
+        const double *recv = w[ir]->unbiased_hist;
+        const int my_end = ir * bpw;
+        double myave = 0.0, nextav = 0.0;
+        for (int k = my_end - overlap; k <= my_end + overlap; ++k) myave = myave + log(joined[k - 1]);
+        myave = myave / (double)(2 * overlap + 1);
+        for (int k = my_end - overlap; k <= my_end + overlap; ++k) nextav = nextav + log(recv[k - 1]);
+        nextav = nextav / (double)(2 * overlap + 1);
+        double shift = myave - nextav;
+        if (isnan(shift)) shift = 0.0;
+        for (int k = my_end + 1; k <= nb; ++k) joined[k - 1] = recv[k - 1] * exp(shift);
+    }
+}
+
+/* comms_mpi.f90:377-459 */
+void orc_join_eta(orc_system **w, int n, int overlap, double *joined)
+{
+    const int nb = w[0]->p.nbins;
+    const int bpw = nb / n;
+    for (int k = 0; k < nb; ++k) joined[k] = w[0]->weight[k];
+    for (int ir = 1; ir < n; ++ir) {
+        const double *recv = w[ir]->weight;
+        const int my_end = ir * bpw;
+        double myave = 0.0, nextav = 0.0;
+        for (int k = my_end - overlap; k <= my_end + overlap; ++k) myave = myave + joined[k - 1];
+        myave = myave / (double)(2 * overlap + 1);
+        for (int k = my_end - overlap; k <= my_end + overlap; ++k) nextav = nextav + recv[k - 1];
+        nextav = nextav / (double)(2 * overlap + 1);
+        const double shift = myave - nextav;
+        for (int k = my_end + 1; k <= nb; ++k) joined[k - 1] = recv[k - 1] + shift;
+    }
+    const double mid = joined[nb / 2];
+    for (int k = 0; k < nb; ++k) joined[k] = joined[k] - mid;
+}
+
+/* mc_moves.F90:2498-2621 (called for sample runs only, :305) */
+double orc_mc_deltaG_from_hist(orc_system **w, int n, double *normP)
+{
+    const int nb = w[0]->p.nbins;
+    orc_system *s0 = w[0];
+    double *joined = (double *)calloc(nb, sizeof(double));
+    if (!s0->p.dd) {
+        allreduce_one(w, n, nb, offsetof(orc_system, unbiased_hist), offsetof(orc_system, uhist_last_sync));
+        for (int k = 0; k < nb; ++k) joined[k] = s0->unbiased_hist[k];
+    } else {
+        orc_join_uhist(w, n, s0->p.window_overlap, joined);
+    }
+    double Pnorm = 0.0;
+    for (int i = 0; i < nb; ++i) Pnorm = Pnorm + joined[i] * s0->binwidth[i];
+    double *np_ = normP ? normP : joined;
+    for (int i = 0; i < nb; ++i) np_[i] = joined[i] / Pnorm;
+    double pA = 0.0, pB = 0.0;
+    for (int i = 0; i < nb / 2; ++i) pA = pA + np_[i] * s0->binwidth[i];
+    for (int i = nb / 2; i < nb; ++i) pB = pB + np_[i] * s0->binwidth[i];
+    double deltaG = log(pA / pB);
+    const double beta = 1.0 / (kB * s0->p.temperature);
+    if (s0->p.leshift) deltaG = deltaG + beta * s0->ref_enthalpy[1] - beta * s0->ref_enthalpy[0];
+    free(joined);
+    return deltaG;
+}
+
+/* ------------------------------------------------------------------ */
 /* batch helpers: independent walkers over host threads (CPU baseline)  */
 /* ------------------------------------------------------------------ */
 #include <pthread.h>
@@ -1261,6 +1414,8 @@ int64_t orc_get_i(const orc_system *s, const char *name)
     if (!strcmp(name, "rng_index")) return (s->rng.mode == 1) ? s->rng.fifo_pos : (int64_t)s->rng.index;
     if (!strcmp(name, "rng_fifo_pos")) return s->rng.fifo_pos;
     if (!strcmp(name, "wl_invt_active")) return s->wl_invt_active;
+    if (!strcmp(name, "firstcycle")) return s->firstcycle;
+    if (!strcmp(name, "histogram_reset")) return s->histogram_reset;
     return -1;
 }
 
@@ -1278,6 +1433,8 @@ void orc_set_i(orc_system *s, const char *name, int64_t v)
     else if (!strcmp(name, "mc_cycle_num")) s->mc_cycle_num = (int)v;
     else if (!strcmp(name, "walker_in_window")) s->walker_in_window = (int)v;
     else if (!strcmp(name, "wl_invt_active")) s->wl_invt_active = (int)v;
+    else if (!strcmp(name, "firstcycle")) s->firstcycle = (int)v;
+    else if (!strcmp(name, "histogram_reset")) s->histogram_reset = (int)v;
 }
 
 void orc_set_rng_philox(orc_system *s, uint64_t seed, uint32_t stream, uint64_t start_index)

@@ -114,6 +114,8 @@ typedef struct orc_system {
     int    walker_in_window;
     double transP, volP, swP;
     int    firstpass;
+    int    firstcycle;                 /* mc_moves.F90:85  "is this the original wl_factor" */
+    int    histogram_reset;            /* mc_moves.F90:1957 (saved local of mc_check_flatness) */
     /* comms module state (comms_mpi.f90:73-104) */
     double *eta_last_sync, *hist_last_sync, *uhist_last_sync;
     orc_rng rng;
@@ -150,6 +152,30 @@ int    orc_mc_run(orc_system *s, int ncycles);
 void   orc_mc_monitor(orc_system *s);                          /* state effects of mc_moves.F90:1722-1732,1786-1810 */
 void   orc_mc_chain_sync(orc_system *s);                       /* mc_moves.F90:2217-2416 */
 void   orc_allreduce_bins(orc_system **walkers, int nwalkers); /* comms_mpi.f90:244-277,461-530 over in-process walkers */
+
+/* ---- periodic bookkeeping that consumes the reduced arrays ---- */
+typedef struct orc_flat_params {       /* userparams.f90:33-36 */
+    int    wl_schedule;                /* 0 = within tol of mean, 1 = min visits, 2 = above (1-tol) of mean */
+    int    wl_minhist;
+    double wl_flattol;
+    int    wl_useinvt;
+} orc_flat_params;
+typedef struct orc_flat_report {       /* what mc_check_flatness writes to the log, for walker (rank) 0 */
+    int    checked;                    /* 0: returned at the samplerun / empty-histogram guard */
+    int    hist_reset;                 /* the one-off histogram reset of :1973-1980 happened in this call */
+    int    flat;
+    int    invt_switched;
+    double mean, max_pct, min_pct;
+    double wl_factor;                  /* after the call */
+} orc_flat_report;
+/* mc_check_flatness (mc_moves.F90:1936-2185), state effects on every walker (= MPI rank); the file
+ * dumps of :2067-2101 / :2147-2178 are left to the caller.  Returns non-zero on the reference's `stop`. */
+int    orc_mc_check_flatness(orc_system **walkers, int nwalkers, const orc_flat_params *fp, orc_flat_report *rep);
+/* mc_compute_deltaG_from_hist (mc_moves.F90:2498-2621): returns deltaG in kT (whole box), normP(nbins) */
+double orc_mc_deltaG_from_hist(orc_system **walkers, int nwalkers, double *normP);
+/* comms_join_uhist / comms_join_eta (comms_mpi.f90:299-375, :377-459): stitch the windows of dd runs */
+void   orc_join_uhist(orc_system **walkers, int nwalkers, int overlap, double *joined);
+void   orc_join_eta(orc_system **walkers, int nwalkers, int overlap, double *joined);
 
 /* RNG */
 void   orc_rng_philox(orc_rng *r, uint64_t seed, uint32_t stream, uint64_t start_index);

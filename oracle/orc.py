@@ -29,6 +29,15 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+class FlatParams(C.Structure):
+    _fields_ = [("wl_schedule", C.c_int), ("wl_minhist", C.c_int), ("wl_flattol", C.c_double), ("wl_useinvt", C.c_int)]
+
+
+class FlatReport(C.Structure):
+    _fields_ = [("checked", C.c_int), ("hist_reset", C.c_int), ("flat", C.c_int), ("invt_switched", C.c_int),
+                ("mean", C.c_double), ("max_pct", C.c_double), ("min_pct", C.c_double), ("wl_factor", C.c_double)]
+
+
 class Params(C.Structure):
     _fields_ = [
         ("temperature", C.c_double), ("pressure", C.c_double), ("npt", C.c_int),
@@ -75,6 +84,11 @@ def lib() -> C.CDLL:
     L.orc_mc_cycle.restype = i; L.orc_mc_cycle.argtypes = [vp]
     L.orc_mc_run.restype = i; L.orc_mc_run.argtypes = [vp, i]
     L.orc_allreduce_bins.argtypes = [C.POINTER(vp), i]
+    L.orc_mc_check_flatness.restype = i
+    L.orc_mc_check_flatness.argtypes = [C.POINTER(vp), i, C.POINTER(FlatParams), C.POINTER(FlatReport)]
+    L.orc_mc_deltaG_from_hist.restype = d; L.orc_mc_deltaG_from_hist.argtypes = [C.POINTER(vp), i, dp]
+    L.orc_join_uhist.argtypes = [C.POINTER(vp), i, i, dp]
+    L.orc_join_eta.argtypes = [C.POINTER(vp), i, i, dp]
     L.orc_philox_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, dp]
     L.orc_philox_raw.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.orc_mc_run_many.restype = i; L.orc_mc_run_many.argtypes = [C.POINTER(vp), i, i, i]
@@ -244,6 +258,36 @@ def _handles(walkers: Sequence[System]):
 
 def allreduce_bins(walkers: Sequence[System]) -> None:
     lib().orc_allreduce_bins(_handles(walkers), len(walkers))
+
+
+def mc_check_flatness(walkers: Sequence[System], wl_schedule: int = 0, wl_minhist: int = 20,
+                      wl_flattol: float = float(np.float32(0.05)), wl_useinvt: bool = False) -> "FlatReport":
+    """mc_check_flatness (mc_moves.F90:1936-2185) over in-process walkers (= MPI ranks)."""
+    fp = FlatParams(wl_schedule, wl_minhist, wl_flattol, int(wl_useinvt))
+    rep = FlatReport()
+    rc = lib().orc_mc_check_flatness(_handles(walkers), len(walkers), C.byref(fp), C.byref(rep))
+    if rc:
+        raise RuntimeError(f"oracle: reference stop {rc} in mc_check_flatness")
+    return rep
+
+
+def mc_deltaG_from_hist(walkers: Sequence[System]):
+    """mc_compute_deltaG_from_hist (mc_moves.F90:2498-2621): (deltaG in kT, normP)."""
+    normP = np.zeros(walkers[0].nbins, dtype=np.float64)
+    dG = lib().orc_mc_deltaG_from_hist(_handles(walkers), len(walkers), _dp(normP))
+    return float(dG), normP
+
+
+def join_uhist(walkers: Sequence[System], overlap: int) -> np.ndarray:
+    out = np.zeros(walkers[0].nbins, dtype=np.float64)
+    lib().orc_join_uhist(_handles(walkers), len(walkers), overlap, _dp(out))
+    return out
+
+
+def join_eta(walkers: Sequence[System], overlap: int) -> np.ndarray:
+    out = np.zeros(walkers[0].nbins, dtype=np.float64)
+    lib().orc_join_eta(_handles(walkers), len(walkers), overlap, _dp(out))
+    return out
 
 
 def mc_run_many(walkers: Sequence[System], ncycles: int, nthreads: int = 0) -> int:

@@ -76,3 +76,35 @@ def used_lists(nn, jn, vn):
 def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+class OracleSchedule:
+    """The periodic section of mc_cycle (mc_moves.F90:257-316) over in-process oracle walkers
+    (= MPI ranks): the checker's counterpart of mc_water_ls_mw_b200.schedule.CycleSchedule."""
+
+    def __init__(self, walkers, up, nthreads: int = 0):
+        self.ws, self.up, self.nthreads = walkers, up, nthreads
+        self.cycle = 0
+        self.flatness, self.deltaG = [], []
+
+    def run(self, ncycles: int):
+        up, ws = self.up, self.ws
+        two, mw = ws[0].nlat == 2, up.parallel_strategy == "mw"
+        for _ in range(int(ncycles)):
+            assert orc.mc_run_many(ws, 1, self.nthreads) == 0
+            self.cycle += 1
+            c = self.cycle
+            if two and mw and c % up.mpi_sync_int == 0:
+                orc.allreduce_bins(ws)
+            if c % up.monitor_int == 0:
+                for s in ws:
+                    s.mc_monitor()
+            if not two:
+                continue
+            if c % up.flat_chk_int == 0:
+                self.flatness.append((c, orc.mc_check_flatness(ws, up.wl_schedule, up.wl_minhist, up.wl_flattol, up.wl_useinvt)))
+            if c % up.latt_sync_int == 0:
+                for s in ws:
+                    s.mc_chain_sync()
+            if up.samplerun and c % up.deltaG_int == 0:
+                self.deltaG.append((c,) + orc.mc_deltaG_from_hist(ws))

@@ -32,13 +32,15 @@ def test_struct_sizes_match_header(tmp_path):
     import subprocess
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mwgpu.h"\n'
-                   'int main(void){printf("%zu %zu %zu %zu\\n", sizeof(mwgpu_mc_params), sizeof(mwgpu_walker_state),'
-                   ' offsetof(mwgpu_mc_params, ls), offsetof(mwgpu_walker_state, error));return 0;}\n')
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mwgpu_mc_params), sizeof(mwgpu_walker_state),'
+                   ' offsetof(mwgpu_mc_params, ls), offsetof(mwgpu_walker_state, error), sizeof(mwgpu_flat_params),'
+                   ' sizeof(mwgpu_flat_report), offsetof(mwgpu_flat_report, wl_factor));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
-    a, b, c, d = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+    a, b, c, d, e, f, g = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
     assert C.sizeof(_lib.McParams) == a and C.sizeof(_lib.WalkerState) == b
     assert _lib.McParams.ls.offset == c and _lib.WalkerState.error.offset == d
+    assert C.sizeof(_lib.FlatParams) == e and C.sizeof(_lib.FlatReport) == f and _lib.FlatReport.wl_factor.offset == g
 
 
 def test_sm100a_code_present():
