@@ -71,6 +71,21 @@ module mwgpu
      integer(c_int)     :: error
   end type mwgpu_walker_state
 
+  ! struct mwgpu_flat_params (userparams.f90:33-36)
+  type,bind(C) :: mwgpu_flat_params
+     integer(c_int) :: wl_schedule
+     integer(c_int) :: wl_minhist
+     real(c_double) :: wl_flattol
+     integer(c_int) :: wl_useinvt
+  end type mwgpu_flat_params
+
+  ! struct mwgpu_flat_report: what mc_check_flatness writes to the log (walker 0 of the context)
+  type,bind(C) :: mwgpu_flat_report
+     integer(c_int) :: checked,hist_reset,flat,invt_switched
+     real(c_double) :: mean,max_pct,min_pct
+     real(c_double) :: wl_factor
+  end type mwgpu_flat_report
+
   interface
 
      !---------------- lifecycle ----------------!
@@ -238,7 +253,38 @@ module mwgpu
        type(c_ptr),value :: ctx
      end function mwgpu_mc_chain_sync
 
+     ! mc_check_flatness (mc_moves.F90:1936-2185) on the device: state effects for every walker
+     integer(c_int) function mwgpu_mc_check_flatness(ctx,p,report) bind(C,name='mwgpu_mc_check_flatness')
+       import :: c_int,c_ptr,mwgpu_flat_params,mwgpu_flat_report
+       type(c_ptr),value                   :: ctx
+       type(mwgpu_flat_params),intent(in)  :: p
+       type(mwgpu_flat_report),intent(out) :: report
+     end function mwgpu_mc_check_flatness
+
+     ! mc_compute_deltaG_from_hist (mc_moves.F90:2498-2621) on the device
+     integer(c_int) function mwgpu_mc_deltag_from_hist(ctx,deltaG,normP) bind(C,name='mwgpu_mc_deltag_from_hist')
+       import :: c_int,c_ptr,c_double
+       type(c_ptr),value          :: ctx
+       real(c_double),intent(out) :: deltaG
+       real(c_double),intent(out) :: normP(*)
+     end function mwgpu_mc_deltag_from_hist
+
      !---------------- comms ----------------!
+     ! comms_join_uhist / comms_join_eta (comms_mpi.f90:299-375, :377-459)
+     integer(c_int) function mwgpu_comms_join_uhist(ctx,overlap,joined) bind(C,name='mwgpu_comms_join_uhist')
+       import :: c_int,c_ptr,c_double
+       type(c_ptr),value          :: ctx
+       integer(c_int),value       :: overlap
+       real(c_double),intent(out) :: joined(*)
+     end function mwgpu_comms_join_uhist
+
+     integer(c_int) function mwgpu_comms_join_eta(ctx,overlap,joined) bind(C,name='mwgpu_comms_join_eta')
+       import :: c_int,c_ptr,c_double
+       type(c_ptr),value          :: ctx
+       integer(c_int),value       :: overlap
+       real(c_double),intent(out) :: joined(*)
+     end function mwgpu_comms_join_eta
+
      integer(c_int) function mwgpu_comms_get_unique_id(id128) bind(C,name='mwgpu_comms_get_unique_id')
        import :: c_int,c_char
        character(kind=c_char),intent(out) :: id128(128)
