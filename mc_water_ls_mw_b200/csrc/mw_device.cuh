@@ -120,6 +120,23 @@ __device__ __forceinline__ void recipmatrix3(const double* h, double* r)
     for (int k = 0; k < 9; ++k) r[k] = xd(xm(xm(r[k], 2.0), PI), vol);
 }
 
+// 64-bit literals cost two UMOV instructions each at every use (10 % of the walker kernel's
+// instruction stream before this table existed); operands taken from the constant bank cost nothing.
+struct EnergyConsts {
+    double log2e, magic, ln2hi, ln2lo, xmin;
+    double e2, e3, e4, e5, e6, e7, e8, e9, e10, e11, e12, e13;   // 1/k!
+    double q3125, q375;
+    double rc, rc2, rcsq, sig02, ss, bigb, aeps, leps, gs, cos0, c099;
+};
+__constant__ EnergyConsts CK = {
+    1.4426950408889634, 6755399441055744.0, 6.93147180369123816490e-01, 1.90821492927058770002e-10, -708.0,
+    0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.333333333333333e-03, 1.388888888888889e-03,
+    1.984126984126984e-04, 2.48015873015873e-05, 2.755731922398589e-06, 2.755731922398589e-07,
+    2.505210838544172e-08, 2.08767569878681e-09, 1.6059043836821613e-10,
+    0.3125, 0.375,
+    RC, RC * RC, RCSQ, 0.2 * SIGMA, SS, BIGB, AEPS, LEPS, GS, COS0, 0.99,
+};
+
 // ---------------------------------------------------------------- fast fp64 math for the ENERGY arithmetic
 // The library routines (division, rsqrt, exp) carry special-case handling that costs 40-60 SASS
 // instructions each; the energy terms only see normal, positive, moderate arguments, so a MUFU
@@ -138,7 +155,7 @@ __device__ __forceinline__ double rsqrt_fast(double x)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));     // MUFU.RSQ64H seed (20 mantissa bits of x), e = 1 - x y^2 ~ 2^-19
     const double e = fma(-(x * y), y, 1.0);                      // x^-1/2 = y (1 - e)^-1/2 = y (1 + e/2 + 3e^2/8 + 5e^3/16 + O(e^4))
-    const double p = fma(fma(0.3125, e, 0.375), e, 0.5);         // one quartic step (error 35/128 e^4); p and y*e are independent
+    const double p = fma(fma(CK.q3125, e, CK.q375), e, 0.5);         // one quartic step (error 35/128 e^4); p and y*e are independent
     return fma(y * e, p, y);
 }
 
@@ -147,8 +164,8 @@ __device__ __forceinline__ double rsqrt_fast(double x)
 __device__ __forceinline__ void bond_radial(double r2, double& ir, double& isr)
 {
     ir = rsqrt_fast(r2);
-    const double id = rcp_fast(r2 - RC * RC);
-    isr = fma(r2, ir, RC) * id;
+    const double id = rcp_fast(r2 - CK.rc2);
+    isr = fma(r2, ir, CK.rc) * id;
 }
 
 // exp(x) for x <= ~700; returns 0 below -708 (the SW terms vanish at the cut-off: x -> -inf).
@@ -156,20 +173,20 @@ __device__ __forceinline__ void bond_radial(double r2, double& ir, double& isr)
 // the walker kernel is bound by latency and instruction supply, not by fp64 throughput).
 __device__ __forceinline__ double exp_fast(double x)
 {
-    const double xc = fmax(x, -708.0);
-    const double t = fma(xc, 1.4426950408889634, 6755399441055744.0);    // round(x*log2 e) in the low word
+    const double xc = fmax(x, CK.xmin);
+    const double t = fma(xc, CK.log2e, CK.magic);                          // round(x*log2 e) in the low word
     const int n = __double2loint(t);
-    const double fn = t - 6755399441055744.0;
-    double r = fma(-fn, 6.93147180369123816490e-01, xc);
-    r = fma(-fn, 1.90821492927058770002e-10, r);                           // |r| <= ln2/2
+    const double fn = t - CK.magic;
+    double r = fma(-fn, CK.ln2hi, xc);
+    r = fma(-fn, CK.ln2lo, r);                                             // |r| <= ln2/2
     const double r2 = r * r;
     const double a0 = 1.0 + r;                                             // 1/0! + r/1!
-    const double a1 = fma(1.6666666666666666e-01, r, 0.5);                 // 1/2! + r/3!
-    const double a2 = fma(8.333333333333333e-03, r, 4.1666666666666664e-02);
-    const double a3 = fma(1.984126984126984e-04, r, 1.388888888888889e-03);
-    const double a4 = fma(2.755731922398589e-06, r, 2.48015873015873e-05);
-    const double a5 = fma(2.505210838544172e-08, r, 2.755731922398589e-07);
-    const double a6 = fma(1.6059043836821613e-10, r, 2.08767569878681e-09);
+    const double a1 = fma(CK.e3, r, CK.e2);                                // 1/2! + r/3!
+    const double a2 = fma(CK.e5, r, CK.e4);
+    const double a3 = fma(CK.e7, r, CK.e6);
+    const double a4 = fma(CK.e9, r, CK.e8);
+    const double a5 = fma(CK.e11, r, CK.e10);
+    const double a6 = fma(CK.e13, r, CK.e12);
     const double r4 = r2 * r2;
     const double b0 = fma(a1, r2, a0);
     const double b1 = fma(a3, r2, a2);
@@ -179,7 +196,7 @@ __device__ __forceinline__ double exp_fast(double x)
     const double c1 = fma(a6, r4, b2);
     const double p = fma(c1, r8, c0);
     const double s = __hiloint2double((n + 1023) << 20, 0);               // 2^n, n in [-1022, 1023]
-    return (x < -708.0) ? 0.0 : p * s;
+    return (x < CK.xmin) ? 0.0 : p * s;
 }
 
 // log(x) for normal positive x (no special cases), ~2e-16 relative: x = m*2^e, m in [sqrt(1/2), sqrt(2)),
@@ -521,20 +538,20 @@ __device__ __forceinline__ double eval_bond(double* q, int r)
     double ir, isr;
     bond_radial(r2, ir, isr);
     // exp(sigma*isr) = e^5 and exp(gamma*sigma*isr) = e^6 with e = exp(0.2*sigma*isr)  (gamma = 1.2)
-    const double e1 = exp_fast((0.2 * SIGMA) * isr);
+    const double e1 = exp_fast(CK.sig02 * isr);
     const double e_2 = e1 * e1, e_4 = e_2 * e_2;
     const double e2 = e_4 * e1;
     const double g = e_4 * e_2;
-    const double s2 = SS * ir * ir;
+    const double s2 = CK.ss * ir * ir;
     q[r] = tx * ir; q[QC + r] = ty * ir; q[2 * QC + r] = tz * ir; q[3 * QC + r] = g;
-    return AEPS * (BIGB * (s2 * s2) - 1.0) * e2;
+    return CK.aeps * (CK.bigb * (s2 * s2) - 1.0) * e2;
 }
 
 // (cos(theta) - cos0)^2 with the reference's k==i filter (molint.F90:367-371)
 __device__ __forceinline__ double hfun(double ct)
 {
-    const double d = ct - COS0;
-    return (ct < 0.99) ? d * d : 0.0;
+    const double d = ct - CK.cos0;
+    return (ct < CK.c099) ? d * d : 0.0;
 }
 
 // Sum 4 per-lane accumulators over the warp (pairwise shuffle tree) and
@@ -627,7 +644,7 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
         const double pjx = P[j] + V[img], pjy = P[N + j] + V[IVC + img], pjz = P[2 * N + j] + V[2 * IVC + img];
         const double tox = pjx - P[imol], toy = pjy - P[N + imol], toz = pjz - P[2 * N + imol];
         const double r2o = tox * tox + toy * toy + toz * toz;
-        const bool fo = has && r2o < RCSQ;
+        const bool fo = has && r2o < CK.rcsq;
         const uint32_t bo = __ballot_sync(FULL, fo);
         mo[lat] = bo;
         const int io = nq + __popc(bo & lt);
@@ -637,7 +654,7 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
         if (WITH_NEW) {
             tnx = pjx - pnew[lat][0]; tny = pjy - pnew[lat][1]; tnz = pjz - pnew[lat][2];
             r2n = tnx * tnx + tny * tny + tnz * tnz;
-            fn = has && r2n < RCSQ;
+            fn = has && r2n < CK.rcsq;
             bn = __ballot_sync(FULL, fn);
             mn[lat] = bn;
             in_ = nq + __popc(bn & lt);
@@ -706,7 +723,7 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
                 tb += q[3 * QC + c] * hfun(ct) * mult;
             }
         }
-        tb *= LEPS * g;
+        tb *= CK.leps * g;
         a0 += (ev == 0) ? tb : 0.0; a1 += (ev == 1) ? tb : 0.0;
         a2 += (ev == 2) ? tb : 0.0; a3 += (ev == 3) ? tb : 0.0;
     }
@@ -771,10 +788,10 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
                     const double ty = (P[N + k] + V[IVC + img]) - P[N + j];
                     const double tz = (P[2 * N + k] + V[2 * IVC + img]) - P[2 * N + j];
                     const double sq = tx * tx + ty * ty + tz * tz;
-                    if (sq < RCSQ) {
+                    if (sq < CK.rcsq) {
                         double vi, isr;
                         bond_radial(sq, vi, isr);
-                        const double ex = LEPS * exp_fast(GS * isr);
+                        const double ex = CK.leps * exp_fast(CK.gs * isr);
                         const double ux = tx * vi, uy = ty * vi, uz = tz * vi;
                         const uint16_t qo = w.cq[c * 2], qn = w.cq[c * 2 + 1];
                         double vo = 0.0, vn = 0.0;

@@ -491,7 +491,9 @@ __device__ __forceinline__ void commit_translation(const WalkerView& w, int imol
 // ---------------------------------------------------------------- the walker kernel
 // One warp (= one CTA of 32 threads) per walker; ncycles MC cycles of the hot
 // part of mc_cycle (mc_moves.F90:117-255).
-template <int NLAT>
+// NT > 0: the number of molecules as a compile-time constant (every offset into the walker's shared
+// memory image folds into the LDS/STS immediates: ~8 % fewer instructions); NT == 0: N = S.N at run time.
+template <int NLAT, int NT>
 __global__ void __launch_bounds__(32, MW_MC_BLOCKS) k_mc_run(const __grid_constant__ DeviceState S,
                                                const __grid_constant__ McParams p, int ncycles)
 {
@@ -499,7 +501,7 @@ __global__ void __launch_bounds__(32, MW_MC_BLOCKS) k_mc_run(const __grid_consta
     const int wi = blockIdx.x;
     if (wi >= S.W) return;
     const int lane = lane_id();
-    const int N = S.N;
+    const int N = (NT > 0) ? NT : S.N;
     const WalkerView w = carve_walker(smem, N, NLAT);
     load_walker(S, wi, w);
     WalkerScalars* sc = w.sc;

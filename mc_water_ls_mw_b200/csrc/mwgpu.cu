@@ -944,13 +944,15 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
     if (ncycles < 0) return fail("mwgpu_mc_run: ncycles must be >= 0");
     const size_t smem = walker_smem_bytes(c->N, c->nlat);
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    if (c->nlat == 2) {
-        CUDA_TRY(cudaFuncSetAttribute(k_mc_run<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_mc_run<2><<<c->W, 32, smem, c->stream>>>(c->S, c->P, ncycles);
-    } else {
-        CUDA_TRY(cudaFuncSetAttribute(k_mc_run<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_mc_run<1><<<c->W, 32, smem, c->stream>>>(c->S, c->P, ncycles);
-    }
+    // the 48-molecule boxes of every reference deck get the kernel with N folded into its addressing
+#define MW_LAUNCH_MC(NLAT_, NT_)                                                                                  \
+    do {                                                                                                          \
+        CUDA_TRY(cudaFuncSetAttribute(k_mc_run<NLAT_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_mc_run<NLAT_, NT_><<<c->W, 32, smem, c->stream>>>(c->S, c->P, ncycles);                                 \
+    } while (0)
+    if (c->nlat == 2) { if (c->N == 48) MW_LAUNCH_MC(2, 48); else MW_LAUNCH_MC(2, 0); }
+    else              { if (c->N == 48) MW_LAUNCH_MC(1, 48); else MW_LAUNCH_MC(1, 0); }
+#undef MW_LAUNCH_MC
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     c->launches++;
     if (int rc = finish(c, sync)) return rc;
