@@ -58,6 +58,9 @@ constexpr double F_HUGE  = 1.7976931348623157e308;
 #ifndef MW_KC
 #define MW_KC 256
 #endif
+#ifndef MW_CAND_ILP
+#define MW_CAND_ILP 1      // neighbour-bond candidates per lane and iteration in the j-centred triplet stage (2: measured 11 % slower)
+#endif
 constexpr int LC  = MW_LC;    // list slots per molecule held in shared memory (one lane per slot)
 constexpr int IVC = 32;    // image vectors per lattice (27 in every BASELINE config)
 constexpr int QC  = MW_QC;    // bond records per batch (a trial move has ~26; more than QC in-range bonds -> ERR_BOND_OVERFLOW)
@@ -630,7 +633,6 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
     const unsigned lt = lt_mask();
     double* q = w.q;
     int nq = 0, nc = 0;
-    int seg_start[4] = {0, 0, 0, 0}, seg_n[4] = {0, 0, 0, 0};
 
     // ---- stage 1: distance tests over imol's own list (lanes = slots), compaction into bond records
 #pragma unroll
@@ -648,7 +650,7 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
         const uint32_t bo = __ballot_sync(FULL, fo);
         mo[lat] = bo;
         const int io = nq + __popc(bo & lt);
-        seg_start[lat * 2] = nq; seg_n[lat * 2] = __popc(bo); nq += __popc(bo);
+        nq += __popc(bo);
         bool fn = false; int in_ = 0; uint32_t bn = 0;
         double tnx = 0, tny = 0, tnz = 0, r2n = 0;
         if (WITH_NEW) {
@@ -658,7 +660,7 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
             bn = __ballot_sync(FULL, fn);
             mn[lat] = bn;
             in_ = nq + __popc(bn & lt);
-            seg_start[lat * 2 + 1] = nq; seg_n[lat * 2 + 1] = __popc(bn); nq += __popc(bn);
+            nq += __popc(bn);
         }
         const uint32_t bu = bo | bn;
         const int ic = nc + __popc(bu & lt);
@@ -666,11 +668,11 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
         // nc <= 2*LC == CC by construction; nq may exceed QC only at unphysical densities (flagged below)
         if (fo && io < QC) {
             q[io] = tox; q[QC + io] = toy; q[2 * QC + io] = toz; q[3 * QC + io] = r2o;
-            w.qmeta[io] = (uint32_t)(lat * 2) | ((uint32_t)j << 8);
+            w.qmeta[io] = (uint32_t)(lat * 2) | ((uint32_t)__popc(bo) << 2) | ((uint32_t)j << 8) | ((uint32_t)__popc(bo & lt) << 18);
         }
         if (WITH_NEW && fn && in_ < QC) {
             q[in_] = tnx; q[QC + in_] = tny; q[2 * QC + in_] = tnz; q[3 * QC + in_] = r2n;
-            w.qmeta[in_] = (uint32_t)(lat * 2 + 1) | ((uint32_t)j << 8);
+            w.qmeta[in_] = (uint32_t)(lat * 2 + 1) | ((uint32_t)__popc(bn) << 2) | ((uint32_t)j << 8) | ((uint32_t)__popc(bn & lt) << 18);
         }
         if (fo || fn) {
             w.cmeta[ic] = (uint32_t)lat | ((uint32_t)j << 6);
@@ -681,8 +683,6 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
     if (nq > QC) {                                  // results of this call are invalid; the walker is flagged
         w.sc->error |= ERR_BOND_OVERFLOW;
         nq = QC;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { seg_start[c] = 0; seg_n[c] = 0; }
     }
     __syncwarp();
 
@@ -700,28 +700,34 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
     }
     __syncwarp();
 
-    // ---- stage 3: triplets centred on imol: all pairs (b<c) of bond records of one evaluation
-    // (lanes = records b, loop over the later records c of the same evaluation)
+    // ---- stage 3: triplets centred on imol: all unordered pairs of bond records of one evaluation.
+    // Lanes = records; a record at position `pos` of its segment of n records pairs with the records
+    // (pos + d) mod n, d = 1 .. n/2: every pair exactly once (for even n the step d = n/2 meets each
+    // pair from both ends, so only the lower half of the segment takes it), all lanes busy in every
+    // step and half as many steps as a "later records" loop.
+    const int nq3 = (w.sc->error & ERR_BOND_OVERFLOW) ? 0 : nq;     // overflowed records are incomplete: flagged, skipped
 #pragma unroll 1
-    for (int b0 = 0; b0 < nq; b0 += 32) {
+    for (int b0 = 0; b0 < nq3; b0 += 32) {
         const int r = b0 + lane;
-        const bool act = r < nq;
-        const uint32_t qm = act ? w.qmeta[r] : 0u;
-        const int ev = qm & 3;
-        const int send = act ? ((ev == 0) ? seg_start[0] + seg_n[0] : (ev == 1) ? seg_start[1] + seg_n[1]
-                                : (ev == 2) ? seg_start[2] + seg_n[2] : seg_start[3] + seg_n[3]) : 0;
+        const bool act = r < nq3;
+        const uint32_t qm = act ? w.qmeta[r] : 0u;                // ev | n << 2 | j << 8 | pos << 18
+        const int ev = qm & 3, n = (qm >> 2) & 63, pos = (qm >> 18) & 63;
+        const int half = n >> 1, send = r - pos + n;
+        const bool even = !(n & 1);
         const double ux = act ? q[r] : 0.0, uy = act ? q[QC + r] : 0.0, uz = act ? q[2 * QC + r] : 0.0;
         const double g = act ? q[3 * QC + r] : 0.0;
-        const int maxd = __reduce_max_sync(FULL, act ? send - r - 1 : 0);
+        const int maxd = __reduce_max_sync(FULL, half);
         double tb = 0.0;
 #pragma unroll 1
         for (int d = 1; d <= maxd; ++d) {
-            const int c = r + d;
-            if (c < send) {
-                const double ct = ux * q[c] + uy * q[QC + c] + uz * q[2 * QC + c];
-                const double mult = ((qm >> 8) == (w.qmeta[c] >> 8)) ? 3.0 : 1.0;   // images of one molecule
-                tb += q[3 * QC + c] * hfun(ct) * mult;
-            }
+            int c = r + d;
+            c = (c >= send) ? c - n : c;
+            const bool on = (d <= half) && !(even && d == half && pos >= half);
+            c = on ? c : r;
+            const double ct = ux * q[c] + uy * q[QC + c] + uz * q[2 * QC + c];
+            const double mult = (((qm ^ w.qmeta[c]) & 0x3ff00u) == 0u) ? 3.0 : 1.0;   // images of one molecule
+            const double v = q[3 * QC + c] * hfun(ct) * mult;
+            tb += on ? v : 0.0;
         }
         tb *= CK.leps * g;
         a0 += (ev == 0) ? tb : 0.0; a1 += (ev == 1) ? tb : 0.0;
@@ -772,40 +778,46 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
             }
         }
         __syncwarp();
-        for (int tb0 = 0; tb0 < ncand; tb0 += 32) {
-            const int t = tb0 + lane;
-            if (t < ncand) {
-                const uint32_t ce = w.cand[t];
+        // Branch-free body: invalid lanes work on clamped indices and are discarded by selects (no
+        // BSSY/BSYNC regions inside the loop).  More than one candidate per lane and iteration
+        // (MW_CAND_ILP) executes empty tail passes and was measured slower: kernel time follows the
+        // number of executed warp-instructions, not the length of the dependency chains.
+        for (int tb0 = 0; tb0 < ncand; tb0 += 32 * MW_CAND_ILP) {
+#pragma unroll
+            for (int h = 0; h < MW_CAND_ILP; ++h) {
+                const int t = tb0 + 32 * h + lane;
+                const bool in = t < ncand;
+                const uint32_t ce = w.cand[in ? t : 0];
                 const int c = cb + (int)(ce >> 5), s2 = ce & 31;
                 const uint32_t cm = w.cmeta[c];
                 const int lat = cm & 1, j = (cm >> 6) & 1023;
                 const uint32_t e2 = w.list[((size_t)lat * N + j) * LC + s2];
                 const int k = e2 & 1023, img = e2 >> 10;
-                if (k != imol) {
-                    const double* P = w.pos + lat * 3 * N;
-                    const double* V = w.iv + lat * 3 * IVC;
-                    const double tx = (P[k] + V[img]) - P[j];
-                    const double ty = (P[N + k] + V[IVC + img]) - P[N + j];
-                    const double tz = (P[2 * N + k] + V[2 * IVC + img]) - P[2 * N + j];
-                    const double sq = tx * tx + ty * ty + tz * tz;
-                    if (sq < CK.rcsq) {
-                        double vi, isr;
-                        bond_radial(sq, vi, isr);
-                        const double ex = CK.leps * exp_fast(CK.gs * isr);
-                        const double ux = tx * vi, uy = ty * vi, uz = tz * vi;
-                        const uint16_t qo = w.cq[c * 2], qn = w.cq[c * 2 + 1];
-                        double vo = 0.0, vn = 0.0;
-                        if (qo != NONE16) {
-                            const double ct = -(q[qo] * ux + q[QC + qo] * uy + q[2 * QC + qo] * uz);
-                            vo = q[3 * QC + qo] * ex * hfun(ct);
-                        }
-                        if (WITH_NEW && qn != NONE16) {
-                            const double ct = -(q[qn] * ux + q[QC + qn] * uy + q[2 * QC + qn] * uz);
-                            vn = q[3 * QC + qn] * ex * hfun(ct);
-                        }
-                        if (lat == 0) { a0 += vo; a1 += vn; } else { a2 += vo; a3 += vn; }
-                    }
+                const double* P = w.pos + lat * 3 * N;
+                const double* V = w.iv + lat * 3 * IVC;
+                const double tx = (P[k] + V[img]) - P[j];
+                const double ty = (P[N + k] + V[IVC + img]) - P[N + j];
+                const double tz = (P[2 * N + k] + V[2 * IVC + img]) - P[2 * N + j];
+                const double sq0 = tx * tx + ty * ty + tz * tz;
+                const bool ok = in && (k != imol) && (sq0 < CK.rcsq);
+                const double sq = ok ? sq0 : CK.ss;                    // any length inside the cut-off
+                double vi, isr;
+                bond_radial(sq, vi, isr);
+                const double ex = CK.leps * exp_fast(CK.gs * isr);
+                const double ux = tx * vi, uy = ty * vi, uz = tz * vi;
+                const uint32_t cq2 = *(const uint32_t*)(w.cq + c * 2);
+                const uint32_t qo = cq2 & 0xffffu, qn = cq2 >> 16;
+                const bool ho = ok && (qo != NONE16), hn = WITH_NEW && ok && (qn != NONE16);
+                const int io = (qo != NONE16) ? (int)qo : 0, in_ = (qn != NONE16) ? (int)qn : 0;
+                const double cto = -(q[io] * ux + q[QC + io] * uy + q[2 * QC + io] * uz);
+                const double vo = ho ? q[3 * QC + io] * ex * hfun(cto) : 0.0;
+                double vn = 0.0;
+                if (WITH_NEW) {
+                    const double ctn = -(q[in_] * ux + q[QC + in_] * uy + q[2 * QC + in_] * uz);
+                    vn = hn ? q[3 * QC + in_] * ex * hfun(ctn) : 0.0;
                 }
+                a0 += (lat == 0) ? vo : 0.0; a1 += (lat == 0) ? vn : 0.0;
+                a2 += (lat == 0) ? 0.0 : vo; a3 += (lat == 0) ? 0.0 : vn;
             }
         }
         __syncwarp();
