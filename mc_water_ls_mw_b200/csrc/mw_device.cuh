@@ -866,7 +866,7 @@ __device__ __noinline__ double full_energy_warp(unsigned char* smem, int N, int 
             if (f) {
                 const int io = nq + __popc(bm & lt);
                 q[io] = tx; q[QC + io] = ty; q[2 * QC + io] = tz; q[3 * QC + io] = r2;
-                w.qmeta[io] = (uint32_t)(nq + cnt);  // end of this molecule's segment
+                w.qmeta[io] = (uint32_t)cnt | ((uint32_t)__popc(bm & lt) << 8);   // segment length | position in it
             }
             nq += cnt;
         }
@@ -877,27 +877,30 @@ __device__ __noinline__ double full_energy_warp(unsigned char* smem, int N, int 
             if (r < nq) acc += 0.5 * eval_bond(q, r);
         }
         __syncwarp();
-        // ---- triplets centred on each molecule of the chunk (lanes = records, loop over later
-        // records of the same molecule)
+        // ---- triplets centred on each molecule of the chunk: lanes = records, rotation pairing inside
+        // the molecule's segment as in local_energies_warp (every unordered pair once, all lanes busy)
         for (int b = 0; b < nq; b += 32) {
             const int r = b + lane;
             const bool act = r < nq;
-            const int send = act ? (int)w.qmeta[r] : 0;
+            const uint32_t qm = act ? w.qmeta[r] : 0u;
+            const int n = qm & 255, pos = qm >> 8;
+            const int half = n >> 1, send = r - pos + n;
+            const bool even = !(n & 1);
             const double ux = act ? q[r] : 0.0, uy = act ? q[QC + r] : 0.0, uz = act ? q[2 * QC + r] : 0.0;
             const double g = act ? q[3 * QC + r] : 0.0;
             double tb = 0.0;
-            const int more = act ? send - r - 1 : 0;
-            const int maxd = __reduce_max_sync(FULL, more);
+            const int maxd = __reduce_max_sync(FULL, half);
             for (int d = 1; d <= maxd; ++d) {
-                const int r2i = r + d;
-                if (act && r2i < send) {
-                    const double ct = ux * q[r2i] + uy * q[QC + r2i] + uz * q[2 * QC + r2i];
-                    // no k==i filter here: compute_model_energy has none (molint.F90:480-483)
-                    const double dd = ct - COS0;
-                    tb += g * q[3 * QC + r2i] * dd * dd;
-                }
+                int c = r + d;
+                c = (c >= send) ? c - n : c;
+                const bool on = (d <= half) && !(even && d == half && pos >= half);
+                c = on ? c : r;
+                const double ct = ux * q[c] + uy * q[QC + c] + uz * q[2 * QC + c];
+                // no k==i filter here: compute_model_energy has none (molint.F90:480-483)
+                const double dd = ct - CK.cos0;
+                tb += on ? q[3 * QC + c] * dd * dd : 0.0;
             }
-            acc += LEPS * tb;
+            acc += CK.leps * g * tb;
         }
         __syncwarp();
         a = a1;
