@@ -694,8 +694,10 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
         if (r < nq) {
             const double pe = eval_bond(q, r);
             const int c = w.qmeta[r] & 3;
-            a0 += (c == 0) ? pe : 0.0; a1 += (c == 1) ? pe : 0.0;
-            a2 += (c == 2) ? pe : 0.0; a3 += (c == 3) ? pe : 0.0;
+            if (c == 0) a0 += pe;
+            if (c == 1) a1 += pe;
+            if (c == 2) a2 += pe;
+            if (c == 3) a3 += pe;
         }
     }
     __syncwarp();
@@ -727,11 +729,13 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
             const double ct = ux * q[c] + uy * q[QC + c] + uz * q[2 * QC + c];
             const double mult = (((qm ^ w.qmeta[c]) & 0x3ff00u) == 0u) ? 3.0 : 1.0;   // images of one molecule
             const double v = q[3 * QC + c] * hfun(ct) * mult;
-            tb += on ? v : 0.0;
+            if (on) tb += v;
         }
         tb *= CK.leps * g;
-        a0 += (ev == 0) ? tb : 0.0; a1 += (ev == 1) ? tb : 0.0;
-        a2 += (ev == 2) ? tb : 0.0; a3 += (ev == 3) ? tb : 0.0;
+        if (ev == 0) a0 += tb;
+        if (ev == 1) a1 += tb;
+        if (ev == 2) a2 += tb;
+        if (ev == 3) a3 += tb;
     }
 
     // ---- stages 4+5: j-centred triplets.  Centres are taken in groups (all of them, or 8 at a time
@@ -816,8 +820,7 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
                     const double ctn = -(q[in_] * ux + q[QC + in_] * uy + q[2 * QC + in_] * uz);
                     vn = hn ? q[3 * QC + in_] * ex * hfun(ctn) : 0.0;
                 }
-                a0 += (lat == 0) ? vo : 0.0; a1 += (lat == 0) ? vn : 0.0;
-                a2 += (lat == 0) ? 0.0 : vo; a3 += (lat == 0) ? 0.0 : vn;
+                if (lat == 0) { a0 += vo; a1 += vn; } else { a2 += vo; a3 += vn; }     // predicated adds
             }
         }
         __syncwarp();
