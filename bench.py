@@ -106,6 +106,19 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def _traffic(kernel: str, cycles: int, walkers: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
+    (profiles/traffic.json, written by scripts/prof_final.sh); only valid for the launch shape it was taken on."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        if cycles == CYCLES_PER_STEP and walkers == WALKERS_PER_GPU:
+            return float(t[kernel]["dram_bytes"])
+    except Exception:
+        pass
+    return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -358,8 +371,8 @@ def run_ours(args):
                              "hbm_frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "hbm_peak": peak_kind,
                              "fp64_tflops_algorithmic": nw * up.num_lattices * FLOP_PER_EVAL / (e_ms * 1e-3) / 1e12},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
-                         "kernel": "k_mc_run<2>", "kernel_ms": k_ms,
+                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": _traffic("k_mc_run", C, nw),
+                         "kernel": "k_mc_run<2,48>", "kernel_ms": k_ms,
                          "note": "algorithmic flop (10730 per attempted move, BASELINE.md) / measured DFMA peak of this GPU "
                                  "(mwgpu_measure_fp64_peak; MEASURED_PEAKS.json has no fp64 entry)"},
             "e2e": {"value": e2e_value, "unit": "attempted MC moves/s", "h2d_bytes_per_step": int(h2d),

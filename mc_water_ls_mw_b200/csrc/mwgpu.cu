@@ -1113,6 +1113,32 @@ __global__ void k_reduce_bins(DeviceState S, double* __restrict__ delta, int NBP
     delta[t] = s;
 }
 
+// The same sum for large batches: one CTA per (array, bin); thread t adds the walkers t, t+256, ... in
+// walker order, then a fixed shared-memory tree.  Deterministic, but not the serial order (MPI leaves the
+// order of its reduction unspecified as well); batches of up to REDUCE_SERIAL_MAX walkers keep the serial
+// kernel, whose order the oracle reproduces bit for bit.
+constexpr int REDUCE_SERIAL_MAX = 256;
+__global__ void __launch_bounds__(256) k_reduce_bins_tree(DeviceState S, double* __restrict__ delta, int NBP, int first)
+{
+    __shared__ double part[256];
+    const int a = first + blockIdx.x / NBP, k = blockIdx.x % NBP;
+    double s = 0.0;
+    if (k < S.NB) {
+        const double* arr = (a == 0) ? S.weight : (a == 1) ? S.hist : S.uhist;
+        const double* base = (a == 0) ? S.wbase : (a == 1) ? S.hbase : S.ubase;
+        for (int w = threadIdx.x; w < S.W; w += 256) s = s + (arr[(size_t)w * S.NB + k] - base[(size_t)w * S.NB + k]);
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) part[threadIdx.x] += part[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) delta[a * NBP + k] = part[0];
+}
+
+static void launch_reduce_bins(mwgpu_ctx* c, int first, int narr);
+
 // arr = total + base ; base = arr
 __global__ void k_apply_bins(DeviceState S, const double* __restrict__ delta, int NBP, int first, int narr)
 {
@@ -1136,13 +1162,20 @@ __global__ void k_clear_wmin(DeviceState S)
 
 static int narr_of(const mwgpu_ctx* c) { return c->user.samplerun ? 3 : 2; }
 
+static void launch_reduce_bins(mwgpu_ctx* c, int first, int narr)
+{
+    const int n = narr * c->NBP;
+    if (c->W <= REDUCE_SERIAL_MAX) k_reduce_bins<<<(n + 127) / 128, 128, 0, c->stream>>>(c->S, c->delta, c->NBP, first, narr);
+    else k_reduce_bins_tree<<<n, 256, 0, c->stream>>>(c->S, c->delta, c->NBP, first);
+    c->launches++;
+}
+
 extern "C" int mwgpu_comms_reduce_local(mwgpu_ctx* c, void** dev_ptr, int* count)
 {
     if (int rc = check_ctx(c, 0, false)) return rc;
     if (!c->mc_ready) return fail("mwgpu_comms_reduce_local: call mwgpu_mc_init first");
     const int narr = narr_of(c), n = narr * c->NBP;
-    k_reduce_bins<<<(n + 127) / 128, 128, 0, c->stream>>>(c->S, c->delta, c->NBP, 0, narr);
-    c->launches++;
+    launch_reduce_bins(c, 0, narr);
     if (dev_ptr) *dev_ptr = c->delta;
     if (count) *count = n;
     return finish(c, dev_ptr != nullptr);
@@ -1260,8 +1293,7 @@ extern "C" int mwgpu_comms_allreduce_bins(mwgpu_ctx* c)
 static int allreduce_arrays(mwgpu_ctx* c, int first, int narr)
 {
     const int n = narr * c->NBP;
-    k_reduce_bins<<<(n + 127) / 128, 128, 0, c->stream>>>(c->S, c->delta, c->NBP, first, narr);
-    c->launches++;
+    launch_reduce_bins(c, first, narr);
     if (c->nccl_comm && c->nranks > 1) {
         double* d = c->delta + (size_t)first * c->NBP;
         const int r = g_nccl.AllReduce(d, d, (size_t)n, 8, 0, c->nccl_comm, c->stream);

@@ -197,3 +197,24 @@ def test_statistical_consistency_of_histograms_and_deltaG():
     err = np.hypot(jk(ug[:half]), jk(ug[half:]))
     assert np.isfinite(ra) and np.isfinite(rb)
     assert abs(ra - rb) < 5 * err + 0.05, (ra, rb, err)
+
+
+def test_tree_reduction_of_large_batches_matches_a_host_sum():
+    """More than 256 walkers take the one-CTA-per-bin reduction (deterministic, not the serial order)."""
+    n = 300
+    g, up = make_gpu_walkers("ice1_gen_weights", nwalkers=n, overrides={"eq_mc_cycles": 1})
+    g.set_rng_philox(SEED, 0, 1000000)
+    g.mc_run(4)
+    per = [g.bins(w) for w in range(n)]
+    w0 = per[0][0].copy()                                       # weights start equal, so the base is anything minus its own delta
+    g.comms_allreduce_bins()
+    base_w = np.zeros_like(w0)                                  # eta_last_sync = the (zero) start weights, hist_last_sync = 0
+    tot_w = base_w + np.sum([p[0] - base_w for p in per], axis=0)
+    tot_h = np.sum([p[1] for p in per], axis=0)
+    for w in (0, 1, n - 1):
+        wg, hg, _ = g.bins(w)
+        np.testing.assert_allclose(wg, tot_w, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(hg, tot_h, rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(g.bins(0)[0], g.bins(n - 1)[0])
+    g.comms_allreduce_bins()                                    # nothing new since the sync: a fixed point
+    np.testing.assert_allclose(g.bins(5)[0], tot_w, rtol=1e-12, atol=1e-12)
