@@ -291,6 +291,7 @@ struct WalkerView {
     double*   save;    // [36]    old cell + recip during a volume move
     double*   rngbuf;  // [RB]    buffered U[0,1) numbers
     double*   lv;      // [2]     log(V1/V2), log(V2/V1)
+    double*   mv;      // [2][6]  trial position (x,y,z) and displacement (x,y,z) of the move in flight, per lattice
     WalkerScalars* sc;
     uint64_t* rngbase; // draw index of rngbuf[0]
     uint32_t* qmeta;   // [QC]   call | j<<8
@@ -307,7 +308,7 @@ struct WalkerView {
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t smem_doubles(int N, int nlat)
 {
-    return (size_t)nlat * 3 * N + (size_t)nlat * 3 * IVC + (size_t)nlat * 18 + 4 * QC + 36 + RB + 2;
+    return (size_t)nlat * 3 * N + (size_t)nlat * 3 * IVC + (size_t)nlat * 18 + 4 * QC + 36 + RB + 2 + 12;
 }
 
 // Layout (every block 16-byte aligned): doubles | scalars | list | 32-bit words | 16-bit words | bytes
@@ -335,6 +336,7 @@ __device__ __forceinline__ WalkerView carve_walker(unsigned char* base, int N, i
     w.save   = w.q + 4 * QC;
     w.rngbuf = w.save + 36;
     w.lv     = w.rngbuf + RB;
+    w.mv     = w.lv + 2;
     p += align16(sizeof(double) * smem_doubles(N, nlat));
     w.sc      = (WalkerScalars*)p;
     w.rngbase = (uint64_t*)(p + sizeof(WalkerScalars));
@@ -626,7 +628,7 @@ __device__ __forceinline__ int nth_set_bit(uint32_t m, int rank)
 // Outputs (uniform over the warp): eo[lat], en[lat]; mo[lat]/mn[lat] = in-range
 // slot masks of imol for the old / new position.
 template <int NLAT, bool WITH_NEW>
-__device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imol, const double (*pnew)[3],
+__device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imol,
                                                     double* eo, double* en, uint32_t* mo, uint32_t* mn)
 {
     const int N = w.N, lane = lane_id();
@@ -634,8 +636,11 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
     double* q = w.q;
     int nq = 0, nc = 0;
 
-    // ---- stage 1: distance tests over imol's own list (lanes = slots), compaction into bond records
-#pragma unroll
+    // ---- stage 1: distance tests over imol's own list (lanes = slots), compaction into bond records.
+    // One copy of the code for both lattices (the loop is NOT unrolled: the kernel sits at the edge of
+    // the instruction cache); the trial position comes from the walker's move record w.mv.
+    uint32_t mo0 = 0, mo1 = 0, mn0 = 0, mn1 = 0;
+#pragma unroll 1
     for (int lat = 0; lat < NLAT; ++lat) {
         const double* P = w.pos + lat * 3 * N;
         const double* V = w.iv + lat * 3 * IVC;
@@ -648,17 +653,18 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
         const double r2o = tox * tox + toy * toy + toz * toz;
         const bool fo = has && r2o < CK.rcsq;
         const uint32_t bo = __ballot_sync(FULL, fo);
-        mo[lat] = bo;
+        if (lat == 0) mo0 = bo; else mo1 = bo;
         const int io = nq + __popc(bo & lt);
         nq += __popc(bo);
         bool fn = false; int in_ = 0; uint32_t bn = 0;
         double tnx = 0, tny = 0, tnz = 0, r2n = 0;
         if (WITH_NEW) {
-            tnx = pjx - pnew[lat][0]; tny = pjy - pnew[lat][1]; tnz = pjz - pnew[lat][2];
+            const double* pn = w.mv + lat * 6;
+            tnx = pjx - pn[0]; tny = pjy - pn[1]; tnz = pjz - pn[2];
             r2n = tnx * tnx + tny * tny + tnz * tnz;
             fn = has && r2n < CK.rcsq;
             bn = __ballot_sync(FULL, fn);
-            mn[lat] = bn;
+            if (lat == 0) mn0 = bn; else mn1 = bn;
             in_ = nq + __popc(bn & lt);
             nq += __popc(bn);
         }
@@ -680,6 +686,8 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
             w.cq[ic * 2 + 1] = (fn && in_ < QC) ? (uint16_t)in_ : NONE16;
         }
     }
+    mo[0] = mo0; mn[0] = mn0;
+    if (NLAT == 2) { mo[1] = mo1; mn[1] = mn1; }
     if (nq > QC) {                                  // results of this call are invalid; the walker is flagged
         w.sc->error |= ERR_BOND_OVERFLOW;
         nq = QC;

@@ -457,17 +457,17 @@ __device__ __noinline__ int volume_move(unsigned char* smem, const DeviceState& 
 // commit of an accepted translation: new position, own bond mask, and the reverse bits of the
 // bonds that formed / broke (rare)
 template <int NLAT>
-__device__ __forceinline__ void commit_translation(const WalkerView& w, int imol, const double (*pnew)[3],
-                                                   const uint32_t* mo, const uint32_t* mn)
+__device__ __forceinline__ void commit_translation(const WalkerView& w, int imol, const uint32_t* mo, const uint32_t* mn)
 {
     const int N = w.N, lane = lane_id();
     __syncwarp();
-#pragma unroll
+#pragma unroll 1
     for (int lat = 0; lat < NLAT; ++lat) {
         double* P = w.pos + lat * 3 * N;
-        if (lane < 3) P[lane * N + imol] = (lane == 0) ? pnew[lat][0] : (lane == 1) ? pnew[lat][1] : pnew[lat][2];
-        uint32_t changed = mo[lat] ^ mn[lat];
-        if (lane == 0) w.bmask[lat * N + imol] = mn[lat];
+        if (lane < 3) P[lane * N + imol] = w.mv[lat * 6 + lane];
+        const uint32_t mol = (lat == 0) ? mo[0] : mo[NLAT - 1], mnl = (lat == 0) ? mn[0] : mn[NLAT - 1];
+        uint32_t changed = mol ^ mnl;
+        if (lane == 0) w.bmask[lat * N + imol] = mnl;
         const int nv = w.niv[lat];
         while (changed) {
             const int s = __ffs(changed) - 1; changed &= changed - 1;
@@ -479,7 +479,7 @@ __device__ __forceinline__ void commit_translation(const WalkerView& w, int imol
             const uint32_t hit = __ballot_sync(FULL, e2 == target);
             if (hit && lane == 0) {
                 const int s2 = __ffs(hit) - 1;
-                const uint32_t bit = (mn[lat] >> s) & 1u;
+                const uint32_t bit = (mnl >> s) & 1u;
                 w.bmask[lat * N + j] = (w.bmask[lat * N + j] & ~(1u << s2)) | (bit << s2);
             }
             __syncwarp();
@@ -578,20 +578,22 @@ __global__ void __launch_bounds__(32, MW_MC_BLOCKS) k_mc_run(const __grid_consta
                     by = xa(xa(xm(MW_H(hm,2,1), sx), xm(MW_H(hm,2,2), sy)), xm(MW_H(hm,2,3), sz));
                     bz = xa(xa(xm(MW_H(hm,3,1), sx), xm(MW_H(hm,3,2), sy)), xm(MW_H(hm,3,3), sz));
                 }
-                double tv[2][3];
-                tv[0][0] = one ? x : bx; tv[0][1] = one ? y : by; tv[0][2] = one ? z : bz;
-                tv[1][0] = one ? bx : x; tv[1][1] = one ? by : y; tv[1][2] = one ? bz : z;
-                double pnew[2][3];
+                // the move record: trial position and displacement of imol in every lattice (shared memory,
+                // every lane stores the same values: "uniform registers in shared memory")
+                __syncwarp();
 #pragma unroll
                 for (int lat = 0; lat < NLAT; ++lat) {
+                    const bool act = (lat == 0) == one;            // lattice `lat` is the active one
+                    const double tx = act ? x : bx, ty = act ? y : by, tz = act ? z : bz;
                     const double* P = w.pos + lat * 3 * N;
-                    pnew[lat][0] = xa(P[imol], tv[lat][0]);
-                    pnew[lat][1] = xa(P[N + imol], tv[lat][1]);
-                    pnew[lat][2] = xa(P[2 * N + imol], tv[lat][2]);
+                    double* m = w.mv + lat * 6;
+                    m[0] = xa(P[imol], tx); m[1] = xa(P[N + imol], ty); m[2] = xa(P[2 * N + imol], tz);
+                    m[3] = tx; m[4] = ty; m[5] = tz;
                 }
+                __syncwarp();
                 double eo[2] = {0.0, 0.0}, en[2] = {0.0, 0.0};
                 uint32_t mo[2] = {0, 0}, mn[2] = {0, 0};
-                local_energies_warp<NLAT, true>(w, imol, pnew, eo, en, mo, mn);
+                local_energies_warp<NLAT, true>(w, imol, eo, en, mo, mn);
 
                 // model_energy bookkeeping exactly as :1013-1016, :1087-1090
                 const double Eb0 = sc->E[0], Eb1 = sc->E[1];
@@ -642,16 +644,14 @@ __global__ void __launch_bounds__(32, MW_MC_BLOCKS) k_mc_run(const __grid_consta
                     if (dmu > sc->max_dmu) sc->max_dmu = dmu;
                     sc->E[0] = Ea0;
                     if (NLAT == 2) { sc->E[1] = Ea1; sc->mu = mu_acc; }
-                    commit_translation<NLAT>(w, imol, pnew, mo, mn);
+                    commit_translation<NLAT>(w, imol, mo, mn);
                 } else {
                     // reject: the reference restores by (x+t)-t, not by copy (mc_moves.F90:1186)
                     __syncwarp();
-#pragma unroll
-                    for (int lat = 0; lat < NLAT; ++lat) {
-                        double* P = w.pos + lat * 3 * N;
-                        const double pn = (lane == 0) ? pnew[lat][0] : (lane == 1) ? pnew[lat][1] : pnew[lat][2];
-                        const double tt = (lane == 0) ? tv[lat][0] : (lane == 1) ? tv[lat][1] : tv[lat][2];
-                        if (lane < 3) P[lane * N + imol] = xs(pn, tt);
+                    if (lane < 3 * NLAT) {
+                        const int lat = (lane >= 3) ? 1 : 0, d = lane - 3 * lat;
+                        const double* m = w.mv + lat * 6;
+                        w.pos[(lat * 3 + d) * N + imol] = xs(m[d], m[3 + d]);
                     }
                     if (NLAT == 2) sc->mu = mu_rej;
                     __syncwarp();

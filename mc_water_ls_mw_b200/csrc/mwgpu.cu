@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
         for (int i = i0; i < i1; ++i) {
             double eo[2] = {0, 0}, en[2] = {0, 0};
             uint32_t mo[2], mn[2];
-            local_energies_warp<NLAT, false>(w, i, nullptr, eo, en, mo, mn);
+            local_energies_warp<NLAT, false>(w, i, eo, en, mo, mn);
             if (lane == 0) a.out[i - i0] = (a.lat == 0) ? eo[0] : eo[1];
         }
         break;
