@@ -69,7 +69,17 @@ module mwgpu
      integer(c_int)     :: my_start_bin,my_end_bin
      integer(c_int)     :: walker_in_window
      integer(c_int)     :: error
+     integer(c_int)     :: wl_invt_active
   end type mwgpu_walker_state
+
+  ! struct mwgpu_therm_row: the values of one row of <seed>RRR_therm.dat (main.f90:200-223)
+  type,bind(C) :: mwgpu_therm_row
+     integer(c_int64_t) :: icyc,ls
+     real(c_double)     :: model_energy(2)
+     real(c_double)     :: ls_mu
+     real(c_double)     :: volume(2)
+     real(c_double)     :: hmatrix1(9)
+  end type mwgpu_therm_row
 
   ! struct mwgpu_flat_params (userparams.f90:33-36)
   type,bind(C) :: mwgpu_flat_params
@@ -268,6 +278,32 @@ module mwgpu
        real(c_double),intent(out) :: deltaG
        real(c_double),intent(out) :: normP(*)
      end function mwgpu_mc_deltag_from_hist
+
+     ! mc_checkpoint_load (mc_moves.F90:403-501) + restart refresh (:842-862) for one uploaded walker
+     integer(c_int) function mwgpu_mc_restore(ctx,walker,mc_cycle_num,mc_max_trans,mc_dv_max,wl_factor, &
+          wl_invt_active,ls,histogram,weight,unbiased_hist,hmatrix,ref_ljr,ljr) bind(C,name='mwgpu_mc_restore')
+       import :: c_int,c_ptr,c_double
+       type(c_ptr),value         :: ctx
+       integer(c_int),value      :: walker,mc_cycle_num,wl_invt_active,ls
+       real(c_double),value      :: mc_max_trans,mc_dv_max,wl_factor
+       real(c_double),intent(in) :: histogram(*),weight(*),unbiased_hist(*)
+       real(c_double),intent(in) :: hmatrix(*),ref_ljr(*),ljr(*)
+     end function mwgpu_mc_restore
+
+     ! therm rows (main.f90:200-223) recorded by the walker kernel
+     integer(c_int) function mwgpu_mc_set_therm(ctx,file_output_int,capacity) bind(C,name='mwgpu_mc_set_therm')
+       import :: c_int,c_ptr
+       type(c_ptr),value    :: ctx
+       integer(c_int),value :: file_output_int,capacity
+     end function mwgpu_mc_set_therm
+
+     integer(c_int) function mwgpu_mc_get_therm(ctx,walker,rows,max_rows,nrows,ndropped) bind(C,name='mwgpu_mc_get_therm')
+       import :: c_int,c_ptr,mwgpu_therm_row
+       type(c_ptr),value                 :: ctx
+       integer(c_int),value              :: walker,max_rows
+       type(mwgpu_therm_row),intent(out) :: rows(*)
+       integer(c_int),intent(out)        :: nrows,ndropped
+     end function mwgpu_mc_get_therm
 
      !---------------- comms ----------------!
      ! comms_join_uhist / comms_join_eta (comms_mpi.f90:299-375, :377-459)

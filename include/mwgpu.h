@@ -87,6 +87,7 @@ typedef struct mwgpu_walker_state {
     int    my_start_bin, my_end_bin;
     int    walker_in_window;
     int    error;              /* MWGPU_ERR_* bits */
+    int    wl_invt_active;     /* 1/t increment active (mc_moves.F90:87; part of the checkpoint, :366) */
 } mwgpu_walker_state;
 
 enum {
@@ -219,6 +220,32 @@ int  mwgpu_mc_deltag_from_hist(mwgpu_ctx *ctx, double *deltaG_kT, double *normP)
  * 'dd' run (walker = window, rank order; NCCL all-gather when the windows span several GPUs) */
 int  mwgpu_comms_join_uhist(mwgpu_ctx *ctx, int overlap, double *joined /* nbins */);
 int  mwgpu_comms_join_eta(mwgpu_ctx *ctx, int overlap, double *joined /* nbins */);
+
+/* ---- restart and therm rows ----------------------------------- */
+/* State effects of mc_checkpoint_load (mc_moves.F90:403-501: cycle number, step sizes, wl_factor, bins,
+ * comms_set_histogram, sumhist, firstcycle, cell, reference positions, positions, active lattice) followed
+ * by the refresh of mc_init (:842-862: volumes, reciprocal cells, image vectors, chain synchronisation,
+ * energies, ls_mu) for one walker of a context that went through the normal start-up (upload of the input
+ * configuration, energy_init, mc_init).  As in the reference, ref_hmatrix stays the input cell and the
+ * neighbour lists are NOT rebuilt here (they are refreshed at the next list_update_int cycle). */
+int  mwgpu_mc_restore(mwgpu_ctx *ctx, int walker, int mc_cycle_num, double mc_max_trans, double mc_dv_max,
+                      double wl_factor, int wl_invt_active, int ls,
+                      const double *histogram, const double *weight, const double *unbiased_hist,
+                      const double *hmatrix, const double *ref_ljr, const double *ljr);
+/* the values of one row of <seed>RRR_therm.dat (main.f90:200-223), recorded by the walker kernel */
+typedef struct mwgpu_therm_row {
+    int64_t icyc;
+    int64_t ls;
+    double  model_energy[2];   /* Hartree */
+    double  ls_mu;
+    double  volume[2];         /* Bohr^3 */
+    double  hmatrix1[9];       /* hmatrix(:,:,1), Bohr (single-lattice rows print a,b,c,alpha,beta,gamma) */
+} mwgpu_therm_row;
+/* record a row every file_output_int cycles, at most `capacity` rows per walker between two drains
+ * (0, 0 switches recording off) */
+int  mwgpu_mc_set_therm(mwgpu_ctx *ctx, int file_output_int, int capacity);
+/* drain the rows of one walker; *ndropped = rows lost because the ring was full */
+int  mwgpu_mc_get_therm(mwgpu_ctx *ctx, int walker, mwgpu_therm_row *rows, int max_rows, int *nrows, int *ndropped);
 
 /* ---- measurement helpers ------------------------------------------------------------ */
 /* elapsed milliseconds of the last mwgpu_mc_run / mwgpu_compute_model_energy_all kernel

@@ -52,6 +52,7 @@ class WalkerState(C.Structure):
         ("rng_index", C.c_int64), ("ls", C.c_int), ("mc_cycle_num", C.c_int),
         ("accepted", C.c_int * 3), ("attempted", C.c_int * 3),
         ("my_start_bin", C.c_int), ("my_end_bin", C.c_int), ("walker_in_window", C.c_int), ("error", C.c_int),
+        ("wl_invt_active", C.c_int),
     ]
 
 
@@ -66,6 +67,13 @@ class FlatReport(C.Structure):
 
     _fields_ = [("checked", C.c_int), ("hist_reset", C.c_int), ("flat", C.c_int), ("invt_switched", C.c_int),
                 ("mean", C.c_double), ("max_pct", C.c_double), ("min_pct", C.c_double), ("wl_factor", C.c_double)]
+
+
+class ThermRow(C.Structure):
+    """mwgpu_therm_row (include/mwgpu.h): the values of one row of <seed>RRR_therm.dat."""
+
+    _fields_ = [("icyc", C.c_int64), ("ls", C.c_int64), ("model_energy", C.c_double * 2), ("ls_mu", C.c_double),
+                ("volume", C.c_double * 2), ("hmatrix1", C.c_double * 9)]
 
 
 # every symbol include/mwgpu.h declares: name -> (restype, argtypes)
@@ -115,6 +123,9 @@ SYMBOLS = {
     "mwgpu_mc_deltag_from_hist": (_i, [_vp, _dp, _dp]),
     "mwgpu_comms_join_uhist": (_i, [_vp, _i, _dp]),
     "mwgpu_comms_join_eta": (_i, [_vp, _i, _dp]),
+    "mwgpu_mc_restore": (_i, [_vp, _i, _i, _d, _d, _d, _i, _i, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "mwgpu_mc_set_therm": (_i, [_vp, _i, _i]),
+    "mwgpu_mc_get_therm": (_i, [_vp, _i, C.POINTER(ThermRow), _i, _ip, _ip]),
     "mwgpu_timer_start": (_i, [_vp]),
     "mwgpu_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
     "mwgpu_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),

@@ -59,7 +59,13 @@ struct DeviceState {
     double* hinc;       // [NB]  av_binwidth/binwidth(k): histogram increment of bin k (mc_moves.F90:1621)
     const double* fifo; // host-supplied random numbers (walker 0 only)
     unsigned long long fifo_len;
+    // therm rows (main.f90:200-223): what the reference writes every file_output_int cycles, recorded by
+    // the walker kernel so that a launch can span many output intervals
+    double* therm;      // [W][therm_cap][THERM_ROW]
+    int*    therm_n;    // [W] rows recorded since the last drain (may exceed therm_cap: the excess was dropped)
+    int     therm_int, therm_cap;
 };
+constexpr int THERM_ROW = 16;   // icyc, ls, E(1:2), ls_mu, volume(1:2), hmatrix(:,:,1)
 
 // ---------------------------------------------------------------- staging
 __device__ __forceinline__ void load_walker(const DeviceState& S, int wi, const WalkerView& w)
@@ -709,6 +715,26 @@ __global__ void __launch_bounds__(32, MW_MC_BLOCKS) k_mc_run(const __grid_consta
             double a = sc->avgE[lat] + sc->E[lat];
             if (p.npt) a = a + p.pressure * sc->vol[lat];
             sc->avgE[lat] = a;
+        }
+        if (S.therm_int > 0 && cycle % S.therm_int == 0) {     // main.f90:200-223 (values only; formatted by the host)
+            const int n = S.therm_n[wi];
+            __syncwarp();
+            if (n < S.therm_cap && lane < THERM_ROW) {
+                double v;
+                switch (lane) {
+                case 0: v = (double)cycle; break;
+                case 1: v = (double)sc->ls; break;
+                case 2: v = sc->E[0]; break;
+                case 3: v = sc->E[1]; break;
+                case 4: v = sc->mu; break;
+                case 5: v = sc->vol[0]; break;
+                case 6: v = sc->vol[1]; break;
+                default: v = w.cell[lane - 7]; break;
+                }
+                S.therm[((size_t)wi * S.therm_cap + n) * THERM_ROW + lane] = v;
+            }
+            __syncwarp();
+            if (lane == 0) S.therm_n[wi] = n + 1;
         }
     }
     const uint64_t idx = *w.rngbase + (uint64_t)rng.pos;

@@ -152,7 +152,7 @@ extern "C" void mwgpu_destroy(mwgpu_ctx* c)
     void* ptrs[] = {S.pos, S.ref, S.cell, S.recip, S.refcell, S.iv, S.niv, S.list, S.nn, S.scal,
                     S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.transcount, S.mubin,
                     S.binwidth, S.ginv, S.hinc, c->stage, c->out, c->iout, c->delta, c->fifo,
-                    c->book, c->skip, c->gather};
+                    c->book, c->skip, c->gather, S.therm, S.therm_n};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -228,7 +228,7 @@ extern "C" int mwgpu_last_kernel_ms(mwgpu_ctx* c, float* ms)
 // layout conversion kernels: reference AoS ljr(3,1,N,nlat[,W])  <->  device SoA [W][nlat][3][N]
 // ------------------------------------------------------------------------------------------------
 __global__ void k_unpack(DeviceState S, const double* __restrict__ ljr, const double* __restrict__ ref,
-                         const double* __restrict__ hm, int w0, int nw, int bcast)
+                         const double* __restrict__ hm, int w0, int nw, int bcast, int keep_refcell)
 {
     const int N = S.N, L = S.nlat;
     const size_t per = (size_t)L * N;
@@ -247,7 +247,7 @@ __global__ void k_unpack(DeviceState S, const double* __restrict__ ljr, const do
         const int rem = (int)(t % (L * 9));
         const double v = hm[(bcast ? 0 : (size_t)w * L * 9) + rem];
         S.cell[(size_t)(w0 + w) * L * 9 + rem] = v;
-        S.refcell[(size_t)(w0 + w) * L * 9 + rem] = v;
+        if (!keep_refcell) S.refcell[(size_t)(w0 + w) * L * 9 + rem] = v;     // ref_hmatrix = hmatrix at input only
     }
 }
 
@@ -273,7 +273,8 @@ __global__ void k_pack(DeviceState S, double* __restrict__ ljr, double* __restri
     }
 }
 
-static int upload_impl(mwgpu_ctx* c, int w0, int nw, int bcast, const double* ljr, const double* ref, const double* hm)
+static int upload_impl(mwgpu_ctx* c, int w0, int nw, int bcast, const double* ljr, const double* ref, const double* hm,
+                       bool restart = false)
 {
     if (!ljr || !hm) return fail("mwgpu_upload: ljr and hmatrix must not be NULL");
     if (!ref) ref = ljr;                               // init.f90:103: ref_ljr = ljr
@@ -287,9 +288,9 @@ static int upload_impl(mwgpu_ctx* c, int w0, int nw, int bcast, const double* lj
     CUDA_TRY(cudaMemcpyAsync(d_hm, hm, nh * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const size_t threads = (size_t)nw * c->nlat * c->N;
     const int blk = 256;
-    k_unpack<<<(unsigned)((threads + blk - 1) / blk), blk, 0, c->stream>>>(c->S, d_ljr, d_ref, d_hm, w0, nw, bcast);
+    k_unpack<<<(unsigned)((threads + blk - 1) / blk), blk, 0, c->stream>>>(c->S, d_ljr, d_ref, d_hm, w0, nw, bcast, restart ? 1 : 0);
     c->launches++;
-    c->energy_ready = false;
+    if (!restart) c->energy_ready = false;
     return finish(c, true);
 }
 
@@ -346,6 +347,7 @@ enum WalkerOp : int {
     OP_LOCAL_ALL,         // for every molecule
     OP_MONITOR,           // state effects of mc_monitor_stats
     OP_CHAIN_SYNC,        // mc_check_chain_synchronisation
+    OP_RESTART,           // refresh after mc_checkpoint_load (mc_moves.F90:842-862)
 };
 
 struct OpArgs {
@@ -439,6 +441,18 @@ __global__ void __launch_bounds__(32) k_walker_op(const __grid_constant__ Device
         sc->max_dmu = 0.0; sc->min_dmu = F_HUGE;
         break;
     }
+    case OP_RESTART:
+        // mc_moves.F90:842-856: volume, recip, image vectors of the loaded cells -- NOT the neighbour lists
+        // (the reference keeps the lists it built for the input configuration until the next refresh) --
+        // then the chain synchronisation and the energies
+#pragma unroll
+        for (int lat = 0; lat < NLAT; ++lat) {
+            sc->vol[lat] = cell_volume(w, lat);
+            refresh_recip(smem, N, NLAT, lat);
+            err |= compute_ivects_warp(smem, N, NLAT, lat);
+        }
+        if (NLAT == 1) sc->E[0] = full_energy_warp(smem, N, NLAT, 0);
+        // fall through
     case OP_CHAIN_SYNC: {
         // mc_moves.F90:2217-2416 (two lattices only)
         if (NLAT == 2) {
@@ -977,7 +991,7 @@ static void fill_state(const WalkerScalars& s, mwgpu_walker_state* o)
     o->accepted[0] = s.acc_r; o->accepted[1] = s.acc_v; o->accepted[2] = s.acc_s;
     o->attempted[0] = s.att_r; o->attempted[1] = s.att_v; o->attempted[2] = s.att_s;
     o->my_start_bin = s.start_bin; o->my_end_bin = s.end_bin;
-    o->walker_in_window = s.in_window; o->error = s.error;
+    o->walker_in_window = s.in_window; o->error = s.error; o->wl_invt_active = s.wl_invt_active;
 }
 
 extern "C" int mwgpu_mc_get_state(mwgpu_ctx* c, int walker, mwgpu_walker_state* out)
@@ -1091,6 +1105,93 @@ extern "C" int mwgpu_mc_chain_sync(mwgpu_ctx* c)
     if (c->nlat != 2) return 0;
     if (int rc = launch_op(c, make_args(c, OP_CHAIN_SYNC, 0, -1, 0, nullptr), c->W)) return rc;
     return collect_errors(c, "mwgpu_mc_chain_sync");
+}
+
+// ------------------------------------------------------------------------------------------------
+// restart and therm rows
+// ------------------------------------------------------------------------------------------------
+// State effects of mc_checkpoint_load (mc_moves.F90:403-501) + the refresh of mc_init (:842-862) for one walker.
+// ref_hmatrix and the neighbour lists stay what the start-up sequence made them (the reference does not touch
+// them on a restart either).
+extern "C" int mwgpu_mc_restore(mwgpu_ctx* c, int walker, int mc_cycle_num, double mc_max_trans, double mc_dv_max,
+                                double wl_factor, int wl_invt_active, int ls,
+                                const double* histogram, const double* weight, const double* unbiased_hist,
+                                const double* hmatrix, const double* ref_ljr, const double* ljr)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_mc_restore: call mwgpu_mc_init first");
+    if (!histogram || !weight) return fail("mwgpu_mc_restore: histogram / weight is NULL");
+    if (!hmatrix || !ref_ljr || !ljr) return fail("mwgpu_mc_restore: hmatrix / ref_ljr / ljr is NULL");
+    if (int rc = upload_impl(c, walker, 1, 0, ljr, ref_ljr, hmatrix, true)) return rc;                 // :479-489
+    if (ls < 1 || ls > c->nlat) return fail("mwgpu_mc_restore: ls out of range");
+    if (c->user.samplerun && !unbiased_hist) return fail("mwgpu_mc_restore: a sample run needs unbiased_hist");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const size_t off = (size_t)walker * c->NB, nbytes = sizeof(double) * c->NB;
+    WalkerScalars s;
+    CUDA_TRY(cudaMemcpy(&s, c->S.scal + walker, sizeof(s), cudaMemcpyDeviceToHost));
+    s.cycle = mc_cycle_num; s.max_trans = mc_max_trans; s.dv_max = mc_dv_max;          // :449-455
+    s.wl_factor = wl_factor; s.wl_invt_active = wl_invt_active ? 1 : 0; s.ls = ls;
+    double sum = 0.0;
+    for (int k = 0; k < c->NB; ++k) sum = sum + histogram[k];
+    s.sumhist = sum;                                                                    // :470
+    if (wl_factor < c->P.orig_wl_factor) s.firstcycle = 0;                              // :473-476
+    s.wmin_zero = 0;
+    CUDA_TRY(cudaMemcpy(c->S.scal + walker, &s, sizeof(s), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->S.hist + off, histogram, nbytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->S.weight + off, weight, nbytes, cudaMemcpyHostToDevice));
+    if (c->user.samplerun) CUDA_TRY(cudaMemcpy(c->S.uhist + off, unbiased_hist, nbytes, cudaMemcpyHostToDevice));
+    if (!c->user.dd) {                                                                  // :462-466 comms_set_(u)histogram
+        CUDA_TRY(cudaMemcpy(c->S.hbase + off, histogram, nbytes, cudaMemcpyHostToDevice));
+        if (c->user.samplerun) CUDA_TRY(cudaMemcpy(c->S.ubase + off, unbiased_hist, nbytes, cudaMemcpyHostToDevice));
+    }
+    if (int rc = launch_op(c, make_args(c, OP_RESTART, walker, -1, 0, nullptr), 1)) return rc;
+    return collect_errors(c, "mwgpu_mc_restore");
+}
+
+extern "C" int mwgpu_mc_set_therm(mwgpu_ctx* c, int file_output_int, int capacity)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (file_output_int < 0 || capacity < 0) return fail("mwgpu_mc_set_therm: negative argument");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->S.therm) cudaFree(c->S.therm);
+    if (c->S.therm_n) cudaFree(c->S.therm_n);
+    c->S.therm = nullptr; c->S.therm_n = nullptr; c->S.therm_int = 0; c->S.therm_cap = 0;
+    if (file_output_int == 0 || capacity == 0) return 0;
+    if (int rc = dalloc(&c->S.therm, (size_t)c->W * capacity * THERM_ROW)) return rc;
+    if (int rc = dalloc(&c->S.therm_n, (size_t)c->W)) return rc;
+    c->S.therm_int = file_output_int; c->S.therm_cap = capacity;
+    return 0;
+}
+
+extern "C" int mwgpu_mc_get_therm(mwgpu_ctx* c, int walker, mwgpu_therm_row* rows, int max_rows, int* nrows, int* ndropped)
+{
+    if (int rc = check_ctx(c, walker, false)) return rc;
+    if (!nrows) return fail("mwgpu_mc_get_therm: nrows is NULL");
+    *nrows = 0; if (ndropped) *ndropped = 0;
+    if (!c->S.therm) return 0;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    int n = 0;
+    CUDA_TRY(cudaMemcpy(&n, c->S.therm_n + walker, sizeof(int), cudaMemcpyDeviceToHost));
+    const int have = n < c->S.therm_cap ? n : c->S.therm_cap;
+    if (have > max_rows) return fail("mwgpu_mc_get_therm: rows buffer too small");
+    if (have > 0 && !rows) return fail("mwgpu_mc_get_therm: rows is NULL");
+    static_assert(sizeof(mwgpu_therm_row) == sizeof(double) * THERM_ROW, "therm row layout");
+    std::vector<double> tmp((size_t)have * THERM_ROW);
+    if (have > 0)
+        CUDA_TRY(cudaMemcpy(tmp.data(), c->S.therm + (size_t)walker * c->S.therm_cap * THERM_ROW,
+                            sizeof(double) * have * THERM_ROW, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < have; ++r) {
+        const double* t = tmp.data() + (size_t)r * THERM_ROW;
+        mwgpu_therm_row& o = rows[r];
+        o.icyc = (int64_t)t[0]; o.ls = (int64_t)t[1];
+        o.model_energy[0] = t[2]; o.model_energy[1] = t[3]; o.ls_mu = t[4];
+        o.volume[0] = t[5]; o.volume[1] = t[6];
+        for (int k = 0; k < 9; ++k) o.hmatrix1[k] = t[7 + k];
+    }
+    const int zero = 0;
+    CUDA_TRY(cudaMemcpy(c->S.therm_n + walker, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    *nrows = have; if (ndropped) *ndropped = n - have;
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -279,3 +279,122 @@ def write_eta_weights(path: str, wl_factor: float, mu_bin: np.ndarray, weight: n
         fh.write("#Current energy increment = " + s.rjust(20) + "\n")
         for a, b in zip(mu_bin, weight):
             fh.write(f"  {a: .17g}       {b: .17g}     \n")
+
+
+# --------------------------------------------------------------------------------------------------
+# output formats of the host driver that depend on hot-path state
+# --------------------------------------------------------------------------------------------------
+HART_TO_EV = 27.211396181          # constants.f90:47
+WATER_MASS = 18.0158               # constants.f90:52
+AUD_TO_KGM3 = 1.120587168e4        # constants.f90:63
+
+
+def fortran_e(x: float, w: int, d: int) -> str:
+    """Fortran ``Ew.d`` edit descriptor (0.ddddddE+xx form, as gfortran / ifort print it)."""
+    x = float(x)
+    if x != x or x in (float("inf"), float("-inf")):
+        return ("NaN" if x != x else ("Infinity" if x > 0 else "-Infinity")).rjust(w)
+    if x == 0.0:
+        body = "0." + "0" * d + "E+00"
+    else:
+        m, e = f"{abs(x):.{d - 1}E}".split("E")       # d significant digits: D.ddd E exp
+        e = int(e) + 1
+        digits = m.replace(".", "")
+        body = "0." + digits + "E" + ("+" if e >= 0 else "-") + f"{abs(e):02d}"
+    s = ("-" if x < 0 else "") + body
+    if len(s) > w and s.startswith("0."):
+        s = s[1:]
+    elif len(s) > w and s.startswith("-0."):
+        s = "-" + s[2:]
+    return s.rjust(w) if len(s) <= w else "*" * w
+
+
+def fortran_f(x: float, w: int, d: int) -> str:
+    s = f"{float(x):.{d}f}"
+    return s.rjust(w) if len(s) <= w else "*" * w
+
+
+def hmatrix_to_abc(h: np.ndarray):
+    """util_hmatrix_to_abc (util.f90:79-106): h = hmatrix(:,:,1) flattened column-major (Bohr)."""
+    a, b, c = np.asarray(h[0:3], float), np.asarray(h[3:6], float), np.asarray(h[6:9], float)
+    la, lb, lc = np.sqrt(a @ a), np.sqrt(b @ b), np.sqrt(c @ c)
+    alpha = np.degrees(np.arccos((a @ c) / (la * lc)))
+    beta = np.degrees(np.arccos((b @ c) / (lb * lc)))
+    gamma = np.degrees(np.arccos((a @ b) / (la * lb)))
+    return la, lb, lc, alpha, beta, gamma
+
+
+def format_therm_row(row, p: UserParams) -> str:
+    """One line of ``<seed>RRR_therm.dat`` (main.f90:200-223) from the values the walker kernel recorded
+    (``mwgpu_therm_row`` / any object with icyc, ls, model_energy, ls_mu, volume, hmatrix1)."""
+    icyc, ls = int(row.icyc), int(row.ls)
+    E = [float(row.model_energy[0]), float(row.model_energy[1])]
+    V = [float(row.volume[0]), float(row.volume[1])]
+    b3 = BOHR_TO_ANG ** 3
+    if p.num_lattices == 1:                                         # '(I8,E15.6,5x,F15.6,6F15.6)'
+        la, lb, lc, al, be, ga = hmatrix_to_abc(np.array(list(row.hmatrix1)))
+        return (f"{icyc:8d}" + fortran_e(E[0] * HART_TO_EV, 15, 6) + " " * 5 + fortran_f(V[0] * b3, 15, 6)
+                + "".join(fortran_f(v, 15, 6) for v in (la * BOHR_TO_ANG, lb * BOHR_TO_ANG, lc * BOHR_TO_ANG, al, be, ga)))
+    head = f"{icyc:8d}" + fortran_e(E[ls - 1] * HART_TO_EV, 15, 6) + " " * 5
+    if p.wl_factor < np.finfo(np.float64).tiny or p.samplerun:       # '(I8,E15.6,5x,3F15.6,1x,I1)'
+        return head + fortran_f(float(row.ls_mu), 15, 6) + fortran_f(V[0] * b3, 15, 6) + fortran_f(V[1] * b3, 15, 6) + f" {ls:1d}"
+    density = p.nwater * WATER_MASS / V[ls - 1]                      # '(I8,E15.6,5x,2F15.6,1x,I1)'
+    return head + fortran_f(float(row.ls_mu), 15, 6) + fortran_f(density * AUD_TO_KGM3, 15, 6) + f" {ls:1d}"
+
+
+def _rec(payload: bytes) -> bytes:
+    """One record of a Fortran sequential unformatted file (4-byte little-endian length markers: the
+    gfortran / ifort default; the reference leaves the record format to the compiler)."""
+    n = struct.pack("<i", len(payload))
+    return n + payload + n
+
+
+def write_checkpoint(path: str, rec: dict, nbins: int, samplerun: bool) -> None:
+    """``checkpointRRR.dat.N`` exactly as mc_checkpoint_write (mc_moves.F90:324-388) writes it: records
+    nwater | mc_cycle_num | mc_max_trans,mc_dv_max | wl_factor | histogram | weight | wl_invt_active |
+    [unbiased_hist] | hmatrix | ref_ljr | ljr | ls.  Arrays are in the reference's column-major layouts, which is
+    what ``WalkerBatch.checkpoint_record`` returns (hmatrix[nlat,9], ljr[nlat,nwater,3] C-order == Fortran
+    (3,3,nlat) / (3,1,nwater,nlat))."""
+    f8 = lambda a: np.ascontiguousarray(a, dtype="<f8").tobytes()
+    out = [_rec(struct.pack("<i", int(rec["nwater"]))), _rec(struct.pack("<i", int(rec["mc_cycle_num"]))),
+           _rec(struct.pack("<dd", float(rec["mc_max_trans"]), float(rec["mc_dv_max"]))),
+           _rec(struct.pack("<d", float(rec["wl_factor"]))),
+           _rec(f8(np.asarray(rec["histogram"])[:nbins])), _rec(f8(np.asarray(rec["weight"])[:nbins])),
+           _rec(struct.pack("<i", 1 if rec["wl_invt_active"] else 0))]          # default LOGICAL: 4 bytes
+    if samplerun:
+        out.append(_rec(f8(np.asarray(rec["unbiased_hist"])[:nbins])))
+    out += [_rec(f8(rec["hmatrix"])), _rec(f8(rec["ref_ljr"])), _rec(f8(rec["ljr"])), _rec(struct.pack("<i", int(rec["ls"])))]
+    with open(path, "wb") as fh:
+        fh.write(b"".join(out))
+
+
+def read_checkpoint(path: str, nbins: int, num_lattices: int, samplerun: bool) -> dict:
+    """Inverse of write_checkpoint = what mc_checkpoint_load (mc_moves.F90:390-501) reads."""
+    data = open(path, "rb").read()
+    pos = 0
+
+    def rec():
+        nonlocal pos
+        (n,) = struct.unpack_from("<i", data, pos)
+        payload = data[pos + 4: pos + 4 + n]
+        (m,) = struct.unpack_from("<i", data, pos + 4 + n)
+        if m != n:
+            raise ValueError("corrupt checkpoint record")
+        pos += 8 + n
+        return payload
+
+    out = {}
+    (out["nwater"],) = struct.unpack("<i", rec())
+    (out["mc_cycle_num"],) = struct.unpack("<i", rec())
+    out["mc_max_trans"], out["mc_dv_max"] = struct.unpack("<dd", rec())
+    (out["wl_factor"],) = struct.unpack("<d", rec())
+    out["histogram"] = np.frombuffer(rec(), dtype="<f8").copy()
+    out["weight"] = np.frombuffer(rec(), dtype="<f8").copy()
+    out["wl_invt_active"] = bool(struct.unpack("<i", rec())[0])
+    out["unbiased_hist"] = np.frombuffer(rec(), dtype="<f8").copy() if samplerun else np.zeros(nbins)
+    n = out["nwater"]
+    out["hmatrix"] = np.frombuffer(rec(), dtype="<f8").reshape(num_lattices, 9).copy()
+    out["ref_ljr"] = np.frombuffer(rec(), dtype="<f8").reshape(num_lattices, n, 3).copy()
+    out["ljr"] = np.frombuffer(rec(), dtype="<f8").reshape(num_lattices, n, 3).copy()
+    out["ls"] = struct.unpack("<i", rec())[0] if pos < len(data) else 1         # 'read(...,end=10) ls'
+    return out

@@ -20,7 +20,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import FlatParams, FlatReport, McParams, MwgpuError, WalkerState, check, lib
+from ._lib import FlatParams, FlatReport, McParams, MwgpuError, ThermRow, WalkerState, check, lib
 
 
 def _dp(a: Optional[np.ndarray]):
@@ -258,6 +258,39 @@ class WalkerBatch:
         normP = np.zeros(self.nbins, dtype=np.float64)
         check(self.L.mwgpu_mc_deltag_from_hist(self.h, C.byref(dG), _dp(normP)))
         return float(dG.value), normP
+
+    # ------------------------------------------------------------------ restart, therm rows
+    def mc_restore(self, walker: int, rec: dict) -> None:
+        """mc_checkpoint_load (mc_moves.F90:403-501) + the refresh of mc_init (:842-862) for one walker of a batch
+        that went through the normal start-up; ``rec`` = decks.read_checkpoint(...) / checkpoint_record()."""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        h, w, u = f(rec["histogram"]), f(rec["weight"]), f(rec["unbiased_hist"])
+        hm, ref, ljr = f(rec["hmatrix"]), f(rec["ref_ljr"]), f(rec["ljr"])
+        check(self.L.mwgpu_mc_restore(self.h, int(walker), int(rec["mc_cycle_num"]), float(rec["mc_max_trans"]),
+                                      float(rec["mc_dv_max"]), float(rec["wl_factor"]), int(rec["wl_invt_active"]),
+                                      int(rec["ls"]), _dp(h), _dp(w), _dp(u), _dp(hm), _dp(ref), _dp(ljr)))
+
+    def checkpoint_record(self, walker: int = 0) -> dict:
+        """Everything mc_checkpoint_write (mc_moves.F90:324-388) puts into checkpointRRR.dat.N for one walker."""
+        s = self.state(walker)
+        w, h, u = self.bins(walker)
+        ljr, ref, hm = self.download(walker)
+        return dict(nwater=self.nwater, mc_cycle_num=s.mc_cycle_num, mc_max_trans=s.mc_max_trans, mc_dv_max=s.mc_dv_max,
+                    wl_factor=s.wl_factor, histogram=h, weight=w, wl_invt_active=bool(s.wl_invt_active),
+                    unbiased_hist=u, hmatrix=hm, ref_ljr=ref, ljr=ljr, ls=s.ls)
+
+    def set_therm(self, file_output_int: int, capacity: int = 32) -> None:
+        """Record the values of a therm row (main.f90:200-223) every ``file_output_int`` cycles in the kernel."""
+        check(self.L.mwgpu_mc_set_therm(self.h, int(file_output_int), int(capacity)))
+        self._therm_cap = int(capacity)
+
+    def therm(self, walker: int = 0):
+        """Drain the recorded rows of one walker: (list of ThermRow, number of rows dropped)."""
+        cap = getattr(self, "_therm_cap", 0)
+        rows = (ThermRow * max(cap, 1))()
+        n = C.c_int(0); nd = C.c_int(0)
+        check(self.L.mwgpu_mc_get_therm(self.h, int(walker), rows, max(cap, 1), C.byref(n), C.byref(nd)))
+        return [rows[i] for i in range(n.value)], nd.value
 
     def comms_init_nccl(self, nranks: int, rank: int, unique_id: bytes) -> None:
         buf = C.create_string_buffer(unique_id, 128)

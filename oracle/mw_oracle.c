@@ -1118,6 +1118,42 @@ void orc_allreduce_bins(orc_system **w, int n)
         allreduce_one(w, n, nb, offsetof(orc_system, unbiased_hist), offsetof(orc_system, uhist_last_sync));
 }
 
+/* mc_moves.F90:403-501 (mc_checkpoint_load) followed by :842-862 (restart branch of mc_init) */
+void orc_mc_restore(orc_system *s, int mc_cycle_num, double mc_max_trans, double mc_dv_max, double wl_factor,
+                    int wl_invt_active, int ls, const double *histogram, const double *weight,
+                    const double *unbiased_hist, const double *hmatrix, const double *ref_ljr, const double *ljr)
+{
+    const int nb = s->p.nbins, n3 = 3 * s->nwater * s->nlat;
+    s->mc_cycle_num = mc_cycle_num;
+    s->p.mc_max_trans = mc_max_trans; s->p.mc_dv_max = mc_dv_max;
+    s->wl_factor = wl_factor;
+    memcpy(s->histogram, histogram, sizeof(double) * nb);
+    memcpy(s->weight, weight, sizeof(double) * nb);
+    s->wl_invt_active = wl_invt_active ? 1 : 0;
+    if (s->p.samplerun) memcpy(s->unbiased_hist, unbiased_hist, sizeof(double) * nb);
+    if (!s->p.dd) {                                   /* comms_set_histogram / comms_set_uhistogram */
+        memcpy(s->hist_last_sync, s->histogram, sizeof(double) * nb);
+        if (s->p.samplerun) memcpy(s->uhist_last_sync, s->unbiased_hist, sizeof(double) * nb);
+    }
+    double sum = 0.0;
+    for (int k = 0; k < nb; ++k) sum = sum + s->histogram[k];
+    s->sumhist = sum;
+    if (s->wl_factor < s->orig_wl_factor) s->firstcycle = 0;
+    memcpy(s->h, hmatrix, sizeof(double) * 9 * s->nlat);
+    memcpy(s->ref_ljr, ref_ljr, sizeof(double) * n3);
+    memcpy(s->ljr, ljr, sizeof(double) * n3);
+    s->ls = ls;
+    /* :842-856 */
+    for (int ils = 0; ils < s->nlat; ++ils) {
+        s->volume[ils] = fabs(orc_determinant(s->h + 9 * ils));
+        orc_recipmatrix(s->h + 9 * ils, s->recip + 9 * ils);
+        orc_compute_ivects(s, ils);
+    }
+    if (s->nlat == 2) orc_mc_chain_sync(s);
+    for (int ils = 0; ils < s->nlat; ++ils) orc_compute_model_energy(s, ils);
+    if (s->nlat == 2) s->ls_mu = mu_flat(s);          /* :857-862 */
+}
+
 /* ------------------------------------------------------------------ */
 /* periodic bookkeeping on the reduced arrays                          */
 /* ------------------------------------------------------------------ */

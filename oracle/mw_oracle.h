@@ -153,6 +153,12 @@ void   orc_mc_monitor(orc_system *s);                          /* state effects 
 void   orc_mc_chain_sync(orc_system *s);                       /* mc_moves.F90:2217-2416 */
 void   orc_allreduce_bins(orc_system **walkers, int nwalkers); /* comms_mpi.f90:244-277,461-530 over in-process walkers */
 
+/* mc_checkpoint_load (mc_moves.F90:403-501) + the restart refresh of mc_init (:842-862); ref_h and the
+ * neighbour lists stay what the start-up sequence made them, as in the reference */
+void   orc_mc_restore(orc_system *s, int mc_cycle_num, double mc_max_trans, double mc_dv_max, double wl_factor,
+                      int wl_invt_active, int ls, const double *histogram, const double *weight,
+                      const double *unbiased_hist, const double *hmatrix, const double *ref_ljr, const double *ljr);
+
 /* ---- periodic bookkeeping that consumes the reduced arrays ---- */
 typedef struct orc_flat_params {       /* userparams.f90:33-36 */
     int    wl_schedule;                /* 0 = within tol of mean, 1 = min visits, 2 = above (1-tol) of mean */

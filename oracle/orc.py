@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
     L.orc_mc_cycle.restype = i; L.orc_mc_cycle.argtypes = [vp]
     L.orc_mc_run.restype = i; L.orc_mc_run.argtypes = [vp, i]
     L.orc_allreduce_bins.argtypes = [C.POINTER(vp), i]
+    L.orc_mc_restore.argtypes = [vp, i, d, d, d, i, i, dp, dp, dp, dp, dp, dp]
     L.orc_mc_check_flatness.restype = i
     L.orc_mc_check_flatness.argtypes = [C.POINTER(vp), i, C.POINTER(FlatParams), C.POINTER(FlatReport)]
     L.orc_mc_deltaG_from_hist.restype = d; L.orc_mc_deltaG_from_hist.argtypes = [C.POINTER(vp), i, dp]
@@ -246,6 +247,13 @@ class System:
     def mc_update_wl_bins(self) -> None: self.L.orc_mc_update_wl_bins(self.h)
     def mc_monitor(self) -> None: self.L.orc_mc_monitor(self.h)
     def mc_chain_sync(self) -> None: self.L.orc_mc_chain_sync(self.h)
+
+    def mc_restore(self, rec: dict) -> None:
+        """mc_checkpoint_load + restart refresh (mc_moves.F90:403-501, :842-862); rec as decks.read_checkpoint gives it."""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        arrs = [f(rec[k]) for k in ("histogram", "weight", "unbiased_hist", "hmatrix", "ref_ljr", "ljr")]
+        self.L.orc_mc_restore(self.h, int(rec["mc_cycle_num"]), float(rec["mc_max_trans"]), float(rec["mc_dv_max"]),
+                              float(rec["wl_factor"]), int(rec["wl_invt_active"]), int(rec["ls"]), *[_dp(a) for a in arrs])
 
     def counters(self) -> dict:
         return {k: int(self.geti(k)) for k in ("acc_r", "acc_v", "acc_s", "att_r", "att_v", "att_s")}
