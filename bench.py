@@ -119,6 +119,23 @@ def _traffic(kernel: str, cycles: int, walkers: int):
     return None
 
 
+def _issue(kernel: str, cycles: int, walkers: int, k_ms: float, sm_mhz, n_sm: int = 148):
+    """Warp-instruction issue rate of the dominant kernel: executed warp-instructions of one launch (committed ncu
+    capture of the same launch shape) / (live launch duration x SM clock under load x SMs), against the 4 issue
+    slots per cycle of an SM.  This, not the FP64 pipe, is the resource the walker kernel saturates."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        if cycles != CYCLES_PER_STEP or walkers != WALKERS_PER_GPU or not sm_mhz:
+            return None
+        inst = float(t[kernel]["warp_instructions"])
+        ipc = inst / (k_ms * 1e-3 * sm_mhz * 1e6 * n_sm)
+        return {"warp_instructions_per_launch": inst, "ipc_per_sm": ipc, "peak_ipc_per_sm": 4.0, "frac": ipc / 4.0,
+                "instructions_per_move": inst / (walkers * 48 * cycles)}
+    except Exception:
+        return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -373,6 +390,7 @@ def run_ours(args):
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": _traffic("k_mc_run", C, nw),
                          "kernel": "k_mc_run<2,48>", "kernel_ms": k_ms,
+                         "issue": _issue("k_mc_run", C, nw, k_ms, clocks.get("sm_mhz")),
                          "note": "algorithmic flop (10730 per attempted move, BASELINE.md) / measured DFMA peak of this GPU "
                                  "(mwgpu_measure_fp64_peak; MEASURED_PEAKS.json has no fp64 entry)"},
             "e2e": {"value": e2e_value, "unit": "attempted MC moves/s", "h2d_bytes_per_step": int(h2d),

@@ -736,8 +736,8 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
             c = on ? c : r;
             const double ct = ux * q[c] + uy * q[QC + c] + uz * q[2 * QC + c];
             const double mult = (((qm ^ w.qmeta[c]) & 0x3ff00u) == 0u) ? 3.0 : 1.0;   // images of one molecule
-            const double v = q[3 * QC + c] * hfun(ct) * mult;
-            if (on) tb += v;
+            const double dd = ct - CK.cos0;
+            if (on && ct < CK.c099) tb += q[3 * QC + c] * (dd * dd) * mult;      // the k==i filter as a predicate
         }
         tb *= CK.leps * g;
         if (ev == 0) a0 += tb;
@@ -821,14 +821,22 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
                 const uint32_t qo = cq2 & 0xffffu, qn = cq2 >> 16;
                 const bool ho = ok && (qo != NONE16), hn = WITH_NEW && ok && (qn != NONE16);
                 const int io = (qo != NONE16) ? (int)qo : 0, in_ = (qn != NONE16) ? (int)qn : 0;
+                // validity, the cos < 0.99 filter (molint.F90:367-371) and the lattice all end up in the
+                // predicates of the four accumulating adds
                 const double cto = -(q[io] * ux + q[QC + io] * uy + q[2 * QC + io] * uz);
-                const double vo = ho ? q[3 * QC + io] * ex * hfun(cto) : 0.0;
-                double vn = 0.0;
+                const double d_o = cto - CK.cos0;
+                const double vo = q[3 * QC + io] * ex * (d_o * d_o);
+                const bool po = ho && (cto < CK.c099);
+                if (po && lat == 0) a0 += vo;
+                if (po && lat != 0) a2 += vo;
                 if (WITH_NEW) {
                     const double ctn = -(q[in_] * ux + q[QC + in_] * uy + q[2 * QC + in_] * uz);
-                    vn = hn ? q[3 * QC + in_] * ex * hfun(ctn) : 0.0;
+                    const double dn = ctn - CK.cos0;
+                    const double vn = q[3 * QC + in_] * ex * (dn * dn);
+                    const bool pn = hn && (ctn < CK.c099);
+                    if (pn && lat == 0) a1 += vn;
+                    if (pn && lat != 0) a3 += vn;
                 }
-                if (lat == 0) { a0 += vo; a1 += vn; } else { a2 += vo; a3 += vn; }     // predicated adds
             }
         }
         __syncwarp();

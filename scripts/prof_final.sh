@@ -41,6 +41,8 @@ for k,name in (('mc','k_mc_run'),('en','k_model_energy_all')):
     t[name]={'dram_bytes_read':tobytes(*d['dram__bytes_read.sum']),'dram_bytes_write':tobytes(*d['dram__bytes_write.sum']),
              'duration_ms_under_ncu':float(d['gpu__time_duration.sum'][0])*{'ms':1,'us':1e-3,'ns':1e-6,'s':1e3}[d['gpu__time_duration.sum'][1]]}
     t[name]['dram_bytes']=t[name]['dram_bytes_read']+t[name]['dram_bytes_write']
+    t[name]['warp_instructions']=float(d['smsp__inst_executed.sum'][0])
+    t[name]['ipc_per_sm_under_ncu']=float(d['sm__inst_executed.sum.per_cycle_active'][0])/148.0
 t['source']='ncu --set full --clock-control none, one launch of the default bench.py command (4096 walkers, 250 cycles per launch); profiles/${tag}_*_raw.csv'
 json.dump(t, open('profiles/traffic.json','w'), indent=1)
 print(json.dumps(t, indent=1))
