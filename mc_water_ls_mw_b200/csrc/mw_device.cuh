@@ -202,6 +202,10 @@ __device__ __forceinline__ double exp_fast(double x)
     return (x < CK.xmin) ? 0.0 : p * s;
 }
 
+// one shared copy for the call sites outside the bond loops (acceptance, lattice switch): code size matters
+// more than the call there
+__device__ __noinline__ double exp_call(double x) { return exp_fast(x); }
+
 // log(x) for normal positive x (no special cases), ~2e-16 relative: x = m*2^e, m in [sqrt(1/2), sqrt(2)),
 // log m = 2 atanh((m-1)/(m+1))
 __device__ __forceinline__ double log_fast(double x)

@@ -251,7 +251,7 @@ __device__ __noinline__ int lattice_switch_cold(unsigned char* smem, const Devic
     Rng rng{smem, N, nlat, wi, &S, &p, w.rngbuf, w.rngbase, rng_pos};
     const double eta = eta_bin(p, S.mubin, S.ginv, sc, S.weight + (size_t)wi * S.NB, sc->mu).eta;
     const double arg = switch_arg(p, w, sc->E[0], sc->E[1], sc->ls == 1, eta, (double)N);
-    const double compare = (arg > 0.0) ? 1.0 : exp_fast(arg);
+    const double compare = (arg > 0.0) ? 1.0 : exp_call(arg);
     const double x = rng.draw();
     if (x < compare) {
         sc->acc_s += 1;
@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(32, MW_MC_BLOCKS) k_mc_run(const __grid_consta
                 if (lane == 3) arg = eta_acc - p.log_unbiased_norm;
                 if (lane == 4) arg = eta_rej - p.log_unbiased_norm;
                 // min(1, exp(.)) for the probabilities (lanes 0-2); plain exp for the histogram factors
-                const double ex = (arg > 0.0 && lane < 3) ? 1.0 : exp_fast(fmin(arg, 700.0));
+                const double ex = (arg > 0.0 && lane < 3) ? 1.0 : exp_call(fmin(arg, 700.0));
                 const double zeta = rng.draw();
                 const bool accepted = zeta < __shfl_sync(FULL, ex, 0);                         // :1145-1146
                 if (accepted) {
