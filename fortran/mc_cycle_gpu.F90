@@ -130,3 +130,107 @@
     call mwgpu_check(mwgpu_mc_set_wl_factor(gpu_ctx,0_c_int,wl_factor,merge(1_c_int,0_c_int,wl_invt_active)),'mc_gpu_push')
     call mwgpu_check(mwgpu_mc_set_active_lattice(gpu_ctx,0_c_int,int(ls,c_int)),'mc_gpu_push')
   end subroutine mc_gpu_push
+
+!=============================================================================!
+! Device-side variants of the periodic bookkeeping (no pull / push round trip) !
+!                                                                             !
+!  (4) mc_check_flatness (mc_moves.F90:1936-2185): its body becomes            !
+!          call mc_gpu_check_flatness()                                        !
+!      which keeps the log lines and the wlf.dat / eta_weights.dat_* /         !
+!      histogram.dat_* dumps, fed from the returned report and the pulled bins.!
+!  (5) mc_compute_deltaG_from_hist (:2498-2621): the all-reduce / join, the    !
+!      normalisation and the log(pA/pB) come from mwgpu_mc_deltag_from_hist;   !
+!      the log lines and unbiased_histogram_<cycle>.dat stay.                  !
+!  (6) main.f90:200-223: with  call mwgpu_mc_set_therm(gpu_ctx,file_output_int,!
+!      capacity)  at start-up the kernel records the values of every therm row !
+!      itself, so mc_gpu_cycle may advance many cycles per call;               !
+!      mc_gpu_write_therm() drains and prints them with the unchanged formats. !
+!  (7) restart: after mc_checkpoint_load has read the records (:449-492) the   !
+!      refresh of mc_init :842-862 is  call mc_gpu_restore().                  !
+!=============================================================================!
+
+  subroutine mc_gpu_check_flatness()
+    use iso_c_binding
+    use mwgpu
+    use energy,     only : gpu_ctx
+    use comms,      only : myrank
+    use io,         only : glog
+    use userparams, only : wl_schedule,wl_minhist,wl_flattol,wl_useinvt,wl_factor
+    implicit none
+    type(mwgpu_flat_params) :: fp
+    type(mwgpu_flat_report) :: rep
+    fp%wl_schedule = wl_schedule ; fp%wl_minhist = wl_minhist
+    fp%wl_flattol  = wl_flattol  ; fp%wl_useinvt = merge(1,0,wl_useinvt)
+    call mwgpu_check(mwgpu_mc_check_flatness(gpu_ctx,fp,rep),'mc_gpu_check_flatness')
+    if (rep%checked==0) return                                  ! :1961
+    wl_factor = rep%wl_factor
+    wl_invt_active = wl_invt_active.or.(rep%invt_switched/=0)
+    if (rep%flat/=0) firstcycle = .false.
+    if (rep%hist_reset/=0) return                               ! :1973-1980
+    if (myrank==0) then                                         ! :1993-2000
+       write(glog,'("# Checking flatness of histogram at cycle ",I10,"           #")')mc_cycle_num
+       write(glog,'("# Most  populated histogram bin = ",F10.4," % of mean         #")')rep%max_pct
+       write(glog,'("# Least populated histogram bin = ",F10.4," % of mean         #")')rep%min_pct
+    end if
+    if ((rep%flat/=0).and.(myrank==0)) then
+       call mc_gpu_pull_bins()                                  ! weights (shifted) for eta_weights.dat_<f>
+       ! ... the unchanged file dumps of :2067-2101 ...
+    end if
+  end subroutine mc_gpu_check_flatness
+
+  subroutine mc_gpu_deltaG(deltaG,normP)
+    use iso_c_binding
+    use mwgpu
+    use energy, only : gpu_ctx
+    implicit none
+    real(kind=dp),intent(out) :: deltaG
+    real(kind=dp),intent(out) :: normP(:)
+    call mwgpu_check(mwgpu_mc_deltag_from_hist(gpu_ctx,deltaG,normP),'mc_gpu_deltaG')
+  end subroutine mc_gpu_deltaG
+
+  subroutine mc_gpu_write_therm(mytherm)
+    ! main.f90:200-223 from the rows the kernel recorded since the last call
+    use iso_c_binding
+    use mwgpu
+    use energy,     only : gpu_ctx
+    use constants,  only : hart_to_ev,bohr_to_ang,water_mass,aud_to_kgm3
+    use userparams, only : num_lattices,samplerun,wl_factor,nwater
+    use util,       only : util_hmatrix_to_abc
+    implicit none
+    integer,intent(in) :: mytherm
+    integer,parameter  :: maxrows = 64
+    type(mwgpu_therm_row) :: rows(maxrows)
+    integer(c_int) :: n,ndrop
+    integer :: i,l
+    real(kind=dp) :: a,b,c,al,be,ga,h1(3,3)
+    call mwgpu_check(mwgpu_mc_get_therm(gpu_ctx,0_c_int,rows,int(maxrows,c_int),n,ndrop),'mc_gpu_write_therm')
+    if (ndrop/=0) stop 'therm ring overflow: drain more often or raise its capacity'
+    do i = 1,n
+       l = int(rows(i)%ls)
+       if (num_lattices==1) then
+          h1 = reshape(rows(i)%hmatrix1,(/3,3/))
+          call util_hmatrix_to_abc(h1,a,b,c,al,be,ga)
+          write(mytherm,'(I8,E15.6,5x,F15.6,6F15.6)')int(rows(i)%icyc),rows(i)%model_energy(1)*hart_to_ev, &
+               rows(i)%volume(1)*bohr_to_ang**3,a*bohr_to_ang,b*bohr_to_ang,c*bohr_to_ang,al,be,ga
+       else if ((wl_factor<tiny(1.0_dp)).or.samplerun) then
+          write(mytherm,'(I8,E15.6,5x,3F15.6,1x,I1)')int(rows(i)%icyc),rows(i)%model_energy(l)*hart_to_ev, &
+               rows(i)%ls_mu,rows(i)%volume*bohr_to_ang**3,l
+       else
+          write(mytherm,'(I8,E15.6,5x,2F15.6,1x,I1)')int(rows(i)%icyc),rows(i)%model_energy(l)*hart_to_ev, &
+               rows(i)%ls_mu,real(nwater,kind=dp)*water_mass/rows(i)%volume(l)*aud_to_kgm3,l
+       end if
+    end do
+  end subroutine mc_gpu_write_therm
+
+  subroutine mc_gpu_restore()
+    ! after mc_checkpoint_load (:403-501): replaces the host-side refresh of mc_init :842-862
+    use iso_c_binding
+    use mwgpu
+    use energy,     only : gpu_ctx
+    use model,      only : hmatrix,ljr,ref_ljr,ls
+    use userparams, only : mc_max_trans,mc_dv_max,wl_factor
+    implicit none
+    call mwgpu_check(mwgpu_mc_restore(gpu_ctx,0_c_int,int(mc_cycle_num,c_int),mc_max_trans,mc_dv_max,wl_factor, &
+         merge(1_c_int,0_c_int,wl_invt_active),int(ls,c_int),histogram,weight,unbiased_hist, &
+         hmatrix,ref_ljr,ljr),'mc_gpu_restore')
+  end subroutine mc_gpu_restore
