@@ -106,6 +106,18 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def _config(nw: int, total: int, C: int, nwater: int = 48):
+    """The workload both arms are quoted on (BASELINE.json configs[4])."""
+    return {
+        "workload": f"synthetic scale-out (BASELINE configs[4]): {nw} independent lattice-switch walkers per GPU, "
+                    f"{EXAMPLE} deck (48 mW molecules per lattice, cubic<->hexagonal ice, 200 K, 1 atm, fixed weights)",
+        "walkers_per_gpu": nw, "walkers_total": total, "cycles_per_step": C, "moves_per_step": total * nwater * C,
+        "l2_policy": "walker state (~75 MB for 4096 walkers) is read from and written back to global memory once per step; "
+                     "the hot loop runs out of shared memory, so cache state between steps does not matter",
+        "rng": "Philox-4x32-10, one stream per walker",
+    }
+
+
 def _traffic(kernel: str, cycles: int, walkers: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
     (profiles/traffic.json, written by scripts/prof_final.sh); only valid for the launch shape it was taken on."""
@@ -232,9 +244,9 @@ def run_reference(args):
         "impl": "reference", "metric": "attempted MC moves/sec (whole box)", "value": val, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{EXAMPLE}: lattice-switch walkers, 48 mW molecules per lattice, samplerun "
-                               "(the reference's own CPU algorithm restated in C; Fortran toolchain absent)",
-                   "walkers": len(ws), "cycles_per_step": per_step},
+        # the same workload as the GPU arm; each CPU step is the bounded sample of it described in cpu_baseline.sample
+        "config": dict(_config(WALKERS_PER_GPU, WALKERS_PER_GPU * max(args.gpus, 1), CYCLES_PER_STEP, up.nwater),
+                       cpu_sample={"walkers": len(ws), "cycles_per_step": per_step}),
         "cpu_baseline": {"value": val, "unit": unit, "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -374,14 +386,7 @@ def run_ours(args):
             "value": value, "unit": "attempted MC moves/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": f"synthetic scale-out (BASELINE configs[4]): {nw} independent lattice-switch walkers per GPU, "
-                            f"{EXAMPLE} deck (48 mW molecules per lattice, cubic<->hexagonal ice, 200 K, 1 atm, fixed weights)",
-                "walkers_per_gpu": nw, "walkers_total": total, "cycles_per_step": C, "moves_per_step": moves_per_step,
-                "l2_policy": "walker state (~75 MB for 4096 walkers) is read from and written back to global memory once per step; "
-                             "the hot loop runs out of shared memory, so cache state between steps does not matter",
-                "rng": "Philox-4x32-10, one stream per walker",
-            },
+            "config": _config(nw, total, C, up.nwater),
             "energy_evals_per_s": evals_per_s,
             "energy_evals": {"value": evals_per_s, "unit": "single-lattice full mW energy evals/s (dual-lattice = /2)",
                              "ms_per_batch": e_ms, "hbm_gbs_algorithmic": hbm_gbs,
