@@ -208,11 +208,19 @@ def cpu_baseline(target_seconds: float = 12.0):
     while time.perf_counter() - t0 < 2.0:
         orc.model_energy_many(ws, nthreads); reps += 1
     evals = reps * len(ws) * 2 / (time.perf_counter() - t0)
+    # one walker on one thread: the stand-in for the reference's serial build (COMMS_ARCH=serial)
+    one = ws[:1]
+    t0 = time.perf_counter(); ncs = 0
+    while time.perf_counter() - t0 < 2.0:
+        assert orc.mc_run_many(one, 50, 1) == 0; ncs += 50
+    serial = up.nwater * ncs / (time.perf_counter() - t0)
     return {
         "value": moves / dt, "unit": "attempted MC moves/s", "cores": nthreads, "kind": "port",
         "sample": f"{len(ws)} walkers x {ncyc} cycles of {EXAMPLE}, bins merged every {CYCLES_PER_STEP} cycles (oracle "
                   f"restatement, not the Fortran binary; {dt:.1f} s on {nthreads} threads)",
         "energy_evals_per_s": evals,
+        "serial": {"value": serial, "unit": "attempted MC moves/s", "cores": 1,
+                   "sample": f"1 walker x {ncs} cycles on one thread (stand-in for the reference's serial build)"},
     }
 
 
