@@ -81,3 +81,42 @@ def delta_merge_host(arrays, bases, group=None):
         a[:] = total + b
         b[:] = a
     return total
+
+
+def gather_windows_host(mine: np.ndarray, group=None) -> np.ndarray:
+    """All ranks' [W][nbins] blocks in rank order = window order (what the device path does with one
+    ncclAllGather before comms_join_*): returns [size][nbins].  Every rank must own the same number of walkers."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(mine, dtype=np.float64))
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, t, group=group)
+    return np.concatenate([o.numpy() for o in out], axis=0)
+
+
+def join_windows_host(arrs: np.ndarray, overlap: int, eta: bool) -> np.ndarray:
+    """comms_join_eta (eta=True, comms_mpi.f90:377-459) / comms_join_uhist (eta=False, :299-375) on the
+    gathered [size][nbins] windows, in the reference's order of operations (host mirror of k_join_windows)."""
+    size, nb = arrs.shape
+    bpw = nb // size
+    joined = arrs[0].astype(np.float64).copy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for ir in range(1, size):
+            e = ir * bpw
+            myave = 0.0; nextav = 0.0
+            for k in range(e - overlap, e + overlap + 1):
+                myave = myave + (joined[k - 1] if eta else np.log(joined[k - 1]))
+            myave = myave / float(2 * overlap + 1)
+            for k in range(e - overlap, e + overlap + 1):
+                nextav = nextav + (arrs[ir][k - 1] if eta else np.log(arrs[ir][k - 1]))
+            nextav = nextav / float(2 * overlap + 1)
+            shift = myave - nextav
+            if eta:
+                joined[e:] = arrs[ir][e:] + shift
+            else:
+                if np.isnan(shift):
+                    shift = 0.0
+                joined[e:] = arrs[ir][e:] * np.exp(shift)
+    if eta:
+        joined = joined - joined[nb // 2]
+    return joined

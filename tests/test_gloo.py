@@ -75,3 +75,39 @@ def test_world2_delta_allreduce_matches_single_process(tmp_path):
         np.testing.assert_array_equal(got_x[g], ref[g].ljr)                        # chains are untouched by sharding
     assert got_h.sum() > 0
     np.testing.assert_array_equal(got_w[0], got_w[-1])
+
+
+def _join_worker(rank, world, port, per, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nb = 101
+    x = np.linspace(-2, 2, nb)
+    rng = np.random.default_rng(100 + rank)
+    mine_u = np.array([np.exp(-x * x) * 2.0 ** (rank * per + w) * (1 + 0.01 * rng.standard_normal(nb)) for w in range(per)])
+    mine_w = np.array([x * x + 3.0 * (rank * per + w) + 0.01 * rng.standard_normal(nb) for w in range(per)])
+    all_u = comms.gather_windows_host(mine_u)
+    all_w = comms.gather_windows_host(mine_w)
+    np.savez(os.path.join(out_dir, f"join{rank}.npz"), mine_u=mine_u, mine_w=mine_w,
+             ju=comms.join_windows_host(all_u, 2, False), jw=comms.join_windows_host(all_w, 2, True))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_window_join_matches_oracle(tmp_path):
+    """dd windows spread over two ranks: all-gather in rank order + the reference's stitch (comms_mpi.f90:299-459)
+    against the oracle's restatement over all four windows in one process."""
+    from oracle import orc
+    from tests.helpers import make_oracle_walkers
+    world, per = 2, 2
+    mp.spawn(_join_worker, args=(world, _free_port(), per, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"join{r}.npz") for r in range(world)]
+    ws = make_oracle_walkers("ice1_sample_dd", world * per, size=world * per, overrides={"eq_mc_cycles": 100000})
+    for r in range(world):
+        for w in range(per):
+            ws[r * per + w].unbiased_hist[:] = parts[r]["mine_u"][w]
+            ws[r * per + w].weight[:] = parts[r]["mine_w"][w]
+    for r in range(world):                                           # every rank ends with the same joined arrays
+        np.testing.assert_allclose(parts[r]["ju"], orc.join_uhist(ws, 2), rtol=1e-13)
+        np.testing.assert_allclose(parts[r]["jw"], orc.join_eta(ws, 2), rtol=1e-13, atol=1e-13)
