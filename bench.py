@@ -7,9 +7,12 @@
 Workload (BASELINE.json configs[4], "synthetic scale-out"): 4096 independent
 lattice-switch walkers PER GPU of the ice1 size (48 mW molecules per lattice,
 cubic <-> hexagonal ice, deck + weights of examples/ice1_sample: 200 K, 1 atm,
-samplerun, nbins 101, list_update_int 10).  Weak scaling: every rank owns 4096
-walkers; the only exchange is the delta all-reduce of weights / histograms every
-mpi_sync_int = 250 cycles (NCCL).
+samplerun, nbins 101, list_update_int 10).  Weak scaling by default: every rank
+owns 4096 walkers (a B200 holds 2072 walkers resident; 4096 = two full waves);
+the only exchange is the delta all-reduce of weights / histograms every
+mpi_sync_int = 250 cycles (NCCL).  `--scaling strong` splits 4096 walkers in total
+over the GPUs instead (512 per GPU on 8: a quarter of the residency, reported for
+completeness in profiles/README.md).
 
 A *step* = one call of the hot path over the whole batch between two exchanges of
 the reference: `mc_run(mpi_sync_int = 250 cycles)` = 4096 x 48 x 250 attempted moves
@@ -277,7 +280,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nw = args.walkers
+    # weak scaling (default): args.walkers per GPU; strong: args.walkers in total, split evenly over the ranks
+    # (BASELINE configs[4] read literally: "4096 walkers sharded over 1/2/4/8 B200")
+    strong = args.scaling == "strong"
+    if strong and args.walkers % world:
+        raise SystemExit("bench.py: --scaling strong needs --walkers divisible by the number of GPUs")
+    nw = args.walkers // world if strong else args.walkers
     total = nw * world
     up, h, r, w, wl = _example()
 
@@ -393,7 +401,8 @@ def run_ours(args):
             "metric": "attempted MC moves/sec (whole box)",
             "value": value, "unit": "attempted MC moves/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
             "config": _config(nw, total, C, up.nwater),
             "energy_evals_per_s": evals_per_s,
             "energy_evals": {"value": evals_per_s, "unit": "single-lattice full mW energy evals/s (dual-lattice = /2)",
@@ -425,7 +434,10 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--walkers", type=int, default=WALKERS_PER_GPU, help="walkers per GPU")
+    ap.add_argument("--walkers", type=int, default=WALKERS_PER_GPU, help="walkers per GPU (weak) / in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --walkers per GPU (default, what the roofline numbers are quoted on); "
+                         "strong: --walkers in total, split evenly over the GPUs")
     ap.add_argument("--cycles", type=int, default=CYCLES_PER_STEP, help="MC cycles per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
