@@ -197,14 +197,17 @@ __device__ __noinline__ EtaBin eta_bin(const McParams& p, const double* __restri
     k = min(max(k, 1), nb);                                  // memory safety at mu == mu_max (reference would overrun)
     const double* w = wgt - 1;
     const double* mb = mubin - 1;
-    if (!p.eta_interp) { r.eta = __ldcg(w + k); return r; }
+    // fixed weights (sample runs) are read-only for the whole launch: take them through the L1; when the
+    // same warp updates them every move (weight generation) they come from the L2
+    const bool ro = p.samplerun != 0;
+    if (!p.eta_interp) { r.eta = ro ? __ldg(w + k) : __ldcg(w + k); return r; }
     int ka, kb, kr;                                          // gradient between bins ka<kb, anchored at kr
     if (k == sc->start_bin)      { ka = k; kb = k + 1; kr = k; }
     else if (k == sc->end_bin)   { ka = k - 1; kb = k; kr = k; }
     else if (mu > __ldg(mb + k)) { ka = k; kb = k + 1; kr = k; }
     else                         { ka = k - 1; kb = k; kr = k - 1; }
     ka = max(ka, 1); kb = min(kb, nb);
-    const double wa = __ldcg(w + ka), wb = __ldcg(w + kb);
+    const double wa = ro ? __ldg(w + ka) : __ldcg(w + ka), wb = ro ? __ldg(w + kb) : __ldcg(w + kb);
     const double g = (wb - wa) * __ldg(binwidth + ka - 1);       // binwidth = the 2/(bw(ka)+bw(kb)) table here
     const double wr = (kr == ka) ? wa : wb;
     r.eta = wr + (mu - __ldg(mb + kr)) * g;
