@@ -117,6 +117,9 @@ def test_window_joins_and_deltaG_dd():
     # dd windows: no all-reduce, per-window flatness
     ("ice1_sample_dd", 4, 90, {"eq_mc_cycles": 50, "monitor_int": 16, "flat_chk_int": 20, "latt_sync_int": 30,
                                "deltaG_int": 45}),
+    # dd weight generation: every window checks its own histogram and halves its own wl_factor
+    ("ice1_gen_weights_dd", 4, 90, {"eq_mc_cycles": 50, "monitor_int": 16, "flat_chk_int": 10, "latt_sync_int": 30,
+                                    "wl_schedule": 1, "wl_minhist": -1}),
 ])
 def test_whole_run_under_the_reference_schedule(ex, n, ncyc, ov):
     g, ws, up = _pair(ex, n, ov)
@@ -133,7 +136,7 @@ def test_whole_run_under_the_reference_schedule(ex, n, ncyc, ov):
         # (sparsely filled windows give log(0) seams: inf / nan must come out the same way on both sides)
         np.testing.assert_allclose(d1, d2, rtol=1e-10, atol=1e-10, equal_nan=True)
         np.testing.assert_allclose(p1, p2, rtol=1e-9, atol=1e-300, equal_nan=True)
-    if ex == "ice1_gen_weights":
+    if ex.startswith("ice1_gen_weights"):
         assert any(r.flat for _, r in sch.log.flatness)             # wl_factor was halved on the device
     for w, s in enumerate(ws):
         st = g.state(w)
