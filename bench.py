@@ -415,6 +415,13 @@ def run_ours(args):
                          "issue": _issue("k_mc_run", C, nw, k_ms, clocks.get("sm_mhz")),
                          "note": "algorithmic flop (10730 per attempted move, BASELINE.md) / measured DFMA peak of this GPU "
                                  "(mwgpu_measure_fp64_peak; MEASURED_PEAKS.json has no fp64 entry)"},
+            # the same kernel against the HBM roofline, for the record: the walker state crosses HBM once per launch
+            "roofline_hbm": (lambda tb: {"bound": "hbm", "achieved": (tb / (k_ms * 1e-3) / 1e9) if tb else None,
+                                         "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
+                                         "frac": (tb / (k_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0)) if tb else None,
+                                         "traffic": tb, "peak_kind": peak_kind,
+                                         "note": "measured DRAM bytes of one launch / live launch duration: the path is not HBM-bound"}
+                             )(_traffic("k_mc_run", C, nw)),
             "e2e": {"value": e2e_value, "unit": "attempted MC moves/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
