@@ -229,3 +229,37 @@ def test_full_size_properties_4096_walkers():
     o.set_rng_philox(SEED, 1234, 1000000)
     assert o.mc_run(20) == 0
     np.testing.assert_array_equal(g.download(1234)[0], o.ljr)
+
+
+def test_long_run_reproduces_the_reference_energy_drift():
+    """The incrementally maintained model_energy drifts from a fresh evaluation when a neighbour enters the
+    cut-off before the next list refresh (the reference prints this drift at every monitor, mc_moves.F90:1781-1792).
+    That is the algorithm, not an error: the walker with the LARGEST drift out of 768 after 2 500 cycles must be
+    reproduced by the oracle -- positions and counters bit for bit, and the same drift."""
+    ov = {"eq_mc_cycles": 500}
+    nw = 768
+    g, up = make_gpu_walkers("ice1_sample", nwalkers=nw, overrides=ov)
+    g.set_rng_philox(SEED, 0, 1000000)
+    for _ in range(2):
+        g.mc_run(1000); g.mc_monitor()
+    g.mc_run(500)
+    st = g.states()
+    assert not any(s.error for s in st)
+    inc = np.array([list(s.model_energy) for s in st])
+    fresh = g.compute_model_energy_all()
+    d = (np.abs(inc - fresh) / np.abs(fresh)).max(1)
+    worst = int(np.argmax(d))
+    o, _ = make_oracle_walker("ice1_sample", rank=worst, size=nw, overrides=ov)
+    o.set_rng_philox(SEED, worst, 1000000)
+    for _ in range(2):
+        assert o.mc_run(1000) == 0; o.mc_monitor()
+    assert o.mc_run(500) == 0
+    ljr, ref, hm = g.download(worst)
+    np.testing.assert_array_equal(ljr, o.ljr); np.testing.assert_array_equal(hm, o.hmatrix)
+    assert list(st[worst].accepted) == [o.geti("acc_r"), o.geti("acc_v"), o.geti("acc_s")]
+    assert st[worst].rng_index == o.geti("rng_index")
+    oinc = np.array(o.model_energy).copy()
+    ofresh = np.array([o.compute_model_energy(1), o.compute_model_energy(2)])
+    assert rel_err(inc[worst], oinc) < TOL and rel_err(fresh[worst], ofresh) < TOL
+    od = (np.abs(oinc - ofresh) / np.abs(ofresh)).max()
+    assert abs(d[worst] - od) <= 1e-9 * max(od, 1e-12) + 1e-13
