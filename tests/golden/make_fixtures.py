@@ -54,8 +54,60 @@ def oracle_vectors():
     np.savez_compressed(os.path.join(HERE, "oracle_vectors.npz"), **out)
 
 
+def bookkeeping_vectors():
+    """Seeded inputs + oracle outputs of the periodic bookkeeping on the reduced arrays:
+    window joins, deltaG, flatness decisions.  The GPU box replays the inputs through the C ABI."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    from oracle import orc
+    from tests.helpers import make_oracle_walkers
+
+    out = {}
+    rng = np.random.default_rng(20141211)
+    ws = make_oracle_walkers("ice1_sample_dd", 4, size=4)
+    nb = ws[0].nbins
+    x = np.linspace(-2, 2, nb)
+    U = np.array([np.exp(-x * x) * 2.0 ** w * (1 + 0.01 * rng.standard_normal(nb)) for w in range(4)])
+    Wt = np.array([x * x + 3.0 * w + 0.01 * rng.standard_normal(nb) for w in range(4)])
+    for w, s in enumerate(ws):
+        s.unbiased_hist[:] = U[w]; s.weight[:] = Wt[w]
+    out["dd/uhist"] = U; out["dd/weight"] = Wt
+    for ov in (0, 2, 5):
+        out[f"dd/join_uhist_{ov}"] = orc.join_uhist(ws, ov)
+        out[f"dd/join_eta_{ov}"] = orc.join_eta(ws, ov)
+    dg, normP = orc.mc_deltaG_from_hist(ws)
+    out["dd/deltaG"] = np.array([dg]); out["dd/normP"] = normP
+    ws = make_oracle_walkers("ice1_sample", 3)
+    inc = rng.random((3, nb))
+    for s, u in zip(ws, inc):
+        s.unbiased_hist[:] = u
+    dg, normP = orc.mc_deltaG_from_hist(ws)
+    out["mw/uhist_increments"] = inc; out["mw/deltaG"] = np.array([dg]); out["mw/normP"] = normP
+    # flatness: (schedule, histogram) -> (flat, mean, max_pct, min_pct, wl_factor, weights after)
+    ws0 = make_oracle_walkers("ice1_gen_weights", 1)
+    nbg = ws0[0].nbins
+    hists = np.array([np.full(nbg, 100.0), np.r_[np.full(nbg - 1, 100.0), 111.0], np.r_[np.full(nbg - 1, 500.0), 19.4],
+                      np.r_[np.full(nbg - 1, 100.0), 400.0], 50.0 + 100.0 * rng.random(nbg)])
+    wts = np.linspace(3.0, 7.0, nbg)
+    rows = []; wafter = []
+    for sched in (0, 1, 2):
+        for h in hists:
+            s = make_oracle_walkers("ice1_gen_weights", 1)[0]
+            # state as after a restart with an already reduced increment (firstcycle = .false.): the GPU side
+            # reaches it through mwgpu_mc_restore
+            s.seti("firstcycle", 0); s.seti("mc_cycle_num", 100); s.setd("wl_factor", 0.004)
+            s.weight[:] = wts; s.histogram[:] = h; s.arr_d("hist_last_sync", (nbg,))[:] = h
+            r = orc.mc_check_flatness([s], sched, 20, float(np.float32(0.05)), False)
+            rows.append([sched, r.checked, r.hist_reset, r.flat, r.mean, r.max_pct, r.min_pct, r.wl_factor])
+            wafter.append(s.weight.copy())
+    out["flat/hists"] = hists; out["flat/weights"] = wts
+    out["flat/rows"] = np.array(rows); out["flat/weights_after"] = np.array(wafter)
+    np.savez_compressed(os.path.join(HERE, "bookkeeping_vectors.npz"), **out)
+
+
 if __name__ == "__main__":
     if os.path.isdir(REF):
         copy_examples()
     oracle_vectors()
+    bookkeeping_vectors()
     print("fixtures written to", HERE)

@@ -221,3 +221,38 @@ def test_tree_reduction_of_large_batches_matches_a_host_sum():
     np.testing.assert_array_equal(g.bins(0)[0], g.bins(n - 1)[0])
     g.comms_allreduce_bins()                                    # nothing new since the sync: a fixed point
     np.testing.assert_allclose(g.bins(5)[0], tot_w, rtol=1e-12, atol=1e-12)
+
+
+def test_bookkeeping_golden_vectors_on_gpu():
+    """The committed inputs of tests/golden/bookkeeping_vectors.npz replayed through the C ABI."""
+    import os
+    from tests.helpers import GOLDEN
+    v = np.load(os.path.join(GOLDEN, "bookkeeping_vectors.npz"))
+    g, up = make_gpu_walkers("ice1_sample_dd", nwalkers=4, size=4)
+    for w in range(4):
+        g.set_bins(w, weight=v["dd/weight"][w], unbiased_hist=v["dd/uhist"][w])
+    for ov in (0, 2, 5):
+        np.testing.assert_allclose(g.comms_join_uhist(ov), v[f"dd/join_uhist_{ov}"], rtol=1e-13)
+        np.testing.assert_allclose(g.comms_join_eta(ov), v[f"dd/join_eta_{ov}"], rtol=1e-13, atol=1e-13)
+    dg, normP = g.mc_compute_deltaG_from_hist()
+    assert abs(dg - v["dd/deltaG"][0]) < 1e-11 * max(1.0, abs(v["dd/deltaG"][0]))
+    np.testing.assert_allclose(normP, v["dd/normP"], rtol=1e-12)
+    g, up = make_gpu_walkers("ice1_sample", nwalkers=3)
+    for w in range(3):
+        g.set_bins(w, unbiased_hist=v["mw/uhist_increments"][w])    # increments over the zero base
+    dg, normP = g.mc_compute_deltaG_from_hist()
+    assert abs(dg - v["mw/deltaG"][0]) < 1e-11 * max(1.0, abs(v["mw/deltaG"][0]))
+    np.testing.assert_allclose(normP, v["mw/normP"], rtol=1e-12)
+    k = 0
+    for sched in (0, 1, 2):
+        for h in v["flat/hists"]:
+            g, up = make_gpu_walkers("ice1_gen_weights", nwalkers=1)
+            rec = g.checkpoint_record(0)
+            rec.update(mc_cycle_num=100, wl_factor=0.004, histogram=h, weight=v["flat/weights"])
+            g.mc_restore(0, rec)                                     # firstcycle = .false., bases re-set
+            r = g.mc_check_flatness(sched, 20, float(np.float32(0.05)), False)
+            row = v["flat/rows"][k]
+            assert [sched, r.checked, r.hist_reset, r.flat] == row[:4].tolist()
+            assert [r.mean, r.max_pct, r.min_pct, r.wl_factor] == row[4:].tolist()       # bit for bit
+            np.testing.assert_array_equal(g.bins(0)[0], v["flat/weights_after"][k])
+            k += 1

@@ -151,3 +151,34 @@ def test_deltaG_from_hist_formula():
     assert abs((normP * bw).sum() - 1.0) < 1e-13
     for s in ws:                                                    # comms_allreduce_uhist happened (:2530)
         np.testing.assert_allclose(s.unbiased_hist, tot, rtol=1e-15)
+
+
+def test_bookkeeping_golden_vectors():
+    """tests/golden/bookkeeping_vectors.npz (tests/golden/make_fixtures.py): the oracle must keep reproducing it."""
+    import os
+    from tests.helpers import GOLDEN
+    v = np.load(os.path.join(GOLDEN, "bookkeeping_vectors.npz"))
+    ws = _walkers(4, ex="ice1_sample_dd")
+    for w, s in enumerate(ws):
+        s.unbiased_hist[:] = v["dd/uhist"][w]; s.weight[:] = v["dd/weight"][w]
+    for ov in (0, 2, 5):
+        np.testing.assert_array_equal(orc.join_uhist(ws, ov), v[f"dd/join_uhist_{ov}"])
+        np.testing.assert_array_equal(orc.join_eta(ws, ov), v[f"dd/join_eta_{ov}"])
+    dg, normP = orc.mc_deltaG_from_hist(ws)
+    assert dg == v["dd/deltaG"][0]; np.testing.assert_array_equal(normP, v["dd/normP"])
+    ws = _walkers(3, ex="ice1_sample")
+    for s, u in zip(ws, v["mw/uhist_increments"]):
+        s.unbiased_hist[:] = u
+    dg, normP = orc.mc_deltaG_from_hist(ws)
+    assert dg == v["mw/deltaG"][0]; np.testing.assert_array_equal(normP, v["mw/normP"])
+    k = 0
+    for sched in (0, 1, 2):
+        for h in v["flat/hists"]:
+            s = _walkers(1)[0]
+            s.seti("firstcycle", 0); s.seti("mc_cycle_num", 100); s.setd("wl_factor", 0.004)
+            s.weight[:] = v["flat/weights"]; s.histogram[:] = h; s.arr_d("hist_last_sync", (s.nbins,))[:] = h
+            r = orc.mc_check_flatness([s], sched, 20, F32_TOL, False)
+            assert [sched, r.checked, r.hist_reset, r.flat, r.mean, r.max_pct, r.min_pct, r.wl_factor] == v["flat/rows"][k].tolist()
+            np.testing.assert_array_equal(s.weight, v["flat/weights_after"][k])
+            k += 1
+    assert v["flat/rows"][:, 3].sum() >= 3                       # several flat and several non-flat cases
