@@ -102,6 +102,7 @@ SYMBOLS = {
     "mwgpu_mc_set_rng_fifo": (_i, [_vp, _dp, C.c_int64]),
     "mwgpu_mc_run": (_i, [_vp, _i]),
     "mwgpu_mc_run_async": (_i, [_vp, _i]),
+    "mwgpu_mc_set_kernel": (_i, [_vp, _i]),
     "mwgpu_synchronize": (_i, [_vp]),
     "mwgpu_mc_get_state": (_i, [_vp, _i, C.POINTER(WalkerState)]),
     "mwgpu_mc_get_states": (_i, [_vp, C.POINTER(WalkerState)]),
@@ -136,7 +137,7 @@ SYMBOLS = {
 
 def build(force: bool = False) -> str:
     """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("mwgpu.cu", "mw_mc.cuh", "mw_device.cuh", "Makefile")]
+    srcs = [os.path.join(CSRC, f) for f in ("mwgpu.cu", "mw_mc2.cuh", "mw_mc.cuh", "mw_device.cuh", "Makefile")]
     srcs.append(os.path.join(os.path.dirname(_PKG), "include", "mwgpu.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:

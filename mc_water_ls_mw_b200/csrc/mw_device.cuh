@@ -94,6 +94,15 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lowbits(int n) { return (n >= 32) ? 0xffffffffu : ((1u << n) - 1u); }
 __device__ __forceinline__ unsigned lt_mask() { return (1u << (threadIdx.x & 31)) - 1u; }
 
+// Packed Verlet-list entry (uint16).  Boxes of up to 64 molecules (every reference deck has 48) carry the
+// REVERSE SLOT of the entry as well: entry s of row i = (j, image) has rev = the slot of row j that holds
+// (i, inverse image) -- the neighbour test is symmetric (molint.F90:537 on exact negatives), so it always exists.
+//     N <= 64 :  j | rev << 6 | image << 11          N > 64 :  j | image << 10
+struct EntFmt { uint32_t jmask; int ishift; };
+__host__ __device__ __forceinline__ EntFmt ent_fmt(int N) { return (N <= 64) ? EntFmt{63u, 11} : EntFmt{1023u, 10}; }
+__host__ __device__ __forceinline__ bool ent_has_rev(int N) { return N <= 64; }
+__device__ __forceinline__ double dist2(double x, double y, double z) { return fma(z, z, fma(y, y, x * x)); }
+
 // Fortran m(i,j), 1-based, column-major 3x3
 #define MW_H(m, i, j) ((m)[((j) - 1) * 3 + ((i) - 1)])
 
@@ -454,6 +463,7 @@ __device__ __noinline__ int compute_neighbours_warp(unsigned char* smem, int N, 
     const double R1 = RN * (1.0 + 1e-9) * sqrt(b[3] * b[3] + b[4] * b[4] + b[5] * b[5]) + 1e-12;
     const double R2 = RN * (1.0 + 1e-9) * sqrt(b[6] * b[6] + b[7] * b[7] + b[8] * b[8]) + 1e-12;
     const bool boxed = (nv == 27);                              // always, unless the image set is degenerate
+    const EntFmt F = ent_fmt(N);
 #pragma unroll 1
     for (int i = 0; i < N; ++i) {
         const double ix = P[i], iy = P[N + i], iz = P[2 * N + i];
@@ -499,7 +509,7 @@ __device__ __noinline__ int compute_neighbours_warp(unsigned char* smem, int N, 
 #pragma unroll 1
             while (m) {
                 const int k = __ffs(m) - 1; m &= m - 1;
-                if (off < LC) row[off] = (uint16_t)((k << 10) | j);
+                if (off < LC) row[off] = (uint16_t)((k << F.ishift) | j);
                 ++off;
             }
             total += __shfl_sync(FULL, incl, 31);
@@ -509,6 +519,34 @@ __device__ __noinline__ int compute_neighbours_warp(unsigned char* smem, int N, 
     }
     err = (int)__reduce_or_sync(FULL, (unsigned)err);
     __syncwarp();
+    // reverse slots (boxes of up to 64 molecules): lanes = the slots of row i; a row is sorted by (j, image), so
+    // the entry (i, inverse image) of row j is found by bisection.  After an overflow the rows are truncated and
+    // the field is meaningless (the walker is flagged).
+    if (ent_has_rev(N)) {
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+            const int nni = w.nn[lat * N + i];
+            if (lane < nni) {
+                uint16_t* row = w.list + ((size_t)lat * N + i) * LC;
+                const uint32_t e = row[lane];
+                const int j = e & 63, img = e >> 11;
+                const uint32_t key = ((uint32_t)inverse_image(img, nv) << 11) | (uint32_t)i;
+                const uint16_t* rj = w.list + ((size_t)lat * N + j) * LC;
+                // keys compare as (j, image) = low 6 bits major: order by (e & 63) << 5 | (e >> 11)
+                const uint32_t want = ((key & 63u) << 5) | (key >> 11);
+                int lo = 0, hi = (int)w.nn[lat * N + j] - 1;
+#pragma unroll 1
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const uint32_t e2 = rj[mid];
+                    const uint32_t have = ((e2 & 63u) << 5) | (e2 >> 11);
+                    if (have < want) lo = mid + 1; else hi = mid;
+                }
+                row[lane] = (uint16_t)(e | ((uint32_t)lo << 6));
+            }
+        }
+        __syncwarp();
+    }
     return err;
 }
 
@@ -521,15 +559,16 @@ __device__ __noinline__ void compute_bond_masks_warp(unsigned char* smem, int N,
     const int lane = lane_id();
     const double* P = w.pos + lat * 3 * N;
     const double* V = w.iv + lat * 3 * IVC;
+    const EntFmt F = ent_fmt(N);
     for (int a = 0; a < N; ++a) {
         const int nna = w.nn[lat * N + a];
         const bool has = lane < nna;
         const uint32_t e = has ? w.list[((size_t)lat * N + a) * LC + lane] : 0u;
-        const int j = e & 1023, img = e >> 10;
+        const int j = e & F.jmask, img = e >> F.ishift;
         const double tx = (P[j] + V[img]) - P[a];
         const double ty = (P[N + j] + V[IVC + img]) - P[N + a];
         const double tz = (P[2 * N + j] + V[2 * IVC + img]) - P[2 * N + a];
-        const double r2 = tx * tx + ty * ty + tz * tz;
+        const double r2 = dist2(tx, ty, tz);
         const uint32_t m = __ballot_sync(FULL, has && r2 < RCSQ);
         if (lane == 0) w.bmask[lat * N + a] = m;
     }
@@ -644,6 +683,7 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
     // One copy of the code for both lattices (the loop is NOT unrolled: the kernel sits at the edge of
     // the instruction cache); the trial position comes from the walker's move record w.mv.
     uint32_t mo0 = 0, mo1 = 0, mn0 = 0, mn1 = 0;
+    const EntFmt F = ent_fmt(N);
 #pragma unroll 1
     for (int lat = 0; lat < NLAT; ++lat) {
         const double* P = w.pos + lat * 3 * N;
@@ -651,10 +691,10 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
         const int nni = w.nn[lat * N + imol];
         const bool has = lane < nni;
         const uint32_t e = has ? w.list[((size_t)lat * N + imol) * LC + lane] : 0u;
-        const int j = e & 1023, img = e >> 10;
+        const int j = e & F.jmask, img = e >> F.ishift;
         const double pjx = P[j] + V[img], pjy = P[N + j] + V[IVC + img], pjz = P[2 * N + j] + V[2 * IVC + img];
         const double tox = pjx - P[imol], toy = pjy - P[N + imol], toz = pjz - P[2 * N + imol];
-        const double r2o = tox * tox + toy * toy + toz * toz;
+        const double r2o = dist2(tox, toy, toz);
         const bool fo = has && r2o < CK.rcsq;
         const uint32_t bo = __ballot_sync(FULL, fo);
         if (lat == 0) mo0 = bo; else mo1 = bo;
@@ -665,7 +705,7 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
         if (WITH_NEW) {
             const double* pn = w.mv + lat * 6;
             tnx = pjx - pn[0]; tny = pjy - pn[1]; tnz = pjz - pn[2];
-            r2n = tnx * tnx + tny * tny + tnz * tnz;
+            r2n = dist2(tnx, tny, tnz);
             fn = has && r2n < CK.rcsq;
             bn = __ballot_sync(FULL, fn);
             if (lat == 0) mn0 = bn; else mn1 = bn;
@@ -808,13 +848,13 @@ __device__ __forceinline__ void local_energies_warp(const WalkerView& w, int imo
                 const uint32_t cm = w.cmeta[c];
                 const int lat = cm & 1, j = (cm >> 6) & 1023;
                 const uint32_t e2 = w.list[((size_t)lat * N + j) * LC + s2];
-                const int k = e2 & 1023, img = e2 >> 10;
+                const int k = e2 & F.jmask, img = e2 >> F.ishift;
                 const double* P = w.pos + lat * 3 * N;
                 const double* V = w.iv + lat * 3 * IVC;
                 const double tx = (P[k] + V[img]) - P[j];
                 const double ty = (P[N + k] + V[IVC + img]) - P[N + j];
                 const double tz = (P[2 * N + k] + V[2 * IVC + img]) - P[2 * N + j];
-                const double sq0 = tx * tx + ty * ty + tz * tz;
+                const double sq0 = dist2(tx, ty, tz);
                 const bool ok = in && (k != imol) && (sq0 < CK.rcsq);
                 const double sq = ok ? sq0 : CK.ss;                    // any length inside the cut-off
                 double vi, isr;
@@ -866,6 +906,7 @@ __device__ __noinline__ double full_energy_warp(unsigned char* smem, int N, int 
     const double* P = w.pos + lat * 3 * N;
     const double* V = w.iv + lat * 3 * IVC;
     double* q = w.q;
+    const EntFmt F = ent_fmt(N);
     double acc = 0.0;
     int a = 0;
     while (a < N) {
@@ -876,11 +917,11 @@ __device__ __noinline__ double full_energy_warp(unsigned char* smem, int N, int 
             const int nna = w.nn[lat * N + a1];
             const bool has = lane < nna;
             const uint32_t e = has ? w.list[((size_t)lat * N + a1) * LC + lane] : 0u;
-            const int j = e & 1023, img = e >> 10;
+            const int j = e & F.jmask, img = e >> F.ishift;
             const double tx = (P[j] + V[img]) - P[a1];
             const double ty = (P[N + j] + V[IVC + img]) - P[N + a1];
             const double tz = (P[2 * N + j] + V[2 * IVC + img]) - P[2 * N + a1];
-            const double r2 = tx * tx + ty * ty + tz * tz;
+            const double r2 = dist2(tx, ty, tz);
             const bool f = has && r2 < RCSQ;
             const uint32_t bm = __ballot_sync(FULL, f);
             const int cnt = __popc(bm);

@@ -478,13 +478,15 @@ __device__ __forceinline__ void commit_translation(const WalkerView& w, int imol
         uint32_t changed = mol ^ mnl;
         if (lane == 0) w.bmask[lat * N + imol] = mnl;
         const int nv = w.niv[lat];
+        const EntFmt F = ent_fmt(N);
+        const uint32_t keep = ~(ent_has_rev(N) ? (31u << 6) : 0u);     // compare without the reverse-slot field
         while (changed) {
             const int s = __ffs(changed) - 1; changed &= changed - 1;
             const uint32_t e = w.list[((size_t)lat * N + imol) * LC + s];
-            const int j = e & 1023, img = e >> 10;
-            const uint32_t target = ((uint32_t)inverse_image(img, nv) << 10) | (uint32_t)imol;
+            const int j = e & F.jmask, img = e >> F.ishift;
+            const uint32_t target = ((uint32_t)inverse_image(img, nv) << F.ishift) | (uint32_t)imol;
             const int nnj = w.nn[lat * N + j];
-            const uint32_t e2 = (lane < nnj) ? w.list[((size_t)lat * N + j) * LC + lane] : 0xffffffffu;
+            const uint32_t e2 = (lane < nnj) ? (w.list[((size_t)lat * N + j) * LC + lane] & keep) : 0xffffffffu;
             const uint32_t hit = __ballot_sync(FULL, e2 == target);
             if (hit && lane == 0) {
                 const int s2 = __ffs(hit) - 1;

@@ -3,7 +3,7 @@
 // The two hot kernels are k_mc_run (mw_mc.cuh) and k_model_energy_all (below);
 // everything else here is start-up / bookkeeping plumbing around them.
 #include "../../include/mwgpu.h"
-#include "mw_mc.cuh"
+#include "mw_mc2.cuh"
 
 #include <cmath>
 #include <cfloat>
@@ -49,6 +49,7 @@ struct mwgpu_ctx {
     McParams P{};
     mwgpu_mc_params user{};
     bool mc_ready = false, energy_ready = false;
+    int walker_kernel = 0;         // 0: automatic, 1: one warp per walker, 2: two warps per walker (one per lattice)
     int first_rank = 0, size = 1;
     double* stage = nullptr;       // device staging for layout conversion: [W][nlat][N][3] x2 + cells
     size_t stage_doubles = 0;
@@ -596,12 +597,13 @@ static int fetch_lists(mwgpu_ctx* c, int walker, int ils, int* nn, int* jn, int*
     CUDA_TRY(cudaMemcpy(hl.data(), c->S.list + ((size_t)walker * c->nlat + (ils - 1)) * N * LC,
                         sizeof(uint16_t) * N * LC, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(hn.data(), c->S.nn + ((size_t)walker * c->nlat + (ils - 1)) * N, N, cudaMemcpyDeviceToHost));
+    const EntFmt F = ent_fmt(N);
     for (int i = 0; i < N; ++i) {
         if (nn) nn[i] = hn[i];
         for (int s = 0; s < MWGPU_MAXNEIGH; ++s) {
             const bool used = s < hn[i] && s < LC;
-            if (jn) jn[i * MWGPU_MAXNEIGH + s] = used ? (hl[(size_t)i * LC + s] & 1023) + 1 : 0;
-            if (vn) vn[i * MWGPU_MAXNEIGH + s] = used ? (hl[(size_t)i * LC + s] >> 10) + 1 : 0;
+            if (jn) jn[i * MWGPU_MAXNEIGH + s] = used ? (hl[(size_t)i * LC + s] & F.jmask) + 1 : 0;
+            if (vn) vn[i * MWGPU_MAXNEIGH + s] = used ? (hl[(size_t)i * LC + s] >> F.ishift) + 1 : 0;
         }
     }
     return 0;
@@ -964,13 +966,32 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
         CUDA_TRY(cudaFuncSetAttribute(k_mc_run<NLAT_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_mc_run<NLAT_, NT_><<<c->W, 32, smem, c->stream>>>(c->S, c->P, ncycles);                                 \
     } while (0)
-    if (c->nlat == 2) { if (c->N == 48) MW_LAUNCH_MC(2, 48); else MW_LAUNCH_MC(2, 0); }
-    else              { if (c->N == 48) MW_LAUNCH_MC(1, 48); else MW_LAUNCH_MC(1, 0); }
+#define MW_LAUNCH_MC2(NT_)                                                                                        \
+    do {                                                                                                          \
+        CUDA_TRY(cudaFuncSetAttribute(k_mc_run2<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        k_mc_run2<NT_><<<c->W, 64, smem, c->stream>>>(c->S, c->P, ncycles);                                       \
+    } while (0)
+    // two lattices, up to 64 molecules: one warp per lattice (mw_mc2.cuh); everything else: one warp per walker
+    const bool two_warps = c->nlat == 2 && ent_has_rev(c->N) && c->walker_kernel != 1;
+    if (two_warps)         { if (c->N == 48) MW_LAUNCH_MC2(48); else MW_LAUNCH_MC2(0); }
+    else if (c->nlat == 2) { if (c->N == 48) MW_LAUNCH_MC(2, 48); else MW_LAUNCH_MC(2, 0); }
+    else                   { if (c->N == 48) MW_LAUNCH_MC(1, 48); else MW_LAUNCH_MC(1, 0); }
 #undef MW_LAUNCH_MC
+#undef MW_LAUNCH_MC2
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     c->launches++;
     if (int rc = finish(c, sync)) return rc;
     if (sync) return collect_errors(c, "mwgpu_mc_run");
+    return 0;
+}
+
+extern "C" int mwgpu_mc_set_kernel(mwgpu_ctx* c, int warps_per_walker)
+{
+    if (!c) return fail("mwgpu_mc_set_kernel: NULL context");
+    if (warps_per_walker < 0 || warps_per_walker > 2) return fail("mwgpu_mc_set_kernel: 0 (automatic), 1 or 2 warps per walker");
+    if (warps_per_walker == 2 && !(c->nlat == 2 && ent_has_rev(c->N)))
+        return fail("mwgpu_mc_set_kernel: the two-warp kernel needs two lattices of up to 64 molecules");
+    c->walker_kernel = warps_per_walker;
     return 0;
 }
 
