@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmwgpu.so")
+# MWGPU_LIB_PATH: development aid (builds with other -D knobs side by side); the default is the in-tree library
+LIB_PATH = os.environ.get("MWGPU_LIB_PATH") or os.path.join(_PKG, "libmwgpu.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 MAXNEIGH = 50
@@ -137,7 +138,7 @@ SYMBOLS = {
 
 def build(force: bool = False) -> str:
     """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("mwgpu.cu", "mw_mc2.cuh", "mw_mc.cuh", "mw_device.cuh", "Makefile")]
+    srcs = [os.path.join(CSRC, f) for f in ("mwgpu.cu", "mw2.cuh", "mw_mc.cuh", "mw_device.cuh", "Makefile")]
     srcs.append(os.path.join(os.path.dirname(_PKG), "include", "mwgpu.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:

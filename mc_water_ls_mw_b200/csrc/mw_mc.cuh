@@ -122,11 +122,10 @@ __device__ __forceinline__ void store_walker(const DeviceState& S, int wi, const
 // Per-walker stream of U[0,1) numbers (random.f90:87-102), buffered RB at a time in shared
 // memory.  mode 0: Philox (draw n = half n&1 of block n>>1); mode 1: host FIFO (draw n = fifo[n]).
 // `pos` (index of the next draw inside the buffer) is carried in a register by the caller.
-__device__ __noinline__ void rng_refill(unsigned char* smem, int N, int nlat, const DeviceState& S, const McParams& p, int wi)
+__device__ __noinline__ void rng_refill_at(const uint64_t* rngbase, double* rngbuf, const DeviceState& S, const McParams& p, int wi)
 {
-    const WalkerView w = carve_walker(smem, N, nlat);
     const int lane = lane_id();
-    const uint64_t base = *w.rngbase;
+    const uint64_t base = *rngbase;
     __syncwarp();
     double v0, v1;
     if (p.rng_mode == 0) {
@@ -136,8 +135,14 @@ __device__ __noinline__ void rng_refill(unsigned char* smem, int N, int nlat, co
         v0 = (i0 < S.fifo_len) ? S.fifo[i0] : 0.5;
         v1 = (i0 + 1 < S.fifo_len) ? S.fifo[i0 + 1] : 0.5;
     }
-    w.rngbuf[2 * lane] = v0; w.rngbuf[2 * lane + 1] = v1;
+    rngbuf[2 * lane] = v0; rngbuf[2 * lane + 1] = v1;
     __syncwarp();
+}
+
+__device__ __forceinline__ void rng_refill(unsigned char* smem, int N, int nlat, const DeviceState& S, const McParams& p, int wi)
+{
+    const WalkerView w = carve_walker(smem, N, nlat);
+    rng_refill_at(w.rngbase, w.rngbuf, S, p, wi);
 }
 
 struct Rng {
@@ -224,15 +229,14 @@ __device__ __forceinline__ double mu_paren(const McParams& p, const WalkerScalar
 
 // -(diffkT) of mc_lattice_switch (mc_moves.F90:1562-1574) for model energies (E0,E1); eta enters
 // as (x + eta) - eta exactly as in the reference
-__device__ __forceinline__ double switch_arg(const McParams& p, const WalkerView& w, double E0, double E1,
+__device__ __forceinline__ double switch_arg(const McParams& p, const WalkerScalars* sc, const double* lv, double E0, double E1,
                                              bool one, double eta, double N)
 {
-    const WalkerScalars* sc = w.sc;
     const double Es = one ? E0 : E1, En = one ? E1 : E0;
     double d;
     if (p.npt) {
         const double Vs = one ? sc->vol[0] : sc->vol[1], Vn = one ? sc->vol[1] : sc->vol[0];
-        const double lvn = one ? w.lv[1] : w.lv[0];                // log(volume(lsn)/volume(ls))
+        const double lvn = one ? lv[1] : lv[0];                    // log(volume(lsn)/volume(ls))
         d = p.beta * En - p.beta * Es + p.beta * p.pressure * (Vn - Vs) - N * lvn + eta - eta;
     } else {
         d = p.beta * En - p.beta * Es + eta - eta;
@@ -245,33 +249,40 @@ __device__ __forceinline__ double switch_arg(const McParams& p, const WalkerView
 }
 
 // mc_lattice_switch (mc_moves.F90:1536-1594), stand-alone form (cold paths)
-__device__ __noinline__ int lattice_switch_cold(unsigned char* smem, const DeviceState& S, const McParams& p, int wi,
-                                                int nlat, int rng_pos)
+__device__ __noinline__ int lattice_switch_at(WalkerScalars* sc, const double* lv, const double* rngbuf, const DeviceState& S,
+                                              const McParams& p, int wi, int rng_pos)
 {
     const int N = S.N;
-    const WalkerView w = carve_walker(smem, N, nlat);
-    WalkerScalars* sc = w.sc;
-    Rng rng{smem, N, nlat, wi, &S, &p, w.rngbuf, w.rngbase, rng_pos};
     const double eta = eta_bin(p, S.mubin, S.ginv, sc, S.weight + (size_t)wi * S.NB, sc->mu).eta;
-    const double arg = switch_arg(p, w, sc->E[0], sc->E[1], sc->ls == 1, eta, (double)N);
+    const double arg = switch_arg(p, sc, lv, sc->E[0], sc->E[1], sc->ls == 1, eta, (double)N);
     const double compare = (arg > 0.0) ? 1.0 : exp_call(arg);
-    const double x = rng.draw();
-    if (x < compare) {
-        sc->acc_s += 1;
-        sc->mu = mu_paren(p, sc, (double)N, w.lv[0]);
-        sc->ls = 3 - sc->ls;
+    const double x = rngbuf[rng_pos];
+    const double mu_new = mu_paren(p, sc, (double)N, lv[0]);
+    __syncwarp();
+    if (lane_id() == 0) {
+        if (x < compare) {
+            sc->acc_s += 1;
+            sc->mu = mu_new;
+            sc->ls = 3 - sc->ls;
+        }
+        sc->att_s += 1;
     }
-    sc->att_s += 1;
-    return rng.pos;
+    __syncwarp();
+    return rng_pos + 1;
+}
+
+__device__ __forceinline__ int lattice_switch_cold(unsigned char* smem, const DeviceState& S, const McParams& p, int wi,
+                                                   int nlat, int rng_pos)
+{
+    const WalkerView w = carve_walker(smem, S.N, nlat);
+    return lattice_switch_at(w.sc, w.lv, w.rngbuf, S, p, wi, rng_pos);
 }
 
 // mc_moves.F90:1597-1689 for the weight-generation case (not samplerun): the histogram increment
 // is done by the caller; this updates wl_factor (Swetnam / 1-over-t variants) and the weights.
-__device__ __noinline__ void update_weights(unsigned char* smem, int N, int nlat, const McParams& p,
-                                            const double* __restrict__ binwidth, double* wgt, const double* hist, int k)
+__device__ __noinline__ void update_weights_at(WalkerScalars* sc, int N, const McParams& p,
+                                               const double* __restrict__ binwidth, double* wgt, const double* hist, int k)
 {
-    const WalkerView w = carve_walker(smem, N, nlat);
-    WalkerScalars* sc = w.sc;
     const int nb = p.nbins, lane = lane_id();
     if (p.wl_swetnam) {
         // Swetnam's increment from the current histogram (:1636-1653); sequential order as in the reference
@@ -300,7 +311,7 @@ __device__ __noinline__ void update_weights(unsigned char* smem, int N, int nlat
     __syncwarp();
     // minbin = minval(weight(start:end)); weight -= minbin (:1682-1685).  Subtracting an exact 0 is a
     // no-op, and the minimum stays 0 unless bin k was a zero bin.
-    if (sc->wmin_zero && wk_old > 0.0) return;
+    if (sc->wmin_zero && wk_old > 0.0 && wk >= wk_old) return;      // a negative (Swetnam) increment may create a new minimum
     const int sb = sc->start_bin, eb = sc->end_bin;
     double mn = F_HUGE;
     for (int i = sb - 1 + lane; i < eb; i += 32) mn = fmin(mn, __ldcg(wgt + i));
@@ -310,6 +321,13 @@ __device__ __noinline__ void update_weights(unsigned char* smem, int N, int nlat
         for (int i = sb - 1 + lane; i < eb; i += 32) wgt[i] = __ldcg(wgt + i) - mn;
     sc->wmin_zero = 1;
     __syncwarp();
+}
+
+__device__ __forceinline__ void update_weights(unsigned char* smem, int N, int nlat, const McParams& p,
+                                               const double* __restrict__ binwidth, double* wgt, const double* hist, int k)
+{
+    const WalkerView w = carve_walker(smem, N, nlat);
+    update_weights_at(w.sc, N, p, binwidth, wgt, hist, k);
 }
 
 // fractional rescale of one position (mc_moves.F90:1290-1315 and its three copies): exact arithmetic
@@ -640,7 +658,7 @@ __global__ void __launch_bounds__(32, MW_MC_BLOCKS) k_mc_run(const __grid_consta
                 double arg = -diffkT;
                 if (fuse_switch && (lane == 1 || lane == 2)) {
                     const bool a = (lane == 1);
-                    arg = switch_arg(p, w, a ? Ea0 : Eb0, a ? Ea1 : Eb1, one, a ? eta_acc : eta_rej, Nd);
+                    arg = switch_arg(p, w.sc, w.lv, a ? Ea0 : Eb0, a ? Ea1 : Eb1, one, a ? eta_acc : eta_rej, Nd);
                 }
                 if (lane == 3) arg = eta_acc - p.log_unbiased_norm;
                 if (lane == 4) arg = eta_rej - p.log_unbiased_norm;

@@ -3,7 +3,7 @@
 // The two hot kernels are k_mc_run (mw_mc.cuh) and k_model_energy_all (below);
 // everything else here is start-up / bookkeeping plumbing around them.
 #include "../../include/mwgpu.h"
-#include "mw_mc2.cuh"
+#include "mw2.cuh"
 
 #include <cmath>
 #include <cfloat>
@@ -966,16 +966,19 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
         CUDA_TRY(cudaFuncSetAttribute(k_mc_run<NLAT_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_mc_run<NLAT_, NT_><<<c->W, 32, smem, c->stream>>>(c->S, c->P, ncycles);                                 \
     } while (0)
-#define MW_LAUNCH_MC2(NT_)                                                                                        \
+#define MW_LAUNCH_MC2(NLAT_, NT_)                                                                                 \
     do {                                                                                                          \
-        CUDA_TRY(cudaFuncSetAttribute(k_mc_run2<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        k_mc_run2<NT_><<<c->W, 64, smem, c->stream>>>(c->S, c->P, ncycles);                                       \
+        CUDA_TRY(cudaFuncSetAttribute(v2::k_mc_run2<NLAT_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+        v2::k_mc_run2<NLAT_, NT_><<<c->W, 32 * NLAT_, smem2, c->stream>>>(c->S, c->P, ncycles);                   \
     } while (0)
-    // two lattices, up to 64 molecules: one warp per lattice (mw_mc2.cuh); everything else: one warp per walker
-    const bool two_warps = c->nlat == 2 && ent_has_rev(c->N) && c->walker_kernel != 1;
-    if (two_warps)         { if (c->N == 48) MW_LAUNCH_MC2(48); else MW_LAUNCH_MC2(0); }
-    else if (c->nlat == 2) { if (c->N == 48) MW_LAUNCH_MC(2, 48); else MW_LAUNCH_MC(2, 0); }
-    else                   { if (c->N == 48) MW_LAUNCH_MC(1, 48); else MW_LAUNCH_MC(1, 0); }
+    // boxes of up to 64 molecules: one warp per lattice on a per-lattice shared-memory block (mw2.cuh); larger
+    // boxes (and walker_kernel == 1): the first-generation kernel, one warp per walker
+    const bool gen2 = ent_has_rev(c->N) && c->walker_kernel != 1;
+    const size_t smem2 = v2::walker_bytes(c->N, c->nlat);
+    if (gen2 && c->nlat == 2) { if (c->N == 48) MW_LAUNCH_MC2(2, 48); else MW_LAUNCH_MC2(2, 0); }
+    else if (gen2)            { if (c->N == 48) MW_LAUNCH_MC2(1, 48); else MW_LAUNCH_MC2(1, 0); }
+    else if (c->nlat == 2)    { if (c->N == 48) MW_LAUNCH_MC(2, 48); else MW_LAUNCH_MC(2, 0); }
+    else                      { if (c->N == 48) MW_LAUNCH_MC(1, 48); else MW_LAUNCH_MC(1, 0); }
 #undef MW_LAUNCH_MC
 #undef MW_LAUNCH_MC2
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
@@ -989,8 +992,8 @@ extern "C" int mwgpu_mc_set_kernel(mwgpu_ctx* c, int warps_per_walker)
 {
     if (!c) return fail("mwgpu_mc_set_kernel: NULL context");
     if (warps_per_walker < 0 || warps_per_walker > 2) return fail("mwgpu_mc_set_kernel: 0 (automatic), 1 or 2 warps per walker");
-    if (warps_per_walker == 2 && !(c->nlat == 2 && ent_has_rev(c->N)))
-        return fail("mwgpu_mc_set_kernel: the two-warp kernel needs two lattices of up to 64 molecules");
+    if (warps_per_walker == 2 && !ent_has_rev(c->N))
+        return fail("mwgpu_mc_set_kernel: the warp-per-lattice kernel needs boxes of up to 64 molecules");
     c->walker_kernel = warps_per_walker;
     return 0;
 }

@@ -7,7 +7,7 @@ timeout 3000 gpurun --timeout 1200 -- "python bench.py --steps 3 --warmup 3 --no
 ncu -i gpurun_out/prof_$tag.ncu-rep --page source --csv > gpurun_out/src_$tag.csv 2>/dev/null
 ncu -i gpurun_out/prof_$tag.ncu-rep --page raw --csv > gpurun_out/raw_$tag.csv 2>/dev/null
 (cd /tmp && cuobjdump -xelf all /root/repo/mc_water_ls_mw_b200/libmwgpu.so >/dev/null 2>&1 && nvdisasm -g -c /tmp/mwgpu.sm_100a.cubin > /tmp/dis_$tag.txt 2>/dev/null)
-K=${K:-_ZN2mw9k_mc_run2ILi48EEEvNS_11DeviceStateENS_8McParamsEi}
+K=${K:-_ZN2mw2v29k_mc_run2ILi2ELi48EEEvNS_11DeviceStateENS_8McParamsEi}
 python scripts/ncu_by_line.py gpurun_out/src_$tag.csv /tmp/dis_$tag.txt $K 60 > gpurun_out/byline_$tag.txt 2>&1 || true
 python scripts/ncu_hotset.py gpurun_out/src_$tag.csv /tmp/dis_$tag.txt $K 1966080 50 > gpurun_out/hotset_$tag.txt 2>&1 || true
 python - <<PY
