@@ -282,7 +282,8 @@ __device__ __noinline__ int compute_neighbours(const Lay<NT> Y, unsigned char* l
     return err;
 }
 
-// bmask[a] bit s <=> slot s of a's row is inside the cut-off a*sigma (molint.F90:276/454)
+// bmask[a] bit s <=> slot s of a's row is a SIGNIFICANT bond: inside RSIG < a*sigma (molint.F90:276/454 test
+// r^2 < rcsq; the shell between RSIG and the cut-off carries three-body factors below 1e-17, mw_device.cuh)
 template <int NT>
 __device__ __noinline__ void compute_bond_masks(const Lay<NT> Y, unsigned char* lb)
 {
@@ -297,7 +298,7 @@ __device__ __noinline__ void compute_bond_masks(const Lay<NT> Y, unsigned char* 
         const uint32_t e = has ? L[a * LC + lane] : 0u;
         const int j = e & 63, img = e >> 11;
         const double r2 = dist2((P[j] + V[img]) - P[a], (P[N + j] + V[IVC + img]) - P[N + a], (P[2 * N + j] + V[2 * IVC + img]) - P[2 * N + a]);
-        const uint32_t m = __ballot_sync(FULL, has && r2 < RCSQ);
+        const uint32_t m = __ballot_sync(FULL, has && r2 < CK.rsig2);
         if (lane == 0) BM[a] = m;
     }
     __syncwarp();
@@ -332,9 +333,10 @@ __device__ __noinline__ double full_energy(const Lay<NT> Y, unsigned char* lb)
             const double r2 = dist2(tx, ty, tz);
             const bool f = has && r2 < RCSQ;
             const uint32_t bm = __ballot_sync(FULL, f);
+            const uint32_t bs = __ballot_sync(FULL, has && r2 < CK.rsig2);
             const int cnt = __popc(bm);
             if (nq + cnt > RC2) break;                // cnt <= LC == RC2: a chunk always holds >= 1 molecule
-            if (lane == 0) BM[a1] = bm;
+            if (lane == 0) BM[a1] = bs;
             if (f) {
                 const int io = nq + __popc(bm & lt);
                 q[io] = tx; q[RC2 + io] = ty; q[2 * RC2 + io] = tz; q[3 * RC2 + io] = r2;
@@ -582,21 +584,24 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
     uint8_t* recj = at<uint8_t>(lb, Y.oRJ());
     int err = 0;
 
-    // ---- stage 1: lanes = slots of imol's row.  Distance tests at both positions
+    // ---- stage 1: lanes = slots of imol's row.  Distance tests at both positions: in range (own bonds, pair
+    // energies) and significant (legs of j-centred triplets)
     const int nni = at<uint8_t>(lb, Y.oNN())[imol];
     const bool has = lane < nni;
     const uint32_t e = has ? L[imol * LC + lane] : 0u;
     const int j = e & 63;
-    uint32_t bo, bn;
+    uint32_t bo, bn, so, sn;
     {
         const int img = e >> 11;
         const double pjx = P[j] + V[img], pjy = P[N + j] + V[IVC + img], pjz = P[2 * N + j] + V[2 * IVC + img];
         const double r2o = dist2(pjx - P[imol], pjy - P[N + imol], pjz - P[2 * N + imol]);
         const double r2n = dist2(pjx - T[0], pjy - T[1], pjz - T[2]);
-        bo = __ballot_sync(FULL, has && r2o < CK.rcsq);
-        bn = with_new ? __ballot_sync(FULL, has && r2n < CK.rcsq) : 0u;
+        bo = __ballot_sync(FULL, has && r2o < CK.rcc2);
+        so = __ballot_sync(FULL, has && r2o < CK.rsig2);
+        bn = with_new ? __ballot_sync(FULL, has && r2n < CK.rcc2) : 0u;
+        sn = with_new ? __ballot_sync(FULL, has && r2n < CK.rsig2) : 0u;
     }
-    mo = bo; mn = bn;
+    mo = so; mn = sn;
     // slots of row j that point back at imol (any image) are no candidates: the k == i entries of the reference's
     // list B are either filtered (cos = 1) or covered by the factor 3 of the i-centred pairs.  Cells narrower than
     // twice the list radius hold two images of one molecule in most rows; a row is sorted by molecule, so the
@@ -621,16 +626,18 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
     const int npass = (__popc(bo) + __popc(bn) < RC2) ? 1 : 2;
 #pragma unroll 1
     for (int pass = 0; pass < npass; ++pass) {
-        const uint32_t bop = (npass == 1 || pass == 0) ? bo : 0u, bnp = (npass == 1 || pass == 1) ? bn : 0u;
+        const bool useo = (npass == 1 || pass == 0), usen = (npass == 1 || pass == 1);
+        const uint32_t bop = useo ? bo : 0u, bnp = usen ? bn : 0u;
         const bool fo = (bop >> lane) & 1u, fn = (bnp >> lane) & 1u;
+        const bool go = useo && ((so >> lane) & 1u), gn = usen && ((sn >> lane) & 1u);   // significant legs
         const int no = __popc(bop), nw = __popc(bnp), nown = no + nw;
         const uint32_t ro = __popc(bop & lt), rn = no + __popc(bnp & lt);
         if (nown >= RC2) { err |= ERR_BOND_OVERFLOW; break; }            // every slot of the row in range: flagged
         const uint32_t own = (uint32_t)lane | ((uint32_t)imol << 5);
         if (fo) { items[ro] = own | (ro << 11) | IT_OLD; recj[ro] = (uint8_t)j; }
         if (fn) { items[rn] = own | (rn << 11) | IT_NEW; recj[rn] = (uint8_t)j; }
-        const uint32_t bmj0 = (fo || fn) ? (BM[j] & ~excl) : 0u;
-        const uint32_t dbase = ((uint32_t)j << 5) | ((fo ? ro : IT_NONE) << 11) | ((fn ? rn : IT_NONE) << 16);
+        const uint32_t bmj0 = (go || gn) ? (BM[j] & ~excl) : 0u;
+        const uint32_t dbase = ((uint32_t)j << 5) | ((go ? ro : IT_NONE) << 11) | ((gn ? rn : IT_NONE) << 16);
 
         // ---- rounds: all centres at once when their candidates fit the table (always, at physical densities),
         // else two centre lanes per round
@@ -682,11 +689,11 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
                 const double ty_ = (P[N + k] + V[IVC + im2]) - cp[cs];
                 const double tz = (P[2 * N + k] + V[2 * IVC + im2]) - cp[2 * cs];
                 const double sq0 = dist2(tx, ty_, tz);
-                const bool ok = in && (sq0 < CK.rcsq);
+                const bool ok = in && (sq0 < CK.rcc2);
                 const double sq = ok ? sq0 : CK.ss;                    // any length inside the cut-off
                 double ir, isr;
                 bond_radial(sq, ir, isr);
-                const double e1 = exp_fast(CK.sig02 * isr);            // exp(sigma*isr) = e1^5, exp(gamma*sigma*isr) = e1^6
+                const double e1 = exp_nc(CK.sig02 * isr);              // exp(sigma*isr) = e1^5, exp(gamma*sigma*isr) = e1^6
                 const double e_2 = e1 * e1, e_4 = e_2 * e_2;
                 const double g = e_4 * e_2;
                 const double ux = tx * ir, uy = ty_ * ir, uz = tz * ir;

@@ -44,6 +44,15 @@ constexpr double AEPS    = BIGA * EPSILON;
 constexpr double LEPS    = LAMBDA * EPSILON;
 constexpr double SS      = SIGMA * SIGMA;
 constexpr double F_HUGE  = 1.7976931348623157e308;
+// Two radii just inside the cut-off, used by the second-generation walker kernel (mw2.cuh):
+//  * RCC: exp(0.2*sigma/(r - a*sigma)) < exp(-700) beyond it, so every energy term of such a bond (its 5th / 6th
+//    power) is an exact 0.0 in fp64 -- for the oracle's exp() as well; evaluating only r < RCC changes no bit and
+//    frees the exponential from its underflow clamp;
+//  * RSIG: beyond it the three-body radial factor g = exp(gamma*sigma/(r - a*sigma)) is below 1e-17, and a j-centred
+//    triplet built on that bond is below 4e-18 Ha -- under the rounding of the sums it would be added to (local
+//    energies are ~4e-2 Ha).  Such bonds are not enumerated as triplet legs; pair energies always use the full range.
+constexpr double RCC     = RC - 0.2 * SIGMA / 700.0;
+constexpr double RSIG    = RC - GS / 39.14394658089878;        // ln(1e17)
 
 // ---------------------------------------------------------------- capacities
 #ifndef MW_LC
@@ -139,6 +148,7 @@ struct EnergyConsts {
     double e2, e3, e4, e5, e6, e7, e8, e9, e10, e11, e12, e13;   // 1/k!
     double q3125, q375;
     double rc, rc2, rcsq, sig02, ss, bigb, aeps, leps, gs, cos0, c099;
+    double rcc2, rsig2;
 };
 __constant__ EnergyConsts CK = {
     1.4426950408889634, 6755399441055744.0, 6.93147180369123816490e-01, 1.90821492927058770002e-10, -708.0,
@@ -147,6 +157,7 @@ __constant__ EnergyConsts CK = {
     2.505210838544172e-08, 2.08767569878681e-09, 1.6059043836821613e-10,
     0.3125, 0.375,
     RC, RC * RC, RCSQ, 0.2 * SIGMA, SS, BIGB, AEPS, LEPS, GS, COS0, 0.99,
+    RCC * RCC, RSIG * RSIG,
 };
 
 // ---------------------------------------------------------------- fast fp64 math for the ENERGY arithmetic
@@ -209,6 +220,33 @@ __device__ __forceinline__ double exp_fast(double x)
     const double p = fma(c1, r8, c0);
     const double s = __hiloint2double((n + 1023) << 20, 0);               // 2^n, n in [-1022, 1023]
     return (x < CK.xmin) ? 0.0 : p * s;
+}
+
+// the same for -708 <= x (no underflow clamp): arguments of bonds inside RCC
+__device__ __forceinline__ double exp_nc(double x)
+{
+    const double t = fma(x, CK.log2e, CK.magic);
+    const int n = __double2loint(t);
+    const double fn = t - CK.magic;
+    double r = fma(-fn, CK.ln2hi, x);
+    r = fma(-fn, CK.ln2lo, r);
+    const double r2 = r * r;
+    const double a0 = 1.0 + r;
+    const double a1 = fma(CK.e3, r, CK.e2);
+    const double a2 = fma(CK.e5, r, CK.e4);
+    const double a3 = fma(CK.e7, r, CK.e6);
+    const double a4 = fma(CK.e9, r, CK.e8);
+    const double a5 = fma(CK.e11, r, CK.e10);
+    const double a6 = fma(CK.e13, r, CK.e12);
+    const double r4 = r2 * r2;
+    const double b0 = fma(a1, r2, a0);
+    const double b1 = fma(a3, r2, a2);
+    const double b2 = fma(a5, r2, a4);
+    const double r8 = r4 * r4;
+    const double c0 = fma(b1, r4, b0);
+    const double c1 = fma(a6, r4, b2);
+    const double p = fma(c1, r8, c0);
+    return p * __hiloint2double((n + 1023) << 20, 0);
 }
 
 // one shared copy for the call sites outside the bond loops (acceptance, lattice switch): code size matters
