@@ -70,7 +70,8 @@ struct Lay {
     static constexpr int sCTL = sGI + 32;                            // [8] int
     static constexpr int sXCH = sCTL + 32;                           // [8] fp64 energies exchanged between the warps
     static constexpr int sLV = sXCH + 64;                            // [2] log(V1/V2), log(V2/V1)
-    static constexpr int SB = sLV + 16;
+    static constexpr int sKV = sLV + 16;                             // [4] volume terms of the switch / of ls_mu (refresh_kv)
+    static constexpr int SB = sKV + 32;
     __host__ __device__ __forceinline__ size_t bytes(int nlat) const { return (size_t)nlat * LB() + SB; }
 };
 static_assert(sizeof(WalkerScalars) == 208, "layout");
@@ -549,6 +550,21 @@ __device__ __noinline__ int volume_move(const Lay<NT> Y, unsigned char* smem, co
     return rng_pos;
 }
 
+// The parts of the lattice-switch exponent (mc_moves.F90:1562-1574) and of ls_mu (:1583-1585) that only change
+// with the cell: -diffkT(switch 1->2) = -(beta*(E2-E1) + kv[0]), -diffkT(2->1) = -(beta*(E1-E2) + kv[1]),
+// ls_mu = beta*(E1-E2) + kv[2].  Energy-class arithmetic (free association): lane 0 of warp 0 refreshes
+// them at kernel start and after every volume move.
+__device__ __forceinline__ void refresh_kv(const McParams& p, const WalkerScalars* sc, const double* lv, double* kv, double Nd)
+{
+    const double bp = p.beta * p.pressure;
+    double sh = 0.0;
+    if (p.leshift) sh = p.beta * (sc->refH[0] - sc->refH[1]);
+    const double dv = sc->vol[0] - sc->vol[1];
+    kv[0] = (p.npt ? (-bp * dv - Nd * lv[1]) : 0.0) + sh;
+    kv[1] = (p.npt ? (bp * dv - Nd * lv[0]) : 0.0) - sh;
+    kv[2] = bp * dv - sh - Nd * lv[0];
+}
+
 // sum two per-lane accumulators over the warp and broadcast both totals
 __device__ __forceinline__ void reduce2(double& a0, double& a1)
 {
@@ -826,6 +842,7 @@ __global__ void __launch_bounds__(32 * NLAT, MW2_BLOCKS * (3 - NLAT)) k_mc_run2(
     uint64_t* rngbase = at<uint64_t>(sb, Lay<NT>::sRB);
     double* rngbuf = at<double>(sb, Lay<NT>::sRNG);
     double* lv = at<double>(sb, Lay<NT>::sLV);
+    double* kv = at<double>(sb, Lay<NT>::sKV);
     int* ctl = at<int>(sb, Lay<NT>::sCTL);
     const double Nd = (double)N;
     double* wgt = S.weight + (size_t)wi * S.NB;
@@ -844,7 +861,10 @@ __global__ void __launch_bounds__(32 * NLAT, MW2_BLOCKS * (3 - NLAT)) k_mc_run2(
         __syncwarp();
         if (lane == 0) {
             *rngbase = idx & ~(uint64_t)1;
-            if (NLAT == 2) { lv[0] = log(sc->vol[0] / sc->vol[1]); lv[1] = log(sc->vol[1] / sc->vol[0]); }
+            if (NLAT == 2) {
+                lv[0] = log(sc->vol[0] / sc->vol[1]); lv[1] = log(sc->vol[1] / sc->vol[0]);
+                refresh_kv(p, sc, lv, kv, Nd);
+            }
             ctl[CTL_STOP] = (err & ERR_PROB) ? 1 : 0;
         }
         rng_pos = (int)(idx & 1);
@@ -854,6 +874,7 @@ __global__ void __launch_bounds__(32 * NLAT, MW2_BLOCKS * (3 - NLAT)) k_mc_run2(
 
     bool stop = ctl[CTL_STOP] != 0;
     int bpar = 0;                                                       // batch parity (both warps count alike)
+    int klast = p.nbins / 2 + 1;                                        // bin of the previous move's order parameter
     for (int cyc = 0; cyc < ncycles && !stop; ++cyc) {
         const int cycle = cycle0 + cyc + 1;
         if (lat == 0) {
@@ -944,7 +965,7 @@ __global__ void __launch_bounds__(32 * NLAT, MW2_BLOCKS * (3 - NLAT)) k_mc_run2(
                         // three weight look-ups in parallel lanes: eta(mu), eta(mu_acc), eta(mu_rej)
                         const double mine = (lane == 0) ? mu_old : (lane == 1) ? mu_acc : mu_rej;
                         EtaBin eb; eb.eta = 0.0; eb.k = 0;
-                        if (lane < 3) eb = eta_bin(p, S.mubin, S.ginv, sc, wgt, mine);
+                        if (lane < 3) eb = eta_bin_near(p, S, sc, wgt, mine, klast);
                         const double eta_old = __shfl_sync(FULL, eb.eta, 0);
                         eta_acc = __shfl_sync(FULL, eb.eta, 1); eta_rej = __shfl_sync(FULL, eb.eta, 2);
                         k_acc = __shfl_sync(FULL, eb.k, 1); k_rej = __shfl_sync(FULL, eb.k, 2);
@@ -954,13 +975,22 @@ __global__ void __launch_bounds__(32 * NLAT, MW2_BLOCKS * (3 - NLAT)) k_mc_run2(
                     // lanes 3/4 unbiased-histogram factor if accepted / rejected
                     double arg = -diffkT;
                     if (fuse_switch && (lane == 1 || lane == 2)) {
-                        const bool a = (lane == 1);
-                        arg = switch_arg(p, sc, lv, a ? Ea0 : Eb0, a ? Ea1 : Eb1, one, a ? eta_acc : eta_rej, Nd);
+                        // -diffkT of mc_lattice_switch (:1562-1574) for the energies after an accepted / a rejected move
+                        const double dEs = (lane == 1) ? (Ea1 - Ea0) : (Eb1 - Eb0);     // E(2) - E(1)
+                        arg = one ? -(p.beta * dEs + kv[0]) : (p.beta * dEs - kv[1]);
                     }
                     if (lane == 3) arg = eta_acc - p.log_unbiased_norm;
                     if (lane == 4) arg = eta_rej - p.log_unbiased_norm;
-                    const double ex = (arg > 0.0 && lane < 3) ? 1.0 : exp_call(fmin(arg, 700.0));
+                    const double ex = (arg > 0.0 && lane < 3) ? 1.0 : exp_fast(fmin(arg, 700.0));
                     const bool accepted = u[6] < __shfl_sync(FULL, ex, 0);                      // :1145-1146
+                    const double En0 = accepted ? Ea0 : Eb0, En1 = accepted ? Ea1 : Eb1;
+                    bool sw = false;
+                    double mu_new = accepted ? mu_acc : mu_rej;
+                    if (fuse_switch) {
+                        // ====================== mc_lattice_switch (mc_moves.F90:1536-1594) ======================
+                        sw = u[7] < __shfl_sync(FULL, ex, accepted ? 1 : 2);
+                        if (sw) mu_new = p.beta * (En0 - En1) + kv[2];          // ls_mu from scratch (:1583-1585)
+                    }
                     __syncwarp();
                     if (lane == 0) {
                         if (accepted) {
@@ -969,15 +999,20 @@ __global__ void __launch_bounds__(32 * NLAT, MW2_BLOCKS * (3 - NLAT)) k_mc_run2(
                             if (dmu < sc->min_dmu) sc->min_dmu = dmu;
                             if (dmu > sc->max_dmu) sc->max_dmu = dmu;
                             sc->E[0] = Ea0;
-                            if (NLAT == 2) { sc->E[1] = Ea1; sc->mu = mu_acc; }
-                        } else if (NLAT == 2) {
-                            sc->mu = mu_rej;
+                            if (NLAT == 2) sc->E[1] = Ea1;
                         }
+                        if (NLAT == 2) sc->mu = mu_new;
                         sc->att_r += 1;
+                        if (fuse_switch) {
+                            if (sw) { sc->acc_s += 1; sc->ls = 3 - sc->ls; }
+                            sc->att_s += 1;
+                        }
                     }
                     __syncwarp();
                     // ====================== mc_update_wl_bins (mc_moves.F90:1597-1689) ======================
+                    // (the bin of the order parameter BEFORE the switch of this move, as in the reference's order)
                     const int kb = accepted ? k_acc : k_rej;
+                    klast = kb;
                     if (bins_on && kb >= 1 && kb <= p.nbins) {
                         const double c = __ldg(S.hinc + kb - 1);
                         if (lane == 0) atomicAdd(hist + kb - 1, c);
@@ -988,18 +1023,7 @@ __global__ void __launch_bounds__(32 * NLAT, MW2_BLOCKS * (3 - NLAT)) k_mc_run2(
                             update_weights_at(sc, N, p, S.binwidth, wgt, hist, kb);
                         }
                     }
-                    // ====================== mc_lattice_switch (mc_moves.F90:1536-1594) ======================
-                    if (fuse_switch) {
-                        const double compare = __shfl_sync(FULL, ex, accepted ? 1 : 2);
-                        const bool sw = u[7] < compare;
-                        const double mu_sw = mu_paren(p, sc, Nd, lv[0]);
-                        __syncwarp();
-                        if (lane == 0) {
-                            if (sw) { sc->acc_s += 1; sc->mu = mu_sw; sc->ls = 3 - sc->ls; }
-                            sc->att_s += 1;
-                        }
-                        __syncwarp();
-                    } else if (do_switch) {
+                    if (do_switch && !fuse_switch) {
                         // weights may have moved in update_weights: the reference looks eta up again
                         lattice_switch_at(sc, lv, rngbuf, S, p, wi, rng_pos + m * D + 7);
                     }
@@ -1037,6 +1061,7 @@ __global__ void __launch_bounds__(32 * NLAT, MW2_BLOCKS * (3 - NLAT)) k_mc_run2(
                     rng_pos += 1;
                     if (xi < p.volP) {
                         rng_pos = volume_move<NLAT, NT>(Y, smem, S, p, wi, rng_pos);
+                        if (NLAT == 2) { if (lane == 0) refresh_kv(p, sc, lv, kv, Nd); __syncwarp(); }
                         const EtaBin eb = eta_bin(p, S.mubin, S.ginv, sc, wgt, sc->mu);
                         if (bins_on && eb.k >= 1 && eb.k <= p.nbins) {
                             const double c = __ldg(S.hinc + eb.k - 1);

@@ -57,6 +57,7 @@ struct DeviceState {
     double* binwidth;   // [NB]
     double* ginv;       // [NB]  ginv[k-1] = 2/(binwidth(k) + binwidth(k+1)), k = 1..NB-1
     double* hinc;       // [NB]  av_binwidth/binwidth(k): histogram increment of bin k (mc_moves.F90:1621)
+    double* edge;       // [NB+1] bin edges of the grid: bin k (1-based) spans edge[k-1] .. edge[k] (mc_moves.F90:570-656)
     const double* fifo; // host-supplied random numbers (walker 0 only)
     unsigned long long fifo_len;
     // therm rows (main.f90:200-223): what the reference writes every file_output_int cycles, recorded by
@@ -176,36 +177,36 @@ __device__ __noinline__ int bin_exact(double arg, double lr) { return (int)(log(
 // call.  The two sign branches of mu_to_bin share one log: for mu > 0, mu - 0.5 == |mu| - 0.5.
 // wgt is this walker's weight array (global memory, read through L2 because the same warp
 // updates it when generating weights).
-__device__ __noinline__ EtaBin eta_bin(const McParams& p, const double* __restrict__ mubin,
-                                       const double* __restrict__ binwidth /* = DeviceState::ginv */, const WalkerScalars* sc,
-                                       const double* wgt, double mu)
+__device__ __forceinline__ int mu_to_bin_dev(const McParams& p, double mu)
 {
-    EtaBin r;
     const int nb = p.nbins;
-    int k;
-    if (fabs(mu) <= 0.5) {
-        k = nb / 2 + 1;
-    } else {
-        const bool pos = mu > 0.0;
-        // (|mu| - 0.5)*(1 - r)/a with (1 - r)/a precomputed: identical to the reference's order for a == 1
-        const double arg = 1.0 - (fabs(mu) - 0.5) * (pos ? p.c_pos : p.c_neg);
-        // int(log(arg)/log(r)): fast logarithm; the library log and the true division decide only
-        // when the quotient is within 1e-7 of an integer
-        const double y = log_fast(arg) * (pos ? p.inv_log_r_pos : p.inv_log_r_neg);
-        int t = (int)y;
-        if (fabs(y - rint(y)) < 1e-7 || !(arg > 0.0)) t = bin_exact(arg, pos ? p.log_r_pos : p.log_r_neg);
-        k = pos ? nb / 2 + 2 + t : nb / 2 - t;
-    }
-    r.k = k;
-    if (!sc->in_window) { r.eta = 0.0; return r; }          // undefined in the reference (:913); defined as 0
-    if (mu < sc->mu_lo || mu > sc->mu_hi) { r.eta = F_HUGE; return r; }
+    if (fabs(mu) <= 0.5) return nb / 2 + 1;
+    const bool pos = mu > 0.0;
+    // (|mu| - 0.5)*(1 - r)/a with (1 - r)/a precomputed: identical to the reference's order for a == 1
+    const double arg = 1.0 - (fabs(mu) - 0.5) * (pos ? p.c_pos : p.c_neg);
+    // int(log(arg)/log(r)): fast logarithm; the library log and the true division decide only
+    // when the quotient is within 1e-7 of an integer
+    const double y = log_fast(arg) * (pos ? p.inv_log_r_pos : p.inv_log_r_neg);
+    int t = (int)y;
+    if (fabs(y - rint(y)) < 1e-7 || !(arg > 0.0)) t = bin_exact(arg, pos ? p.log_r_pos : p.log_r_neg);
+    return pos ? nb / 2 + 2 + t : nb / 2 - t;
+}
+
+// eta_weight (mc_moves.F90:893-964) for the bin k = mu_to_bin(mu)
+__device__ __forceinline__ double eta_of_bin(const McParams& p, const double* __restrict__ mubin,
+                                             const double* __restrict__ binwidth /* = DeviceState::ginv */, const WalkerScalars* sc,
+                                             const double* wgt, double mu, int k)
+{
+    const int nb = p.nbins;
+    if (!sc->in_window) return 0.0;                          // undefined in the reference (:913); defined as 0
+    if (mu < sc->mu_lo || mu > sc->mu_hi) return F_HUGE;
     k = min(max(k, 1), nb);                                  // memory safety at mu == mu_max (reference would overrun)
     const double* w = wgt - 1;
     const double* mb = mubin - 1;
     // fixed weights (sample runs) are read-only for the whole launch: take them through the L1; when the
     // same warp updates them every move (weight generation) they come from the L2
     const bool ro = p.samplerun != 0;
-    if (!p.eta_interp) { r.eta = ro ? __ldg(w + k) : __ldcg(w + k); return r; }
+    if (!p.eta_interp) return ro ? __ldg(w + k) : __ldcg(w + k);
     int ka, kb, kr;                                          // gradient between bins ka<kb, anchored at kr
     if (k == sc->start_bin)      { ka = k; kb = k + 1; kr = k; }
     else if (k == sc->end_bin)   { ka = k - 1; kb = k; kr = k; }
@@ -215,7 +216,37 @@ __device__ __noinline__ EtaBin eta_bin(const McParams& p, const double* __restri
     const double wa = ro ? __ldg(w + ka) : __ldcg(w + ka), wb = ro ? __ldg(w + kb) : __ldcg(w + kb);
     const double g = (wb - wa) * __ldg(binwidth + ka - 1);       // binwidth = the 2/(bw(ka)+bw(kb)) table here
     const double wr = (kr == ka) ? wa : wb;
-    r.eta = wr + (mu - __ldg(mb + kr)) * g;
+    return wr + (mu - __ldg(mb + kr)) * g;
+}
+
+__device__ __noinline__ EtaBin eta_bin(const McParams& p, const double* __restrict__ mubin,
+                                       const double* __restrict__ binwidth /* = DeviceState::ginv */, const WalkerScalars* sc,
+                                       const double* wgt, double mu)
+{
+    EtaBin r;
+    r.k = mu_to_bin_dev(p, mu);
+    r.eta = eta_of_bin(p, mubin, binwidth, sc, wgt, mu, r.k);
+    return r;
+}
+
+// The same with the bin taken from the table of bin edges, starting at a guess (the bin of the previous move: mu
+// moves by a few kT per move).  mu_to_bin's closed form and the edges agree to ~1e-12; whenever mu is within 1e-9
+// of an edge -- or further than one bin from the guess -- the closed form decides, so the bin is always the
+// reference's.
+__device__ __noinline__ int mu_to_bin_call(const McParams& p, double mu) { return mu_to_bin_dev(p, mu); }
+
+__device__ __forceinline__ EtaBin eta_bin_near(const McParams& p, const DeviceState& S, const WalkerScalars* sc,
+                                               const double* wgt, double mu, int kguess)
+{
+    EtaBin r;
+    const int nb = p.nbins;
+    int k = min(max(kguess, 1), nb);
+    double lo = __ldg(S.edge + k - 1), hi = __ldg(S.edge + k);
+    if (mu >= hi && k < nb) { ++k; lo = hi; hi = __ldg(S.edge + k); }
+    else if (mu < lo && k > 1) { --k; hi = lo; lo = __ldg(S.edge + k - 1); }
+    if (!((mu > lo + 1e-9) && (mu < hi - 1e-9))) k = mu_to_bin_call(p, mu);
+    r.k = k;
+    r.eta = eta_of_bin(p, S.mubin, S.ginv, sc, wgt, mu, k);
     return r;
 }
 

@@ -152,7 +152,7 @@ extern "C" void mwgpu_destroy(mwgpu_ctx* c)
     DeviceState& S = c->S;
     void* ptrs[] = {S.pos, S.ref, S.cell, S.recip, S.refcell, S.iv, S.niv, S.list, S.nn, S.scal,
                     S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.transcount, S.mubin,
-                    S.binwidth, S.ginv, S.hinc, c->stage, c->out, c->iout, c->delta, c->fifo,
+                    S.binwidth, S.ginv, S.hinc, S.edge, c->stage, c->out, c->iout, c->delta, c->fifo,
                     c->book, c->skip, c->gather, S.therm, S.therm_n};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -755,7 +755,7 @@ extern "C" int mwgpu_mc_init(mwgpu_ctx* c, const mwgpu_mc_params* up, int first_
     const double a_pos = 1.0, a_neg = 1.0;
     const int Ns = nb / 2;
     const double r_pos = gp_ratio(a_pos, s_pos, Ns), r_neg = gp_ratio(a_neg, s_neg, Ns);
-    std::vector<double> mu_bin(nb), bw(nb);
+    std::vector<double> mu_bin(nb), bw(nb), edge(nb + 1);
     {
         double mu_u = -0.5, mu_l;
         int k = 0;
@@ -763,6 +763,7 @@ extern "C" int mwgpu_mc_init(mwgpu_ctx* c, const mwgpu_mc_params* up, int first_
             mu_l = mu_u - a_neg * powi(r_neg, k);
             mu_bin[ibin - 1] = 0.5 * (mu_u + mu_l);
             bw[ibin - 1] = mu_u - mu_l;
+            edge[ibin - 1] = mu_l; edge[ibin] = mu_u;
             mu_u = mu_l; ++k;
         }
         mu_bin[nb / 2] = 0.0; bw[nb / 2] = 1.0;
@@ -771,6 +772,7 @@ extern "C" int mwgpu_mc_init(mwgpu_ctx* c, const mwgpu_mc_params* up, int first_
             mu_u = mu_l + a_pos * powi(r_pos, k);
             mu_bin[ibin - 1] = 0.5 * (mu_u + mu_l);
             bw[ibin - 1] = mu_u - mu_l;
+            edge[ibin - 1] = mu_l; edge[ibin] = mu_u;
             mu_l = mu_u; ++k;
         }
     }
@@ -805,17 +807,19 @@ extern "C" int mwgpu_mc_init(mwgpu_ctx* c, const mwgpu_mc_params* up, int first_
 
     // ---- (re)allocate per-walker bin arrays
     DeviceState& S = c->S;
-    void* old[] = {S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.mubin, S.binwidth, S.ginv, S.hinc, c->delta};
+    void* old[] = {S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.mubin, S.binwidth, S.ginv, S.hinc, S.edge, c->delta};
     for (void* p : old) if (p) cudaFree(p);
     S.NB = nb;
     int rc = 0;
     rc |= dalloc(&S.weight, (size_t)W * nb); rc |= dalloc(&S.hist, (size_t)W * nb); rc |= dalloc(&S.uhist, (size_t)W * nb);
     rc |= dalloc(&S.wbase, (size_t)W * nb); rc |= dalloc(&S.hbase, (size_t)W * nb); rc |= dalloc(&S.ubase, (size_t)W * nb);
     rc |= dalloc(&S.mubin, nb); rc |= dalloc(&S.binwidth, nb); rc |= dalloc(&S.ginv, nb); rc |= dalloc(&S.hinc, nb);
+    rc |= dalloc(&S.edge, nb + 1);
     rc |= dalloc(&c->delta, (size_t)3 * c->NBP);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpy(S.mubin, mu_bin.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(S.binwidth, bw.data(), sizeof(double) * nb, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(S.edge, edge.data(), sizeof(double) * (nb + 1), cudaMemcpyHostToDevice));
     {
         std::vector<double> tab(nb, 0.0);
         for (int k = 0; k + 1 < nb; ++k) tab[k] = 2.0 / (bw[k] + bw[k + 1]);
