@@ -744,9 +744,11 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
         }
 
         // ---- triplets centred on imol: all unordered pairs of bond records of one variant (rotation pairing:
-        // record at position pos of a segment of n pairs with (pos + d) mod n, d = 1 .. n/2)
+        // record at position pos of a segment of n pairs with (pos + d) mod n, d = 1 .. n/2).  Up to 16 records
+        // (nearly always) take two lanes each: lanes 0-15 the odd steps d, lanes 16-31 the even ones.
         {
-            const int r = lane;
+            const int stride = (nown <= 16) ? 2 : 1;
+            const int r = (stride == 2) ? (lane & 15) : lane;
             const bool act = r < nown;
             const bool sg = r >= no;
             const int n = act ? (sg ? nw : no) : 0, pos = sg ? r - no : r;
@@ -759,7 +761,7 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
             const int maxd = max(no, nw) >> 1;
             double tb = 0.0;
 #pragma unroll 1
-            for (int d = 1; d <= maxd; ++d) {
+            for (int d = (stride == 2) ? 1 + (lane >> 4) : 1; d <= maxd; d += stride) {
                 int c = r + d;
                 c = (c >= send) ? c - n : c;
                 const bool on = (d <= half) && !(even && d == half && pos >= half);
