@@ -138,7 +138,7 @@ SYMBOLS = {
 
 def build(force: bool = False) -> str:
     """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("mwgpu.cu", "mw2.cuh", "mw_mc.cuh", "mw_device.cuh", "Makefile")]
+    srcs = [os.path.join(CSRC, f) for f in ("mwgpu.cu", "mw2.cuh", "mw2_energy.cuh", "mw_mc.cuh", "mw_device.cuh", "Makefile")]
     srcs.append(os.path.join(os.path.dirname(_PKG), "include", "mwgpu.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:

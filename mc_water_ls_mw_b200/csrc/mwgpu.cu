@@ -4,6 +4,7 @@
 // everything else here is start-up / bookkeeping plumbing around them.
 #include "../../include/mwgpu.h"
 #include "mw2.cuh"
+#include "mw2_energy.cuh"
 
 #include <cmath>
 #include <cfloat>
@@ -50,6 +51,7 @@ struct mwgpu_ctx {
     mwgpu_mc_params user{};
     bool mc_ready = false, energy_ready = false;
     int walker_kernel = 0;         // 0: automatic, 1: one warp per walker, 2: two warps per walker (one per lattice)
+    int energy_kernel = 0;         // batched full energy: 0 flattened-entry kernel (mw2_energy.cuh), 1 first generation
     int first_rank = 0, size = 1;
     double* stage = nullptr;       // device staging for layout conversion: [W][nlat][N][3] x2 + cells
     size_t stage_doubles = 0;
@@ -695,10 +697,19 @@ __global__ void __launch_bounds__(32) k_model_energy_all(const __grid_constant__
 extern "C" int mwgpu_compute_model_energy_all(mwgpu_ctx* c, double* energies)
 {
     if (int rc = check_ctx(c, 0, false)) return rc;
-    const size_t smem = walker_smem_bytes(c->N, 1);
-    CUDA_TRY(cudaFuncSetAttribute(k_model_energy_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)v2::ELay(c->N).bytes();
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    k_model_energy_all<<<c->W * c->nlat, 32, smem, c->stream>>>(c->S, c->out);
+    if (c->energy_kernel == 1) {
+        const size_t smem1 = walker_smem_bytes(c->N, 1);
+        CUDA_TRY(cudaFuncSetAttribute(k_model_energy_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        k_model_energy_all<<<c->W * c->nlat, 32, smem1, c->stream>>>(c->S, c->out);
+    } else if (c->N == 48) {
+        CUDA_TRY(cudaFuncSetAttribute(v2::k_model_energy2<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        v2::k_model_energy2<48><<<c->W * c->nlat, 32, smem, c->stream>>>(c->S, c->out);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(v2::k_model_energy2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        v2::k_model_energy2<0><<<c->W * c->nlat, 32, smem, c->stream>>>(c->S, c->out);
+    }
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     c->launches++;
     if (int rc = finish(c, false)) return rc;
@@ -999,6 +1010,7 @@ extern "C" int mwgpu_mc_set_kernel(mwgpu_ctx* c, int warps_per_walker)
     if (warps_per_walker == 2 && !ent_has_rev(c->N))
         return fail("mwgpu_mc_set_kernel: the warp-per-lattice kernel needs boxes of up to 64 molecules");
     c->walker_kernel = warps_per_walker;
+    c->energy_kernel = (warps_per_walker == 1) ? 1 : 0;       // generation 1 keeps its own batched energy kernel
     return 0;
 }
 
