@@ -14,12 +14,17 @@
 !      and the comms_allreduce_* calls at :264-268 by                         !
 !          call mwgpu_check(mwgpu_comms_allreduce_bins(gpu_ctx),'mc_cycle')   !
 !          call mc_gpu_pull_bins()                                            !
-!  (3) mc_monitor_stats / mc_check_flatness / mc_check_chain_synchronisation  !
-!      / mc_checkpoint_write start with  call mc_gpu_pull()  so that the host  !
-!      copies of ljr, hmatrix, model_energy, counters, histogram and weight   !
-!      are current; routines that MODIFY state (monitor: step sizes + energy  !
-!      re-sync :1722-1792; flatness: histogram reset / wl_factor :1977-2106;  !
-!      chain sync :2262-2402) end with  call mc_gpu_push().                    !
+!  (3) the periodic bookkeeping keeps its log lines and files on the host but  !
+!      its STATE effects happen on the device -- there is no host-side path   !
+!      that modifies the state and pushes it back (the device owns step       !
+!      sizes, counters, running averages, energies, lists, *_last_sync bases):!
+!        mc_monitor_stats               -> call mc_gpu_monitor()      (below) !
+!        mc_check_chain_synchronisation -> call mc_gpu_chain_sync()   (below) !
+!        mc_check_flatness              -> call mc_gpu_check_flatness()       !
+!        mc_compute_deltaG_from_hist    -> call mc_gpu_deltaG()               !
+!      mc_checkpoint_write / dcd output only READ:  call mc_gpu_pull()  first. !
+!      mc_gpu_push() is for start-up and restart only (it rebuilds the lists  !
+!      and the energies as energy_init does).                                 !
 !                                                                             !
 ! Everything else in mc_moves.F90 / main.f90 / io.f90 is untouched: program   !
 ! entry, input decks and output formats stay as they are.                     !
@@ -45,7 +50,7 @@
     p%npt = merge(1,0,mc_ensemble=='npt')
     p%mc_max_trans = mc_max_trans        ; p%mc_dv_max = mc_dv_max        ! Bohr (io.f90:185-186)
     p%mc_target_ratio = mc_target_ratio
-    p%wl_factor = orig_wl_factor         ; p%wl_swetnam = merge(1,0,wl_schedule==2)
+    p%wl_factor = orig_wl_factor         ; p%wl_swetnam = merge(1,0,wl_swetnam)   ! userparams.f90:37 (wl_schedule travels in mwgpu_flat_params)
     p%wl_alpha = wl_alpha
     p%eta_interp = merge(1,0,eta_interp) ; p%samplerun = merge(1,0,samplerun)
     p%leshift = merge(1,0,leshift)       ; p%nbins = nbins
@@ -117,7 +122,8 @@
   end subroutine mc_gpu_pull
 
   subroutine mc_gpu_push()
-    ! host -> device after host-side bookkeeping changed the state
+    ! host -> device at start-up / after a checkpoint load ONLY: re-initialises lists and energies like energy_init.
+    ! The periodic bookkeeping never goes through here (see (3) above).
     use iso_c_binding
     use mwgpu
     use energy,     only : gpu_ctx,energy_push_to_device
@@ -130,6 +136,38 @@
     call mwgpu_check(mwgpu_mc_set_wl_factor(gpu_ctx,0_c_int,wl_factor,merge(1_c_int,0_c_int,wl_invt_active)),'mc_gpu_push')
     call mwgpu_check(mwgpu_mc_set_active_lattice(gpu_ctx,0_c_int,int(ls,c_int)),'mc_gpu_push')
   end subroutine mc_gpu_push
+
+  subroutine mc_gpu_monitor()
+    ! mc_monitor_stats (mc_moves.F90:1692-1850): the host prints what it always printed from the pulled
+    ! counters; step-size adjustment (:1722-1732), energy re-synchronisation (:1786-1792), counter reset
+    ! (:1797-1810) and the all-reduce of histogram / weights / unbiased histogram (:1813-1821) run on the device
+    use iso_c_binding
+    use mwgpu
+    use energy,     only : gpu_ctx,model_energy
+    use userparams, only : num_lattices,parallel_strategy,mc_max_trans,mc_dv_max
+    implicit none
+    type(mwgpu_walker_state) :: st
+    call mc_gpu_pull()                    ! acceptance counters, mc_translations, average_energy for the log lines
+    ! ... the unchanged write statements of :1734-1780 (ratios, attempts per molecule, mu span, energies) ...
+    call mwgpu_check(mwgpu_mc_monitor(gpu_ctx),'mc_gpu_monitor')
+    if (num_lattices==2 .and. parallel_strategy=='mw') then
+       call mwgpu_check(mwgpu_comms_allreduce_bins(gpu_ctx),'mc_gpu_monitor')
+       call mc_gpu_pull_bins()            ! for the histogram.dat / eta_weights.dat dumps of :1827-1847
+    end if
+    call mwgpu_check(mwgpu_mc_get_state(gpu_ctx,0_c_int,st),'mc_gpu_monitor')
+    mc_max_trans = st%mc_max_trans ; mc_dv_max = st%mc_dv_max          ! tuned on the device during equilibration
+    model_energy(1:num_lattices) = st%model_energy(1:num_lattices)     ! "Checking accumulated energies" (:1781-1792)
+  end subroutine mc_gpu_monitor
+
+  subroutine mc_gpu_chain_sync()
+    ! mc_check_chain_synchronisation (mc_moves.F90:2217-2416) on the device; the report lines of :2404-2412 read
+    ! the energies before / after from two mwgpu_mc_get_state calls
+    use iso_c_binding
+    use mwgpu
+    use energy, only : gpu_ctx
+    implicit none
+    call mwgpu_check(mwgpu_mc_chain_sync(gpu_ctx),'mc_gpu_chain_sync')
+  end subroutine mc_gpu_chain_sync
 
 !=============================================================================!
 ! Device-side variants of the periodic bookkeeping (no pull / push round trip) !

@@ -195,6 +195,21 @@ module mwgpu
        integer(c_int32_t),value  :: first_stream
      end function mwgpu_mc_set_rng_philox
 
+     ! next draw index of one walker (-1: all): a restart must advance the stream (checkpoints carry no generator state)
+     integer(c_int) function mwgpu_mc_set_rng_index(ctx,walker,index) bind(C,name='mwgpu_mc_set_rng_index')
+       import :: c_int,c_ptr,c_int64_t
+       type(c_ptr),value         :: ctx
+       integer(c_int),value      :: walker
+       integer(c_int64_t),value  :: index
+     end function mwgpu_mc_set_rng_index
+
+     ! which walker kernel mwgpu_mc_run uses: 0 automatic, 1 one warp per walker, 2 one warp per lattice
+     integer(c_int) function mwgpu_mc_set_kernel(ctx,warps_per_walker) bind(C,name='mwgpu_mc_set_kernel')
+       import :: c_int,c_ptr
+       type(c_ptr),value    :: ctx
+       integer(c_int),value :: warps_per_walker
+     end function mwgpu_mc_set_kernel
+
      integer(c_int) function mwgpu_mc_set_rng_fifo(ctx,u,n) bind(C,name='mwgpu_mc_set_rng_fifo')
        import :: c_int,c_ptr,c_int64_t,c_double
        type(c_ptr),value         :: ctx

@@ -31,9 +31,20 @@
 extern "C" {
 #endif
 
-#define MWGPU_MAXNEIGH 50      /* molint.F90:79  leading dimension of jn/vn in the ABI */
+#define MWGPU_MAXNEIGH 50      /* molint.F90:79  leading dimension of jn/vn in the ABI (NOT the device capacity, see below) */
 #define MWGPU_MAXIVECT 32      /* image vectors supported per lattice (27 in all reference decks) */
 #define MWGPU_LIST_SLOTS 32    /* neighbours per molecule held on the device (reference decks: 16..23) */
+/* Capacity envelope of the device path (the reference allocates maxneigh = 50 list slots and checks nothing,
+ * molint.F90:79; here every limit is checked and reported through the MWGPU_ERR_* bits instead of a result):
+ *   - 32 list neighbours per molecule within 1.18*a*sigma        -> MWGPU_ERR_LIST_OVERFLOW   (decks: <= 23)
+ *   - 32 image vectors per lattice (cell wider than the cut-off) -> MWGPU_ERR_IVECT_OVERFLOW  (decks: 27)
+ *   - a molecule must not neighbour its own periodic image       -> MWGPU_ERR_SELF_IMAGE
+ *   - bonds inside the cut-off of the moved molecule per lattice: 31 per evaluated variant in the warp-per-lattice
+ *     kernel (old and new position share a 32-record table and fall back to one variant at a time); 64 in total over
+ *     both lattices and both variants in the one-warp kernel     -> MWGPU_ERR_BOND_OVERFLOW   (decks: <= 11 per variant)
+ *   - boxes of up to 1024 molecules; the warp-per-lattice kernel serves boxes of up to 64 (all reference decks: 48)
+ * The reference's compile-time variant MINU (lattice switch folded into every move, mc_moves.F90:1119-1140,
+ * :1385-1401) is not implemented. */
 
 typedef struct mwgpu_ctx mwgpu_ctx;
 
@@ -150,6 +161,10 @@ int  mwgpu_mc_init(mwgpu_ctx *ctx, const mwgpu_mc_params *p, int first_rank, int
  * Philox-4x32-10 keyed by seed, walker w uses stream first_stream + w, first draw = start_index
  * (main.f90:79-81 burns 1 000 000 draws) ... */
 int  mwgpu_mc_set_rng_philox(mwgpu_ctx *ctx, uint64_t seed, uint32_t first_stream, uint64_t start_index);
+/* next draw index of one walker (walker -1: all): a restart must advance the stream past what the first segment
+ * consumed -- mwgpu_mc_get_state().rng_index at checkpoint time -- or use another seed; the reference re-seeds from
+ * the clock (random.f90:62-63) and its checkpoint carries no generator state (mc_moves.F90:353-379) */
+int  mwgpu_mc_set_rng_index(mwgpu_ctx *ctx, int walker, uint64_t index);
 /* ... or a host FIFO of U[0,1) numbers for walker 0 of a 1-walker context: the device consumes
  * them in the reference's draw order; mwgpu_mc_get_state().rng_index tells how many were used */
 int  mwgpu_mc_set_rng_fifo(mwgpu_ctx *ctx, const double *u, int64_t n);

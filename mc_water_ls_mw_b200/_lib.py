@@ -101,6 +101,7 @@ SYMBOLS = {
     "mwgpu_mc_init": (_i, [_vp, C.POINTER(McParams), _i, _i, _dp, _i, _d]),
     "mwgpu_mc_set_rng_philox": (_i, [_vp, C.c_uint64, C.c_uint32, C.c_uint64]),
     "mwgpu_mc_set_rng_fifo": (_i, [_vp, _dp, C.c_int64]),
+    "mwgpu_mc_set_rng_index": (_i, [_vp, _i, C.c_uint64]),
     "mwgpu_mc_run": (_i, [_vp, _i]),
     "mwgpu_mc_run_async": (_i, [_vp, _i]),
     "mwgpu_mc_set_kernel": (_i, [_vp, _i]),

@@ -544,12 +544,26 @@ static OpArgs make_args(mwgpu_ctx* c, int op, int w0, int lat, int imol, double*
     return a;
 }
 
+// OR of the walkers' error bits and the first flagged walker, reduced on the device: 8 bytes come back
+__global__ void k_collect_errors(DeviceState S, int* __restrict__ out)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = (w < S.W) ? S.scal[w].error : 0;
+    const unsigned any = __ballot_sync(0xffffffffu, e != 0);
+    if (any == 0) return;
+    const int all = (int)__reduce_or_sync(0xffffffffu, (unsigned)e);
+    if ((threadIdx.x & 31) == __ffs(any) - 1) { atomicOr(out, all); atomicMin(out + 1, w); }
+}
+
 static int collect_errors(mwgpu_ctx* c, const char* what)
 {
-    std::vector<WalkerScalars> h(c->W);
-    CUDA_TRY(cudaMemcpy(h.data(), c->S.scal, sizeof(WalkerScalars) * c->W, cudaMemcpyDeviceToHost));
-    int all = 0, first = -1;
-    for (int w = 0; w < c->W; ++w) if (h[w].error) { all |= h[w].error; if (first < 0) first = w; }
+    int h[2] = {0, 0x7fffffff};
+    CUDA_TRY(cudaMemcpyAsync(c->iout, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+    k_collect_errors<<<(c->W + 255) / 256, 256, 0, c->stream>>>(c->S, c->iout);
+    c->launches++;
+    CUDA_TRY(cudaMemcpyAsync(h, c->iout, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const int all = h[0], first = h[1];
     if (!all) return 0;
     std::string msg = std::string(what) + ": device error bits " + std::to_string(all) + " (first walker " +
                       std::to_string(first) + "):";
@@ -935,16 +949,42 @@ extern "C" int mwgpu_mc_init(mwgpu_ctx* c, const mwgpu_mc_params* up, int first_
     return 0;
 }
 
+// one field of the per-walker scalars, for one walker or (walker < 0) all of them: no host round trip
+enum ScalarField : int { SF_RNG_INDEX = 0, SF_WL_FACTOR, SF_LS, SF_WMIN_ZERO };
+__global__ void k_set_scalar(DeviceState S, int walker, int field, double dval, unsigned long long uval, int ival)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= S.W || (walker >= 0 && w != walker)) return;
+    WalkerScalars& sc = S.scal[w];
+    switch (field) {
+    case SF_RNG_INDEX: sc.rng_index = uval; break;
+    case SF_WL_FACTOR: sc.wl_factor = dval; sc.wl_invt_active = ival; break;
+    case SF_LS: sc.ls = ival; break;
+    case SF_WMIN_ZERO: sc.wmin_zero = ival; break;
+    default: break;
+    }
+}
+
+static int set_scalar(mwgpu_ctx* c, int walker, int field, double dval, unsigned long long uval, int ival)
+{
+    k_set_scalar<<<(c->W + 127) / 128, 128, 0, c->stream>>>(c->S, walker, field, dval, uval, ival);
+    c->launches++;
+    return finish(c, true);
+}
+
 extern "C" int mwgpu_mc_set_rng_philox(mwgpu_ctx* c, uint64_t seed, uint32_t first_stream, uint64_t start_index)
 {
     if (int rc = check_ctx(c, 0, false)) return rc;
     if (!c->mc_ready) return fail("mwgpu_mc_set_rng_philox: call mwgpu_mc_init first");
     c->P.seed = seed; c->P.stream0 = first_stream; c->P.rng_mode = 0;
-    std::vector<WalkerScalars> h(c->W);
-    CUDA_TRY(cudaMemcpy(h.data(), c->S.scal, sizeof(WalkerScalars) * c->W, cudaMemcpyDeviceToHost));
-    for (auto& s : h) s.rng_index = start_index;
-    CUDA_TRY(cudaMemcpy(c->S.scal, h.data(), sizeof(WalkerScalars) * c->W, cudaMemcpyHostToDevice));
-    return 0;
+    return set_scalar(c, -1, SF_RNG_INDEX, 0.0, start_index, 0);
+}
+
+extern "C" int mwgpu_mc_set_rng_index(mwgpu_ctx* c, int walker, uint64_t index)
+{
+    if (int rc = check_ctx(c, walker, true)) return rc;
+    if (!c->mc_ready) return fail("mwgpu_mc_set_rng_index: call mwgpu_mc_init first");
+    return set_scalar(c, walker, SF_RNG_INDEX, 0.0, index, 0);
 }
 
 extern "C" int mwgpu_mc_set_rng_fifo(mwgpu_ctx* c, const double* u, int64_t n)
@@ -958,11 +998,7 @@ extern "C" int mwgpu_mc_set_rng_fifo(mwgpu_ctx* c, const double* u, int64_t n)
     CUDA_TRY(cudaMemcpy(c->fifo, u, sizeof(double) * n, cudaMemcpyHostToDevice));
     c->S.fifo = c->fifo; c->S.fifo_len = (unsigned long long)n;
     c->P.rng_mode = 1;
-    WalkerScalars s;
-    CUDA_TRY(cudaMemcpy(&s, c->S.scal, sizeof(s), cudaMemcpyDeviceToHost));
-    s.rng_index = 0;
-    CUDA_TRY(cudaMemcpy(c->S.scal, &s, sizeof(s), cudaMemcpyHostToDevice));
-    return 0;
+    return set_scalar(c, 0, SF_RNG_INDEX, 0.0, 0ull, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1085,12 +1121,7 @@ extern "C" int mwgpu_mc_set_bins(mwgpu_ctx* c, int walker, const double* weight,
     if (weight) CUDA_TRY(cudaMemcpy(c->S.weight + off, weight, nbytes, cudaMemcpyHostToDevice));
     if (hist) CUDA_TRY(cudaMemcpy(c->S.hist + off, hist, nbytes, cudaMemcpyHostToDevice));
     if (uhist) CUDA_TRY(cudaMemcpy(c->S.uhist + off, uhist, nbytes, cudaMemcpyHostToDevice));
-    if (weight) {           // the wl-bin update may no longer assume min(weight) == 0
-        WalkerScalars s;
-        CUDA_TRY(cudaMemcpy(&s, c->S.scal + walker, sizeof(s), cudaMemcpyDeviceToHost));
-        s.wmin_zero = 0;
-        CUDA_TRY(cudaMemcpy(c->S.scal + walker, &s, sizeof(s), cudaMemcpyHostToDevice));
-    }
+    if (weight) return set_scalar(c, walker, SF_WMIN_ZERO, 0.0, 0ull, 0);    // the wl-bin update may no longer assume min(weight) == 0
     return 0;
 }
 
@@ -1109,25 +1140,14 @@ extern "C" int mwgpu_mc_get_grid(mwgpu_ctx* c, double* mu_bin, double* binwidth,
 extern "C" int mwgpu_mc_set_wl_factor(mwgpu_ctx* c, int walker, double wl_factor, int wl_invt_active)
 {
     if (int rc = check_ctx(c, walker, true)) return rc;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    std::vector<WalkerScalars> h(c->W);
-    CUDA_TRY(cudaMemcpy(h.data(), c->S.scal, sizeof(WalkerScalars) * c->W, cudaMemcpyDeviceToHost));
-    for (int w = 0; w < c->W; ++w)
-        if (walker < 0 || walker == w) { h[w].wl_factor = wl_factor; h[w].wl_invt_active = wl_invt_active; }
-    CUDA_TRY(cudaMemcpy(c->S.scal, h.data(), sizeof(WalkerScalars) * c->W, cudaMemcpyHostToDevice));
-    return 0;
+    return set_scalar(c, walker, SF_WL_FACTOR, wl_factor, 0ull, wl_invt_active);
 }
 
 extern "C" int mwgpu_mc_set_active_lattice(mwgpu_ctx* c, int walker, int ls)
 {
     if (int rc = check_ctx(c, walker, true)) return rc;
     if (int rc = check_ils(c, ls)) return rc;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    std::vector<WalkerScalars> h(c->W);
-    CUDA_TRY(cudaMemcpy(h.data(), c->S.scal, sizeof(WalkerScalars) * c->W, cudaMemcpyDeviceToHost));
-    for (int w = 0; w < c->W; ++w) if (walker < 0 || walker == w) h[w].ls = ls;
-    CUDA_TRY(cudaMemcpy(c->S.scal, h.data(), sizeof(WalkerScalars) * c->W, cudaMemcpyHostToDevice));
-    return 0;
+    return set_scalar(c, walker, SF_LS, 0.0, 0ull, ls);
 }
 
 extern "C" int mwgpu_mc_monitor(mwgpu_ctx* c)
@@ -1162,9 +1182,10 @@ extern "C" int mwgpu_mc_restore(mwgpu_ctx* c, int walker, int mc_cycle_num, doub
     if (!c->mc_ready) return fail("mwgpu_mc_restore: call mwgpu_mc_init first");
     if (!histogram || !weight) return fail("mwgpu_mc_restore: histogram / weight is NULL");
     if (!hmatrix || !ref_ljr || !ljr) return fail("mwgpu_mc_restore: hmatrix / ref_ljr / ljr is NULL");
-    if (int rc = upload_impl(c, walker, 1, 0, ljr, ref_ljr, hmatrix, true)) return rc;                 // :479-489
     if (ls < 1 || ls > c->nlat) return fail("mwgpu_mc_restore: ls out of range");
     if (c->user.samplerun && !unbiased_hist) return fail("mwgpu_mc_restore: a sample run needs unbiased_hist");
+    // every argument is checked before the walker is touched: a rejected call leaves it as it was
+    if (int rc = upload_impl(c, walker, 1, 0, ljr, ref_ljr, hmatrix, true)) return rc;                 // :479-489
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     const size_t off = (size_t)walker * c->NB, nbytes = sizeof(double) * c->NB;
     WalkerScalars s;
@@ -1334,16 +1355,31 @@ extern "C" int mwgpu_comms_apply(mwgpu_ctx* c)
     return finish(c, true);
 }
 
+// base[w][k] = src[k] for every walker
+__global__ void k_broadcast_bins(double* __restrict__ base, const double* __restrict__ src, int W, int NB)
+{
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t < (size_t)W * NB) base[t] = src[t % NB];
+}
+
 extern "C" int mwgpu_comms_set_hist_base(mwgpu_ctx* c, const double* hist, const double* uhist)
 {
     if (int rc = check_ctx(c, 0, false)) return rc;
     if (!c->mc_ready) return fail("mwgpu_comms_set_hist_base: call mwgpu_mc_init first");
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    for (int w = 0; w < c->W; ++w) {
-        if (hist) CUDA_TRY(cudaMemcpy(c->S.hbase + (size_t)w * c->NB, hist, sizeof(double) * c->NB, cudaMemcpyHostToDevice));
-        if (uhist) CUDA_TRY(cudaMemcpy(c->S.ubase + (size_t)w * c->NB, uhist, sizeof(double) * c->NB, cudaMemcpyHostToDevice));
+    // one upload per array into the reduction staging buffer, one broadcast kernel: no per-walker copies
+    const size_t n = (size_t)c->W * c->NB;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (hist) {
+        CUDA_TRY(cudaMemcpyAsync(c->delta, hist, sizeof(double) * c->NB, cudaMemcpyHostToDevice, c->stream));
+        k_broadcast_bins<<<grid, 256, 0, c->stream>>>(c->S.hbase, c->delta, c->W, c->NB);
+        c->launches++;
     }
-    return 0;
+    if (uhist) {
+        CUDA_TRY(cudaMemcpyAsync(c->delta + c->NBP, uhist, sizeof(double) * c->NB, cudaMemcpyHostToDevice, c->stream));
+        k_broadcast_bins<<<grid, 256, 0, c->stream>>>(c->S.ubase, c->delta + c->NBP, c->W, c->NB);
+        c->launches++;
+    }
+    return finish(c, true);
 }
 
 // ---- NCCL, loaded lazily so that the library has no link-time dependency on it -------------------

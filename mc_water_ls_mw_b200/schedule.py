@@ -4,7 +4,7 @@ The reference calls ``mc_cycle`` once per cycle (main.f90:181-198); after the mo
 cycle checks five intervals, in this order:
 
     mpi_sync_int   -> comms_allreduce_eta / _hist / _uhist        (two lattices, 'mw')
-    monitor_int    -> mc_monitor_stats
+    monitor_int    -> mc_monitor_stats (+ the same all-reduces again, mc_moves.F90:1813-1821)
     flat_chk_int   -> mc_check_flatness                            (two lattices)
     latt_sync_int  -> mc_check_chain_synchronisation               (two lattices)
     deltaG_int     -> mc_compute_deltaG_from_hist                  (two lattices, samplerun)
@@ -59,6 +59,11 @@ class CycleSchedule:
             self._note("sync", cyc)
         if up.monitor_int > 0 and cyc % up.monitor_int == 0:                                # :280-285
             g.mc_monitor()
+            if self.two and self.mw:
+                # mc_monitor_stats synchronises histogram, weights and (sample runs) the unbiased histogram itself
+                # (mc_moves.F90:1813-1821): a no-op right after the mpi_sync_int merge, a real merge whenever
+                # monitor_int is not a multiple of mpi_sync_int
+                g.comms_allreduce_bins()
             self._note("monitor", cyc)
         if not self.two:
             return

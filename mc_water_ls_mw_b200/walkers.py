@@ -157,6 +157,10 @@ class WalkerBatch:
     def set_rng_philox(self, seed: int, first_stream: int = 0, start_index: int = 0) -> None:
         check(self.L.mwgpu_mc_set_rng_philox(self.h, seed, first_stream, start_index))
 
+    def set_rng_index(self, index: int, walker: int = -1) -> None:
+        """Next draw index of one walker (-1: all), e.g. after mc_restore (mwgpu_mc_set_rng_index)."""
+        check(self.L.mwgpu_mc_set_rng_index(self.h, walker, int(index)))
+
     def set_rng_fifo(self, u: np.ndarray) -> None:
         u = np.ascontiguousarray(u, dtype=np.float64)
         check(self.L.mwgpu_mc_set_rng_fifo(self.h, _dp(u), len(u)))

@@ -99,6 +99,8 @@ class OracleSchedule:
             if c % up.monitor_int == 0:
                 for s in ws:
                     s.mc_monitor()
+                if two and mw:                               # mc_monitor_stats re-synchronises the bins (mc_moves.F90:1813-1821)
+                    orc.allreduce_bins(ws)
             if not two:
                 continue
             if c % up.flat_chk_int == 0:

@@ -42,6 +42,9 @@ def _same_state(g, o, up, w=0):
     ("single_box", 45, {"eq_mc_cycles": 5}),
     ("ice1_sample", 25, {"mc_vol_prob": 0.08, "eq_mc_cycles": 3}),          # volume moves next to cycle ends / list rebuilds
     ("ice1_sample", 25, {"mc_always_switch": False, "mc_switch_prob": 0.2, "eq_mc_cycles": 3}),
+    # Swetnam's increment (mc_moves.F90:1636-1653): log(rms) < 0 makes it negative, a visit can then create a new
+    # window minimum that the reference subtracts from every bin (:1682-1685)
+    ("ice1_gen_weights", 30, {"wl_swetnam": True, "eq_mc_cycles": 3}),
 ])
 def test_chain_bit_exact_on_both_kernels(kernel, ex, ncyc, ov):
     o, up = make_oracle_walker(ex, overrides=ov)
