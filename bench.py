@@ -24,9 +24,20 @@ reference positions / cells, list + energy re-initialisation as after a checkpoi
 load, the 250 cycles, and the device -> host read of positions and observables)
 inside the timed region.
 
+Both arms run the PRODUCTION phase of the deck: eq_mc_cycles is set to the 100 untimed
+preparation cycles (the deck's own 10 000 equilibration cycles would leave the histogram
+updates of mc_update_wl_bins out of every timed step).
+
+At N > 1 the line also carries `"strong"`: BASELINE configs[4] read literally (4096 walkers
+IN TOTAL, split evenly over the GPUs), measured in the same run on a second batch, and
+`"allreduce_check"`: the library's NCCL delta all-reduce against a host sum of the per-rank
+increments and across ranks.
+
 `--impl reference`: the reference cannot be compiled here (no Fortran compiler, no
 MPI in this image or on the GPU box); the arm times the CPU oracle (C restatement of
-the same algorithm, oracle/mw_oracle.c) on all host cores, same config and metric.
+the same algorithm, oracle/mw_oracle.c) built with -O3 -march=native -ffp-contract=fast
+on the machine it runs on (the parity tests keep the strict -O2 -ffp-contract=off build),
+on all host cores, same config and metric.
 """
 from __future__ import annotations
 
@@ -49,12 +60,15 @@ FLOP_PER_EVAL = 35424.0          # one lattice full energy (mean of 34560 / 3628
 BYTES_PER_EVAL = 8336.0          # one lattice, reference int32 list layout (mean of 8144 / 8528)
 EXAMPLE = "ice1_sample"
 SEED = 20141211
+PREP_CYCLES = 100                # untimed: 4 x (25 cycles + monitor with eq_adjust_mc); eq_mc_cycles of both arms
+ENERGY_REPLICAS = 8              # full-energy batch: the rank's decorrelated walkers x 8 = 65 536 evaluations per launch
 
 
 def _example():
     from mc_water_ls_mw_b200 import decks
     d = os.path.join(ROOT, "tests", "golden", "examples", os.environ.get("MW_BENCH_EXAMPLE", EXAMPLE))
     up = decks.read_input(os.path.join(d, "ice.input"))
+    up.eq_mc_cycles = PREP_CYCLES        # production phase: histogram / unbiased-histogram updates inside the timed steps
     h, r = decks.read_config(d, up)
     wl, _, w = decks.read_eta_weights(os.path.join(d, "eta_weights.dat"))
     return up, h, r, w, wl
@@ -109,21 +123,43 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def _config(nw: int, total: int, C: int, nwater: int = 48):
+def _config(nw: int, total: int, C: int, nwater: int = 48, cpu: bool = False):
     """The workload both arms are quoted on (BASELINE.json configs[4])."""
+    work = {} if cpu else {"walkers_per_gpu": nw, "walkers_total": total, "moves_per_step": total * nwater * C}
     return {
         "workload": f"synthetic scale-out (BASELINE configs[4]): {nw} independent lattice-switch walkers per GPU, "
-                    f"{EXAMPLE} deck (48 mW molecules per lattice, cubic<->hexagonal ice, 200 K, 1 atm, fixed weights)",
-        "walkers_per_gpu": nw, "walkers_total": total, "cycles_per_step": C, "moves_per_step": total * nwater * C,
+                    f"{EXAMPLE} deck (48 mW molecules per lattice, cubic<->hexagonal ice, 200 K, 1 atm, fixed weights), "
+                    f"production phase (eq_mc_cycles = {PREP_CYCLES} preparation cycles)",
+        **work, "cycles_per_step": C,
         "l2_policy": "walker state (~75 MB for 4096 walkers) is read from and written back to global memory once per step; "
                      "the hot loop runs out of shared memory, so cache state between steps does not matter",
         "rng": "Philox-4x32-10, one stream per walker",
     }
 
 
+def csrc_sha256() -> str:
+    """Fingerprint of the CUDA sources the committed ncu capture (profiles/traffic.json) was taken on."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "mc_water_ls_mw_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
+
+
+def _traffic_stale() -> bool:
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("csrc_sha256") != csrc_sha256()
+    except Exception:
+        return True
+
+
 def _traffic(kernel: str, cycles: int, walkers: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
-    (profiles/traffic.json, written by scripts/prof_final.sh); only valid for the launch shape it was taken on."""
+    (profiles/traffic.json, written by scripts/prof_final.sh together with the sha256 of csrc/ it was taken on:
+    `traffic_stale` in the bench line says whether the sources changed since); only valid for the launch shape
+    it was taken on."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         t = json.load(open(p))
@@ -164,11 +200,11 @@ def _peaks():
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the CPU oracle on the host cores
 # --------------------------------------------------------------------------------------------------
-def _oracle_walkers(n, up, h, r, w, wl, first_stream=0):
+def _oracle_walkers(n, up, h, r, w, wl, first_stream=0, fast=True):
     from oracle import orc
     ws = []
     for i in range(n):
-        s = orc.System(up.nwater, up.num_lattices)
+        s = orc.System(up.nwater, up.num_lattices, fast=fast)
         s.set_config(r, h)
         s.energy_init()
         s.mc_init(orc.params_from_user(up), rank=i, size=max(n, 1), weights=w, file_wl_factor=wl)
@@ -177,11 +213,31 @@ def _oracle_walkers(n, up, h, r, w, wl, first_stream=0):
     return ws
 
 
+def _check_fast_build(up, h, r, w, wl):
+    """The timing build (-O3 -march=native, FMA contraction) against the strict parity build: full and local
+    energies of a thermalised configuration to 1e-11 before anything is timed."""
+    from oracle import orc
+    a = _oracle_walkers(1, up, h, r, w, wl, fast=False)[0]
+    assert a.mc_run(30) == 0
+    b = orc.System(up.nwater, up.num_lattices, fast=True)
+    b.set_config(np.array(a.ljr), np.array(a.hmatrix)); b.energy_init()
+    worst = 0.0
+    for l in range(1, up.num_lattices + 1):
+        ea, eb = a.compute_model_energy(l), b.compute_model_energy(l)
+        worst = max(worst, abs(ea - eb) / abs(ea))
+        for i in (1, 17, up.nwater):
+            la, lb = a.compute_local_real_energy(i, l), b.compute_local_real_energy(i, l)
+            worst = max(worst, abs(la - lb) / abs(la))
+    if not worst < 1e-11:
+        raise SystemExit(f"bench.py: the -O3 oracle build disagrees with the strict build ({worst:.3g})")
+    return worst
+
+
 def _decorrelate_oracle(ws, nthreads):
     """Same untimed preparation as the GPU arm: 4 x (25 cycles + monitor with eq_adjust_mc)."""
     from oracle import orc
     for _ in range(4):
-        assert orc.mc_run_many(ws, 25, nthreads) == 0
+        assert orc.mc_run_many(ws, PREP_CYCLES // 4, nthreads) == 0
         for s in ws:
             s.mc_monitor()
 
@@ -194,10 +250,16 @@ def _oracle_step(ws, nsync, nthreads):
         orc.allreduce_bins(ws)
 
 
+def _cpu_flags():
+    from oracle import orc
+    return f"gcc {orc.FAST_FLAGS} (timed) / {orc.STRICT_FLAGS} (parity tests)"
+
+
 def cpu_baseline(target_seconds: float = 12.0):
-    """Oracle timed on all host cores on a bounded sample of the same workload."""
+    """Oracle (timing build) on all host cores on a bounded sample of the same workload."""
     from oracle import orc
     up, h, r, w, wl = _example()
+    agree = _check_fast_build(up, h, r, w, wl)
     nthreads = orc.max_threads()
     ws = _oracle_walkers(nthreads * 2, up, h, r, w, wl)
     _decorrelate_oracle(ws, nthreads)
@@ -220,7 +282,8 @@ def cpu_baseline(target_seconds: float = 12.0):
     return {
         "value": moves / dt, "unit": "attempted MC moves/s", "cores": nthreads, "kind": "port",
         "sample": f"{len(ws)} walkers x {ncyc} cycles of {EXAMPLE}, bins merged every {CYCLES_PER_STEP} cycles (oracle "
-                  f"restatement, not the Fortran binary; {dt:.1f} s on {nthreads} threads)",
+                  f"restatement, not the Fortran binary; {dt:.1f} s on {nthreads} threads; {_cpu_flags()}; "
+                  f"timing build vs strict build on energies: {agree:.1e})",
         "energy_evals_per_s": evals,
         "serial": {"value": serial, "unit": "attempted MC moves/s", "cores": 1,
                    "sample": f"1 walker x {ncs} cycles on one thread (stand-in for the reference's serial build)"},
@@ -233,6 +296,7 @@ def run_reference(args):
         return
     from oracle import orc
     up, h, r, w, wl = _example()
+    agree = _check_fast_build(up, h, r, w, wl)
     nthreads = orc.max_threads()
     ws = _oracle_walkers(nthreads * 2, up, h, r, w, wl)
     _decorrelate_oracle(ws, nthreads)
@@ -250,14 +314,15 @@ def run_reference(args):
     val = moves / dt
     unit = "attempted MC moves/s"
     sample = (f"{len(ws)} walkers x {per_step} cycles per step of {EXAMPLE} on {nthreads} host threads, bins merged every "
-              f"{CYCLES_PER_STEP} cycles (CPU oracle)")
+              f"{CYCLES_PER_STEP} cycles (CPU oracle, {_cpu_flags()}; timing build vs strict build on energies: {agree:.1e})")
     print(json.dumps({
         "impl": "reference", "metric": "attempted MC moves/sec (whole box)", "value": val, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        # the same workload as the GPU arm; each CPU step is the bounded sample of it described in cpu_baseline.sample
-        "config": dict(_config(WALKERS_PER_GPU, WALKERS_PER_GPU * max(args.gpus, 1), CYCLES_PER_STEP, up.nwater),
-                       cpu_sample={"walkers": len(ws), "cycles_per_step": per_step}),
+        # the same workload as the GPU arm; each CPU step is the bounded sample of it described in cpu_sample
+        "config": dict(_config(WALKERS_PER_GPU, WALKERS_PER_GPU * max(args.gpus, 1), CYCLES_PER_STEP, up.nwater, cpu=True),
+                       cpu_sample={"walkers": len(ws), "cycles_per_step": per_step,
+                                   "moves_per_step": len(ws) * up.nwater * per_step}),
         "cpu_baseline": {"value": val, "unit": unit, "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -289,55 +354,62 @@ def run_ours(args):
     total = nw * world
     up, h, r, w, wl = _example()
 
-    g = W.WalkerBatch(up.nwater, up.num_lattices, nw, device=local)
-    g.upload(r, h)
-    g.energy_init()
-    g.mc_init(W.params_from_user(up), first_rank=rank * nw, size=total, weights=w, file_wl_factor=wl)
-    g.set_rng_philox(SEED, rank * nw, 1000000)
-    if world > 1:
-        comms.init_nccl(g, rank, world)
-    # untimed decorrelation: 100 cycles with the reference's equilibration step-size adjustment
-    for _ in range(4):
-        g.mc_run(25)
-        g.mc_monitor()
+    def make_batch(n, first_global, size, tag):
+        b_ = W.WalkerBatch(up.nwater, up.num_lattices, n, device=local)
+        b_.upload(r, h)
+        b_.energy_init()
+        b_.mc_init(W.params_from_user(up), first_rank=first_global, size=size, weights=w, file_wl_factor=wl)
+        b_.set_rng_philox(SEED, first_global, 1000000)
+        if world > 1:
+            comms.init_nccl(b_, rank, world)
+        # untimed decorrelation: 100 cycles with the reference's equilibration step-size adjustment
+        for _ in range(4):
+            b_.mc_run(PREP_CYCLES // 4)
+            b_.mc_monitor()
+        if world > 1:
+            b_.comms_allreduce_bins()   # untimed: the first NCCL collective of a communicator sets up its channels
+        return b_
 
     C = args.cycles
     sync_every = max(1, up.mpi_sync_int // C)
-    if world > 1:
-        g.comms_allreduce_bins()        # untimed: the first NCCL collective sets up its channels
 
-    def barrier():
-        g.synchronize()
+    def barrier(b_):
+        b_.synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
-    def step(i):
-        g.mc_run_async(C)
+    def step(b_, i):
+        b_.mc_run_async(C)
         if (i + 1) % sync_every == 0:
-            g.comms_allreduce_bins()
+            b_.comms_allreduce_bins()
 
-    for i in range(args.warmup):
-        step(i)
-    barrier()
+    def timed(b_, steps, warmup):
+        for i in range(warmup):
+            step(b_, i)
+        barrier(b_)
+        l0 = b_.kernel_launches()
+        b_.timer_start()
+        for i in range(steps):
+            step(b_, i)
+        ms_ = b_.timer_stop()
+        barrier(b_)
+        launches_ = b_.kernel_launches() - l0
+        if world > 1:
+            t = torch.tensor([ms_], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        return ms_, launches_
+
+    g = make_batch(nw, rank * nw, total, "main")
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = g.kernel_launches()
-    g.timer_start()
-    for i in range(args.steps):
-        step(i)
-    ms = g.timer_stop()
-    barrier()
-    launches = g.kernel_launches() - l0
+    ms, launches = timed(g, args.steps, args.warmup)
     clocks = sampler.finish()
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     moves_per_step = total * up.nwater * C
     value = moves_per_step * args.steps / (ms * 1e-3)
 
-    # ---- dominant kernel (k_mc_run) timed live with CUDA events on its own stream
+    # ---- dominant kernel (k_mc_run2) timed live with CUDA events on its own stream
     kms = []
     for i in range(min(args.steps, 10)):
         g.mc_run(C)
@@ -347,20 +419,65 @@ def run_ours(args):
     achieved_tf = nw * up.nwater * C * FLOP_PER_MOVE / (k_ms * 1e-3) / 1e12
     peaks, peak_kind = _peaks()
 
-    # ---- full mW energy evals / s (second half of the metric): batched kernel, device resident
-    e_out = np.empty((nw, up.num_lattices))
+    # ---- the N > 1 extras: NCCL delta all-reduce checked against a host sum; BASELINE's strong shape
+    allreduce_check = None
+    strong_leg = None
+    if world > 1:
+        g.comms_allreduce_bins()                                   # sync point: every walker holds the merged arrays
+        w0, h0, u0 = g.bins(0)
+        g.mc_run(10)
+        ptr, n = g.comms_reduce_local()                            # this rank's summed increments [3][nbins padded]
+        loc = torch.as_tensor(comms._DevBuf(ptr, n), device=torch.device("cuda", local)).clone()
+        parts = [torch.empty_like(loc) for _ in range(world)]
+        dist.all_gather(parts, loc)
+        host_total = np.sum(np.stack([p_.cpu().numpy() for p_ in parts]), axis=0).reshape(-1, n // (3 if up.samplerun else 2))
+        g.comms_allreduce_bins()                                   # the library's own NCCL all-reduce + re-base
+        w1, h1, u1 = g.bins(0)
+        nb = len(w1)
+        d_host = max(float(np.max(np.abs((w1 - w0) - host_total[0][:nb]))), float(np.max(np.abs((h1 - h0) - host_total[1][:nb]))),
+                     float(np.max(np.abs((u1 - u0) - host_total[2][:nb]))) if up.samplerun else 0.0)
+        mine = torch.tensor(np.concatenate([w1, h1, u1]), device="cuda", dtype=torch.float64)
+        alls = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(alls, mine)
+        d_ranks = max(float((a_ - alls[0]).abs().max().item()) for a_ in alls)
+        wl_, hl_, ul_ = g.bins(nw - 1)
+        allreduce_check = {"max_abs_diff_across_ranks": d_ranks,
+                           "max_abs_diff_first_vs_last_walker": float(max(np.max(np.abs(wl_ - w1)), np.max(np.abs(hl_ - h1)), np.max(np.abs(ul_ - u1)))),
+                           "vs_host_sum": d_host, "histogram_increment_total": float(np.sum(h1 - h0)),
+                           "note": "10 cycles of increments: library NCCL all-reduce vs numpy sum of the per-rank partial sums"}
+        if not strong and args.walkers % world == 0:
+            nws = args.walkers // world
+            g2 = make_batch(nws, rank * nws, args.walkers, "strong")
+            ms2, _ = timed(g2, args.steps, args.warmup)
+            v2 = args.walkers * up.nwater * C * args.steps / (ms2 * 1e-3)
+            strong_leg = {"value": v2, "unit": "attempted MC moves/s", "ms_per_step": ms2 / args.steps,
+                          "walkers_total": args.walkers, "walkers_per_gpu": nws,
+                          "efficiency_vs_one_gpu": v2 / (value / world),
+                          "note": "BASELINE configs[4] read literally: 4096 walkers in total, split evenly; efficiency = "
+                                  "value / (N x the per-GPU rate of the weak leg of this run, i.e. 4096 walkers on one GPU)"}
+            del g2
+
+    # ---- full mW energy evals / s (second half of the metric): batched kernel on 65 536 evaluations per launch
+    # (the rank's decorrelated walkers x ENERGY_REPLICAS, device resident; > 126 MB of state: not L2 resident)
+    ljr, ref, hm = g.download_all()
+    rep = ENERGY_REPLICAS
+    big = W.WalkerBatch(up.nwater, up.num_lattices, nw * rep, device=local)
+    big.upload_all(np.ascontiguousarray(np.tile(ljr, (rep, 1, 1, 1))), np.ascontiguousarray(np.tile(hm, (rep, 1, 1))))
+    big.energy_init()
+    e_out = np.empty((nw * rep, up.num_lattices))
     for _ in range(3):
-        g.compute_model_energy_all(e_out)
+        big.compute_model_energy_all(e_out)
     ems = []
     for _ in range(20):
-        g.compute_model_energy_all(e_out)
-        ems.append(g.last_kernel_ms())
+        big.compute_model_energy_all(e_out)
+        ems.append(big.last_kernel_ms())
     e_ms = float(np.mean(ems))
-    evals_per_s = nw * up.num_lattices / (e_ms * 1e-3) * world
-    hbm_gbs = nw * up.num_lattices * BYTES_PER_EVAL / (e_ms * 1e-3) / 1e9
+    n_evals = nw * rep * up.num_lattices
+    evals_per_s = n_evals / (e_ms * 1e-3) * world
+    hbm_gbs = n_evals * BYTES_PER_EVAL / (e_ms * 1e-3) / 1e9
+    del big
 
     # ---- end to end through the C ABI with host buffers (pinned), every step
-    ljr, ref, hm = g.download_all()
     pin = [torch.from_numpy(a.copy()).pin_memory() for a in (ljr, ref, hm)]
     hl, hr, hh = [p.numpy() for p in pin]
     out_l = torch.empty_like(pin[0]).pin_memory(); out_r = torch.empty_like(pin[1]).pin_memory()
@@ -378,12 +495,12 @@ def run_ours(args):
 
     for _ in range(max(1, min(args.warmup, 3))):
         e2e_step()
-    barrier()
+    barrier(g)
     t0 = time.perf_counter()
     n_e2e = max(3, min(args.steps, 10))
     for _ in range(n_e2e):
         e2e_step()
-    barrier()
+    barrier(g)
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
@@ -397,6 +514,7 @@ def run_ours(args):
         raise SystemExit(f"bench.py: device error bits {bad[:4]}")
 
     if rank == 0:
+        tb = _traffic("k_mc_run", C, nw)
         line = {
             "metric": "attempted MC moves/sec (whole box)",
             "value": value, "unit": "attempted MC moves/s",
@@ -406,27 +524,35 @@ def run_ours(args):
             "config": _config(nw, total, C, up.nwater),
             "energy_evals_per_s": evals_per_s,
             "energy_evals": {"value": evals_per_s, "unit": "single-lattice full mW energy evals/s (dual-lattice = /2)",
-                             "ms_per_batch": e_ms, "hbm_gbs_algorithmic": hbm_gbs,
+                             "evals_per_launch": n_evals, "ms_per_batch": e_ms, "hbm_gbs_algorithmic": hbm_gbs,
                              "hbm_frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "hbm_peak": peak_kind,
-                             "fp64_tflops_algorithmic": nw * up.num_lattices * FLOP_PER_EVAL / (e_ms * 1e-3) / 1e12},
+                             "fp64_tflops_algorithmic": n_evals * FLOP_PER_EVAL / (e_ms * 1e-3) / 1e12,
+                             "kernel": "k_model_energy2<48>",
+                             "inputs": f"the {nw} decorrelated walkers x {rep} replicas"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": _traffic("k_mc_run", C, nw),
-                         "kernel": "k_mc_run<2,48>", "kernel_ms": k_ms,
+                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": tb,
+                         "traffic_stale": _traffic_stale(),
+                         "kernel": "v2::k_mc_run2<2,48>", "kernel_ms": k_ms,
                          "issue": _issue("k_mc_run", C, nw, k_ms, clocks.get("sm_mhz")),
                          "note": "algorithmic flop (10730 per attempted move, BASELINE.md) / measured DFMA peak of this GPU "
-                                 "(mwgpu_measure_fp64_peak; MEASURED_PEAKS.json has no fp64 entry)"},
+                                 "(mwgpu_measure_fp64_peak; MEASURED_PEAKS.json has no fp64 entry); traffic / issue come from "
+                                 "the committed ncu capture of the same launch shape (profiles/traffic.json), traffic_stale "
+                                 "says whether csrc/ changed since that capture"},
             # the same kernel against the HBM roofline, for the record: the walker state crosses HBM once per launch
-            "roofline_hbm": (lambda tb: {"bound": "hbm", "achieved": (tb / (k_ms * 1e-3) / 1e9) if tb else None,
-                                         "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
-                                         "frac": (tb / (k_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0)) if tb else None,
-                                         "traffic": tb, "peak_kind": peak_kind,
-                                         "note": "measured DRAM bytes of one launch / live launch duration: the path is not HBM-bound"}
-                             )(_traffic("k_mc_run", C, nw)),
+            "roofline_hbm": {"bound": "hbm", "achieved": (tb / (k_ms * 1e-3) / 1e9) if tb else None,
+                             "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
+                             "frac": (tb / (k_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0)) if tb else None,
+                             "traffic": tb, "peak_kind": peak_kind,
+                             "note": "measured DRAM bytes of one launch / live launch duration: the path is not HBM-bound"},
             "e2e": {"value": e2e_value, "unit": "attempted MC moves/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if strong_leg:
+            line["strong"] = strong_leg
+        if allreduce_check:
+            line["allreduce_check"] = allreduce_check
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))

@@ -55,14 +55,55 @@ class Params(C.Structure):
 
 
 _lib: Optional[C.CDLL] = None
+_lib_fast: Optional[C.CDLL] = None
+_FAST_DIR = os.path.join(_HERE, "_fast")
+FAST_FLAGS = "-O3 -march=native -ffp-contract=fast -fno-math-errno -fno-trapping-math"
+STRICT_FLAGS = "-O2 -ffp-contract=off -fno-fast-math"
 
 
-def lib() -> C.CDLL:
-    global _lib
+def _cpu_tag() -> str:
+    """Identifies the host CPU: the -march=native build is redone when the library travels to another machine."""
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        model = next((l for l in txt.splitlines() if l.startswith("model name")), "")
+        flags = next((l for l in txt.splitlines() if l.startswith("flags")), "")
+        return hashlib.sha1((model + flags).encode()).hexdigest()[:16]
+    except Exception:
+        return "unknown"
+
+
+def build_fast(force: bool = False) -> str:
+    """The TIMING build of the same source (-O3 -march=native, FMA contraction allowed, as an
+    optimising Fortran compiler would build the reference).  Never used for parity: the strict build is."""
+    os.makedirs(_FAST_DIR, exist_ok=True)
+    so = os.path.join(_FAST_DIR, "libmw_oracle_fast.so")
+    tag_file = os.path.join(_FAST_DIR, "cpu.tag")
+    src = os.path.join(_HERE, "mw_oracle.c")
+    tag = _cpu_tag()
+    have = open(tag_file).read().strip() if os.path.exists(tag_file) else ""
+    stale = (not os.path.exists(so)) or have != tag or os.path.getmtime(src) > os.path.getmtime(so)
+    if force or stale:
+        cmd = ["gcc"] + FAST_FLAGS.split() + ["-std=gnu99", "-fPIC", "-pthread", "-shared", "-o", so, src, "-lm"]
+        subprocess.run(cmd, check=True, capture_output=True)
+        open(tag_file, "w").write(tag)
+    return so
+
+
+def lib(fast: bool = False) -> C.CDLL:
+    global _lib, _lib_fast
+    if fast:
+        if _lib_fast is None:
+            _lib_fast = _bind(C.CDLL(build_fast()))
+        return _lib_fast
     if _lib is not None:
         return _lib
     build()
-    L = C.CDLL(_LIB_PATH)
+    _lib = _bind(C.CDLL(_LIB_PATH))
+    return _lib
+
+
+def _bind(L: C.CDLL) -> C.CDLL:
     vp, cp, d, i, i64 = C.c_void_p, C.c_char_p, C.c_double, C.c_int, C.c_int64
     dp = C.POINTER(C.c_double)
     L.orc_const.restype = d; L.orc_const.argtypes = [cp]
@@ -103,7 +144,6 @@ def lib() -> C.CDLL:
     L.orc_set_i.argtypes = [vp, cp, i64]
     L.orc_set_rng_philox.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint64]
     L.orc_set_rng_fifo.argtypes = [vp, dp, i64]
-    _lib = L
     return L
 
 
@@ -138,8 +178,8 @@ def params_from_user(up) -> Params:
 class System:
     """One walker (= one MPI rank of the reference)."""
 
-    def __init__(self, nwater: int, nlat: int):
-        self.L = lib()
+    def __init__(self, nwater: int, nlat: int, fast: bool = False):
+        self.L = lib(fast)
         self.nwater, self.nlat = nwater, nlat
         self.h = self.L.orc_create(nwater, nlat)
         self._keep = []
@@ -265,7 +305,7 @@ def _handles(walkers: Sequence[System]):
 
 
 def allreduce_bins(walkers: Sequence[System]) -> None:
-    lib().orc_allreduce_bins(_handles(walkers), len(walkers))
+    walkers[0].L.orc_allreduce_bins(_handles(walkers), len(walkers))
 
 
 def mc_check_flatness(walkers: Sequence[System], wl_schedule: int = 0, wl_minhist: int = 20,
@@ -299,12 +339,12 @@ def join_eta(walkers: Sequence[System], overlap: int) -> np.ndarray:
 
 
 def mc_run_many(walkers: Sequence[System], ncycles: int, nthreads: int = 0) -> int:
-    return lib().orc_mc_run_many(_handles(walkers), len(walkers), ncycles, nthreads)
+    return walkers[0].L.orc_mc_run_many(_handles(walkers), len(walkers), ncycles, nthreads)
 
 
 def model_energy_many(walkers: Sequence[System], nthreads: int = 0) -> np.ndarray:
     out = np.zeros((len(walkers), 2), dtype=np.float64)
-    lib().orc_model_energy_many(_handles(walkers), len(walkers), nthreads, _dp(out))
+    walkers[0].L.orc_model_energy_many(_handles(walkers), len(walkers), nthreads, _dp(out))
     return out
 
 

@@ -1,0 +1,84 @@
+"""Generates tests/golden/numpy_vectors.npz from the independent numpy restatement (ref_numpy.py): lists, full and
+local energies of both lattices, and the state after 3 MC cycles (accept / reject sequence, positions, counters,
+bins) of ice1_sample and single_box under a host FIFO of random numbers.  tests/test_oracle_numpy.py holds the C
+oracle to these vectors.
+
+    python tests/golden/make_fixtures_numpy.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from mc_water_ls_mw_b200 import decks          # input readers only (namelists, xmol, eta_weights: host I/O)
+from tests.golden import ref_numpy as R
+
+CASES = {
+    # deck: (overrides, cycles, rng seed)
+    "ice1_sample": ({"eq_mc_cycles": 1, "mc_vol_prob": 0.04, "list_update_int": 2}, 3, 101),
+    "single_box": ({"eq_mc_cycles": 1, "mc_vol_prob": 0.04, "list_update_int": 2}, 3, 202),
+    "ice1_gen_weights": ({"eq_mc_cycles": 1, "list_update_int": 2}, 2, 303),
+}
+
+
+def load(name, ov):
+    d = os.path.join(HERE, "examples", name)
+    up = decks.read_input(os.path.join(d, "ice.input"))
+    for k, v in ov.items():
+        setattr(up, k, v)
+    h, r = decks.read_config(d, up)
+    wl, w = 0.0, None
+    p = os.path.join(d, "eta_weights.dat")
+    if up.num_lattices == 2 and os.path.exists(p):
+        wl, _, w = decks.read_eta_weights(p)
+    return up, h, r, w, wl
+
+
+def main():
+    out = {}
+    for name, (ov, ncyc, seed) in CASES.items():
+        up, h, r, w, wl = load(name, ov)
+        b = R.Box(up, h, r, weights=w, file_wl_factor=wl)
+        nl, N = b.nlat, b.N
+        out[f"{name}/nn"] = np.array(b.nn, dtype=np.int32)
+        out[f"{name}/jn"] = np.array(b.jn, dtype=np.int32)
+        out[f"{name}/vn"] = np.array(b.vn, dtype=np.int32)
+        out[f"{name}/energy0"] = np.array(b.model_energy[:nl])
+        out[f"{name}/local0"] = np.array([[b.compute_local_real_energy(i, l) for i in range(N)] for l in range(nl)])
+        out[f"{name}/mu0"] = np.array([b.ls_mu])
+        out[f"{name}/mu_bin"] = np.array(b.mu_bin)
+        out[f"{name}/binwidth"] = np.array(b.binwidth)
+        out[f"{name}/scalars"] = np.array([b.r_pos, b.r_neg, b.av_binwidth, b.log_unbiased_norm])
+        u = np.random.default_rng(seed).random(8 * N * ncyc + 16)
+        out[f"{name}/fifo"] = u
+        b.set_fifo(u)
+        for _ in range(ncyc):
+            b.mc_cycle()
+        out[f"{name}/ncycles"] = np.array([ncyc])
+        out[f"{name}/ljr"] = np.array(b.r)
+        out[f"{name}/ref_ljr"] = np.array(b.ref)
+        out[f"{name}/hmatrix"] = b.hflat()
+        out[f"{name}/counters"] = np.array(b.acc + b.att + [b.ls, b.fpos, b.mc_cycle_num], dtype=np.int64)
+        out[f"{name}/trace"] = np.array(b.trace, dtype=np.int8)
+        out[f"{name}/energy"] = np.array(b.model_energy[:nl])
+        out[f"{name}/mu"] = np.array([b.ls_mu])
+        out[f"{name}/volume"] = np.array(b.volume[:nl])
+        out[f"{name}/average_energy"] = np.array(b.average_energy[:nl])
+        out[f"{name}/histogram"] = np.array(b.histogram)
+        out[f"{name}/weight"] = np.array(b.weight)
+        out[f"{name}/unbiased_hist"] = np.array(b.unbiased_hist)
+        out[f"{name}/mc_translations"] = np.array(b.mc_translations, dtype=np.int32)
+        out[f"{name}/nn_end"] = np.array(b.nn, dtype=np.int32)
+        tr = np.array(b.trace)
+        print(f"{name}: E0 = {b.model_energy[:nl]}, accepted {b.acc}, attempted {b.att}, draws {b.fpos}, "
+              f"volume moves {(tr[:, 0] == 1).sum()}")
+    np.savez_compressed(os.path.join(HERE, "numpy_vectors.npz"), **out)
+    print("wrote", os.path.join(HERE, "numpy_vectors.npz"))
+
+
+if __name__ == "__main__":
+    main()
