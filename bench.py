@@ -24,8 +24,8 @@ reference positions / cells, list + energy re-initialisation as after a checkpoi
 load, the 250 cycles, and the device -> host read of positions and observables)
 inside the timed region.
 
-Both arms run the PRODUCTION phase of the deck: eq_mc_cycles is set to the 100 untimed
-preparation cycles (the deck's own 10 000 equilibration cycles would leave the histogram
+Both arms run the PRODUCTION phase of the deck: eq_mc_cycles is set to the 1000 untimed
+preparation cycles + 1 (the deck's own 10 000 equilibration cycles would leave the histogram
 updates of mc_update_wl_bins out of every timed step).
 
 At N > 1 the line also carries `"strong"`: BASELINE configs[4] read literally (4096 walkers
@@ -60,7 +60,9 @@ FLOP_PER_EVAL = 35424.0          # one lattice full energy (mean of 34560 / 3628
 BYTES_PER_EVAL = 8336.0          # one lattice, reference int32 list layout (mean of 8144 / 8528)
 EXAMPLE = "ice1_sample"
 SEED = 20141211
-PREP_CYCLES = 100                # untimed: 4 x (25 cycles + monitor with eq_adjust_mc); eq_mc_cycles of both arms
+PREP_CYCLES = 1000               # untimed equilibration: 2 x (500 cycles + monitor with eq_adjust_mc); ~30 volume-move
+                                 # attempts per monitor, enough for the reference's acceptance-ratio tuning of the step sizes
+                                 # (mc_moves.F90:1722-1732) to be more than noise; eq_mc_cycles = PREP_CYCLES + 1
 ENERGY_REPLICAS = 8              # full-energy batch: the rank's decorrelated walkers x 8 = 65 536 evaluations per launch
 
 
@@ -68,7 +70,7 @@ def _example():
     from mc_water_ls_mw_b200 import decks
     d = os.path.join(ROOT, "tests", "golden", "examples", os.environ.get("MW_BENCH_EXAMPLE", EXAMPLE))
     up = decks.read_input(os.path.join(d, "ice.input"))
-    up.eq_mc_cycles = PREP_CYCLES        # production phase: histogram / unbiased-histogram updates inside the timed steps
+    up.eq_mc_cycles = PREP_CYCLES + 1    # production phase: histogram / unbiased-histogram updates inside the timed steps
     h, r = decks.read_config(d, up)
     wl, _, w = decks.read_eta_weights(os.path.join(d, "eta_weights.dat"))
     return up, h, r, w, wl
@@ -129,7 +131,7 @@ def _config(nw: int, total: int, C: int, nwater: int = 48, cpu: bool = False):
     return {
         "workload": f"synthetic scale-out (BASELINE configs[4]): {nw} independent lattice-switch walkers per GPU, "
                     f"{EXAMPLE} deck (48 mW molecules per lattice, cubic<->hexagonal ice, 200 K, 1 atm, fixed weights), "
-                    f"production phase (eq_mc_cycles = {PREP_CYCLES} preparation cycles)",
+                    f"production phase after {PREP_CYCLES} equilibration cycles",
         **work, "cycles_per_step": C,
         "l2_policy": "walker state (~75 MB for 4096 walkers) is read from and written back to global memory once per step; "
                      "the hot loop runs out of shared memory, so cache state between steps does not matter",
@@ -234,10 +236,10 @@ def _check_fast_build(up, h, r, w, wl):
 
 
 def _decorrelate_oracle(ws, nthreads):
-    """Same untimed preparation as the GPU arm: 4 x (25 cycles + monitor with eq_adjust_mc)."""
+    """Same untimed preparation as the GPU arm: 2 x (500 cycles + monitor with eq_adjust_mc)."""
     from oracle import orc
-    for _ in range(4):
-        assert orc.mc_run_many(ws, PREP_CYCLES // 4, nthreads) == 0
+    for _ in range(2):
+        assert orc.mc_run_many(ws, PREP_CYCLES // 2, nthreads) == 0
         for s in ws:
             s.mc_monitor()
 
@@ -362,9 +364,9 @@ def run_ours(args):
         b_.set_rng_philox(SEED, first_global, 1000000)
         if world > 1:
             comms.init_nccl(b_, rank, world)
-        # untimed decorrelation: 100 cycles with the reference's equilibration step-size adjustment
-        for _ in range(4):
-            b_.mc_run(PREP_CYCLES // 4)
+        # untimed equilibration with the reference's step-size adjustment
+        for _ in range(2):
+            b_.mc_run(PREP_CYCLES // 2)
             b_.mc_monitor()
         if world > 1:
             b_.comms_allreduce_bins()   # untimed: the first NCCL collective of a communicator sets up its channels

@@ -109,3 +109,35 @@ def test_checkpoint_restart_continues_like_the_oracle(ex, tmp_path):
             wt, h, u = g2.bins(w)
             np.testing.assert_allclose(h, s.histogram, rtol=0, atol=1e-9)
             np.testing.assert_allclose(wt, s.weight, rtol=1e-11, atol=1e-11)
+
+
+def test_restart_continues_the_random_stream_and_rejected_restore_leaves_the_walker_alone():
+    """The reference's checkpoint carries no generator state (mc_moves.F90:353-379; it re-seeds from the clock): a
+    restart has to advance the Philox stream itself -- mwgpu_mc_set_rng_index with mwgpu_mc_get_state().rng_index of
+    the checkpoint -- or it replays the numbers the first segment consumed.  And a restore whose arguments are
+    rejected must not touch the walker."""
+    from mc_water_ls_mw_b200._lib import MwgpuError
+    from tests.helpers import make_oracle_walker
+    ov = {"eq_mc_cycles": 4}
+    first, up = make_gpu_walkers("ice1_sample", nwalkers=1, overrides=ov)
+    first.set_rng_philox(SEED, 3, 1000000)
+    first.mc_run(9)
+    rec = first.checkpoint_record(0)
+    idx = first.state(0).rng_index
+    assert idx > 1000000 + 9 * 48 * 6
+    g2, _ = make_gpu_walkers("ice1_sample", nwalkers=1, overrides=ov)
+    g2.set_rng_philox(SEED, 3, 1000000)
+    before = g2.download(0)[0].copy()
+    bad = dict(rec); bad["ls"] = 7
+    with pytest.raises(MwgpuError):
+        g2.mc_restore(0, bad)
+    np.testing.assert_array_equal(g2.download(0)[0], before)      # untouched by the rejected call
+    g2.mc_restore(0, rec)
+    assert g2.state(0).rng_index == 1000000                      # restore does not know where the stream was ...
+    g2.set_rng_index(idx, walker=0)                               # ... the caller says so
+    o, _ = make_oracle_walker("ice1_sample", overrides=ov)
+    o.mc_restore(rec)
+    o.set_rng_philox(SEED, 3, idx)
+    g2.mc_run(6); assert o.mc_run(6) == 0
+    np.testing.assert_array_equal(g2.download(0)[0], o.ljr)
+    assert g2.state(0).rng_index == o.geti("rng_index") > idx and list(g2.state(0).accepted)[0] > 0
