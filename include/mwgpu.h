@@ -192,7 +192,10 @@ int  mwgpu_mc_get_grid(mwgpu_ctx *ctx, double *mu_bin, double *binwidth, double 
 int  mwgpu_mc_set_wl_factor(mwgpu_ctx *ctx, int walker, double wl_factor, int wl_invt_active);  /* walker -1: all */
 int  mwgpu_mc_set_active_lattice(mwgpu_ctx *ctx, int walker, int ls);
 /* state effects of mc_monitor_stats (mc_moves.F90:1722-1732 step-size adjustment during
- * equilibration, :1786-1792 energy re-synchronisation, :1797-1810 counter reset), all walkers */
+ * equilibration, :1786-1792 energy re-synchronisation, :1797-1810 counter reset), all walkers.
+ * mc_monitor_stats also re-synchronises histogram / weights / unbiased histogram in 'mw' runs (:1813-1821): follow
+ * this call with mwgpu_comms_allreduce_bins() (a no-op right after the mpi_sync_int merge, a real merge whenever
+ * monitor_int is not a multiple of mpi_sync_int). */
 int  mwgpu_mc_monitor(mwgpu_ctx *ctx);
 /* mc_check_chain_synchronisation (mc_moves.F90:2217-2416), all walkers */
 int  mwgpu_mc_chain_sync(mwgpu_ctx *ctx);

@@ -826,9 +826,12 @@ __device__ __forceinline__ int generate_moves(const Lay<NT> Y, unsigned char* sm
 }
 
 // ---------------------------------------------------------------- the kernel: NLAT warps per walker
-template <int NLAT, int NT>
-__global__ void __launch_bounds__(32 * NLAT, MW2_BLOCKS * (3 - NLAT)) k_mc_run2(const __grid_constant__ DeviceState S,
-                                                                     const __grid_constant__ McParams p, int ncycles)
+// BL = resident walkers per SM the register allocation is bounded for: MW2_BLOCKS (72 registers) when the batch
+// fills the GPU, MW2_BLOCKS / 2 (no spills, 122 registers) for small ensembles, where a step lasts as long as one
+// walker's chain and more registers shorten it by 8 % (profiles/README.md).  Same PTX, same results.
+template <int NLAT, int NT, int BL>
+__global__ void __launch_bounds__(32 * NLAT, BL * (3 - NLAT)) k_mc_run2(const __grid_constant__ DeviceState S,
+                                                                         const __grid_constant__ McParams p, int ncycles)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int wi = blockIdx.x;

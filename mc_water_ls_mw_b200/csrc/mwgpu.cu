@@ -53,6 +53,7 @@ struct mwgpu_ctx {
     int walker_kernel = 0;         // 0: automatic, 1: one warp per walker, 2: two warps per walker (one per lattice)
     int energy_kernel = 0;         // batched full energy: 0 flattened-entry kernel (mw2_energy.cuh), 1 first generation
     int first_rank = 0, size = 1;
+    int num_sms = 148;
     double* stage = nullptr;       // device staging for layout conversion: [W][nlat][N][3] x2 + cells
     size_t stage_doubles = 0;
     double* out = nullptr;         // device scratch for results
@@ -109,9 +110,10 @@ extern "C" int mwgpu_create(int nwater, int nlat, int nwalkers, int device, mwgp
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (smem > prop.sharedMemPerBlockOptin)
         return fail("mwgpu_create: a walker of this size does not fit in shared memory");
+    const int num_sms = prop.multiProcessorCount;
 
     mwgpu_ctx* c = new mwgpu_ctx();
-    c->device = device; c->N = nwater; c->nlat = nlat; c->W = nwalkers;
+    c->device = device; c->N = nwater; c->nlat = nlat; c->W = nwalkers; c->num_sms = num_sms;
     const size_t W = nwalkers, N = nwater, L = nlat;
     DeviceState& S = c->S;
     S.N = nwater; S.nlat = nlat; S.W = nwalkers; S.NB = 0;
@@ -1017,17 +1019,23 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
         CUDA_TRY(cudaFuncSetAttribute(k_mc_run<NLAT_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_mc_run<NLAT_, NT_><<<c->W, 32, smem, c->stream>>>(c->S, c->P, ncycles);                                 \
     } while (0)
-#define MW_LAUNCH_MC2(NLAT_, NT_)                                                                                 \
+#define MW_LAUNCH_MC2(NLAT_, NT_, BL_)                                                                            \
     do {                                                                                                          \
-        CUDA_TRY(cudaFuncSetAttribute(v2::k_mc_run2<NLAT_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
-        v2::k_mc_run2<NLAT_, NT_><<<c->W, 32 * NLAT_, smem2, c->stream>>>(c->S, c->P, ncycles);                   \
+        CUDA_TRY(cudaFuncSetAttribute(v2::k_mc_run2<NLAT_, NT_, BL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+        v2::k_mc_run2<NLAT_, NT_, BL_><<<c->W, 32 * NLAT_, smem2, c->stream>>>(c->S, c->P, ncycles);              \
     } while (0)
     // boxes of up to 64 molecules: one warp per lattice on a per-lattice shared-memory block (mw2.cuh); larger
     // boxes (and walker_kernel == 1): the first-generation kernel, one warp per walker
     const bool gen2 = ent_has_rev(c->N) && c->walker_kernel != 1;
     const size_t smem2 = v2::walker_bytes(c->N, c->nlat);
-    if (gen2 && c->nlat == 2) { if (c->N == 48) MW_LAUNCH_MC2(2, 48); else MW_LAUNCH_MC2(2, 0); }
-    else if (gen2)            { if (c->N == 48) MW_LAUNCH_MC2(1, 48); else MW_LAUNCH_MC2(1, 0); }
+    // small ensembles (at most MW2_BLOCKS / 2 walkers per SM): the instantiation with the larger register budget
+    const bool small = (long long)c->W * 2 <= (long long)c->num_sms * MW2_BLOCKS;
+    if (gen2 && c->nlat == 2) {
+        if (c->N == 48) { if (small) MW_LAUNCH_MC2(2, 48, MW2_BLOCKS / 2); else MW_LAUNCH_MC2(2, 48, MW2_BLOCKS); }
+        else MW_LAUNCH_MC2(2, 0, MW2_BLOCKS);
+    } else if (gen2) {
+        if (c->N == 48) MW_LAUNCH_MC2(1, 48, MW2_BLOCKS); else MW_LAUNCH_MC2(1, 0, MW2_BLOCKS);
+    }
     else if (c->nlat == 2)    { if (c->N == 48) MW_LAUNCH_MC(2, 48); else MW_LAUNCH_MC(2, 0); }
     else                      { if (c->N == 48) MW_LAUNCH_MC(1, 48); else MW_LAUNCH_MC(1, 0); }
 #undef MW_LAUNCH_MC
