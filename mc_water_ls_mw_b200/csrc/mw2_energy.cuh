@@ -142,5 +142,133 @@ __global__ void __launch_bounds__(32, 24) k_model_energy2(const __grid_constant_
     }
 }
 
+
+// ================================================================================================================
+// k_model_energy3 -- the same energy with ONE LANE PER MOLECULE and the three-body sum in tensor form.
+//
+//   sum_{b<c} g_b g_c (u_b.u_c - c0)^2  =  1/2 [ T:T - 2 c0 |v|^2 + c0^2 s^2 - (1 - c0)^2 sum_b g_b^2 ]
+//   T = sum_b g_b u_b (x) u_b,   v = sum_b g_b u_b,   s = sum_b g_b          (b, c: bonds of the centre inside the cut-off)
+//
+// -- exact for compute_model_energy, which has no cos < 0.99 filter (molint.F90:470-483) -- so a centre needs 11
+// running sums instead of a table of bond records and a pairing loop.  A CTA of 3 warps holds TWO units (2 x 48
+// molecules = 96 lanes, every lane busy).  Phase 1: every lane walks its own Verlet row (stored transposed in shared
+// memory, [slot][molecule], so that the lanes of a warp read consecutive addresses) and keeps the in-range slots as
+// a bit mask in a register.  Phase 2: every lane walks its mask: geometry, radial functions, one exponential, pair
+// energy, 11 FMAs.  Nothing is compacted and nothing is paired.  The molecules' energies are summed per unit in
+// molecule order by one thread (fixed order; parity tolerance 1e-11).
+// ================================================================================================================
+constexpr int E3_THREADS = 96;
+
+struct E3Lay {                    // byte offsets of one unit's image; units follow each other
+    int N;
+    __host__ __device__ explicit E3Lay(int n) : N(n) {}
+    __host__ __device__ int oP()  const { return 0; }                               // [3][N] fp64
+    __host__ __device__ int oV()  const { return 24 * N; }                          // [3][IVC]
+    __host__ __device__ int oL()  const { return oV() + 24 * IVC; }                 // [LC][N] uint16, TRANSPOSED rows
+    __host__ __device__ int oE()  const { return oL() + 2 * LC * N; }               // [N] fp64 energies of the molecules
+    __host__ __device__ int unit() const { return (oE() + 8 * N + 15) & ~15; }
+    __host__ __device__ int upc() const { return E3_THREADS / N; }                  // units per CTA
+    __host__ __device__ int bytes() const { return upc() * unit(); }
+};
+
+template <int NT>
+__global__ void __launch_bounds__(E3_THREADS, 7) k_model_energy3(const __grid_constant__ DeviceState S, double* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int N = (NT > 0) ? NT : S.N;
+    const E3Lay Y(N);
+    const int upc = Y.upc();
+    const int nunits = S.W * S.nlat;
+    const int unit0 = blockIdx.x * upc;
+    const int tid = threadIdx.x;
+    const EntFmt F = ent_fmt(N);
+
+    // ---- stage the CTA's units; the Verlet rows are transposed on the way in
+    for (int u = 0; u < upc; ++u) {
+        const int unit = unit0 + u;
+        if (unit >= nunits) break;
+        unsigned char* ub = smem + u * Y.unit();
+        double* P = (double*)(ub + Y.oP());
+        double* V = (double*)(ub + Y.oV());
+        uint16_t* LT = (uint16_t*)(ub + Y.oL());
+        const double* gp = S.pos + (size_t)unit * 3 * N;
+        for (int t = tid; t < 3 * N; t += E3_THREADS) P[t] = gp[t];
+        const double* gi = S.iv + (size_t)unit * 3 * IVC;
+        for (int t = tid; t < 3 * IVC; t += E3_THREADS) V[t] = gi[t];
+        const uint4* gl = (const uint4*)(S.list + (size_t)unit * N * LC);
+        for (int t = tid; t < N * LC / 8; t += E3_THREADS) {
+            const uint4 v = gl[t];                       // entries 8*(t % (LC/8)) .. +7 of row t / (LC/8)
+            const int row = t / (LC / 8), s0 = (t % (LC / 8)) * 8;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                LT[(s0 + 2 * k) * N + row] = (uint16_t)(w[k] & 0xffffu);
+                LT[(s0 + 2 * k + 1) * N + row] = (uint16_t)(w[k] >> 16);
+            }
+        }
+    }
+    __syncthreads();
+
+    const int u = tid / N, i = tid - u * N;              // my unit (within the CTA) and molecule
+    const int unit = unit0 + u;
+    const bool live = (u < upc) && (unit < nunits);
+    unsigned char* ub = smem + (live ? u : 0) * Y.unit();
+    const double* P = (const double*)(ub + Y.oP());
+    const double* V = (const double*)(ub + Y.oV());
+    const uint16_t* LT = (const uint16_t*)(ub + Y.oL());
+    double e_mol = 0.0;
+    if (live) {
+        const int nni = S.nn[(size_t)unit * N + i];
+        const double px = P[i], py = P[N + i], pz = P[2 * N + i];
+        // ---- phase 1: in-range slots of my row
+        uint32_t mask = 0;
+#pragma unroll 1
+        for (int s = 0; s < nni; ++s) {
+            const uint32_t e = LT[s * N + i];
+            const int j = e & F.jmask, img = e >> F.ishift;
+            const double r2 = dist2((P[j] + V[img]) - px, (P[N + j] + V[IVC + img]) - py, (P[2 * N + j] + V[2 * IVC + img]) - pz);
+            if (r2 < CK.rcc2) mask |= 1u << s;            // beyond RCC every term of the bond is an exact 0.0
+        }
+        // ---- phase 2: my bonds: pair energy and the 11 running sums of the tensor form
+        double txx = 0.0, tyy = 0.0, tzz = 0.0, txy = 0.0, txz = 0.0, tyz = 0.0, vx = 0.0, vy = 0.0, vz = 0.0, sg = 0.0, sg2 = 0.0;
+        double pair = 0.0;
+#pragma unroll 1
+        while (mask) {
+            const int s = __ffs(mask) - 1; mask &= mask - 1;
+            const uint32_t e = LT[s * N + i];
+            const int j = e & F.jmask, img = e >> F.ishift;
+            const double tx = (P[j] + V[img]) - px, ty = (P[N + j] + V[IVC + img]) - py, tz = (P[2 * N + j] + V[2 * IVC + img]) - pz;
+            const double r2 = dist2(tx, ty, tz);
+            double ir, isr;
+            bond_radial(r2, ir, isr);
+            const double e1 = exp_nc(CK.sig02 * isr);
+            const double e_2 = e1 * e1, e_4 = e_2 * e_2;
+            const double g = e_4 * e_2;
+            const double s2 = CK.ss * ir * ir;
+            pair += CK.aeps * (CK.bigb * (s2 * s2) - 1.0) * (e_4 * e1);
+            const double ux = tx * ir, uy = ty * ir, uz = tz * ir;
+            const double gx = g * ux, gy = g * uy, gz = g * uz;
+            txx = fma(gx, ux, txx); tyy = fma(gy, uy, tyy); tzz = fma(gz, uz, tzz);
+            txy = fma(gx, uy, txy); txz = fma(gx, uz, txz); tyz = fma(gy, uz, tyz);
+            vx += gx; vy += gy; vz += gz; sg += g; sg2 = fma(g, g, sg2);
+        }
+        const double tt = txx * txx + tyy * tyy + tzz * tzz + 2.0 * (txy * txy + txz * txz + tyz * tyz);
+        const double vv = vx * vx + vy * vy + vz * vz;
+        const double omc = 1.0 - CK.cos0;
+        const double three = 0.5 * (tt - 2.0 * CK.cos0 * vv + CK.cos0 * CK.cos0 * sg * sg - omc * omc * sg2);
+        e_mol = 0.5 * pair + CK.leps * three;                // molint.F90:464 (half the pair term), :483
+        ((double*)(ub + Y.oE()))[i] = e_mol;
+    }
+    __syncthreads();
+    if (tid < upc && unit0 + tid < nunits) {
+        const double* E = (const double*)(smem + tid * Y.unit() + Y.oE());
+        double acc = 0.0;
+        for (int k = 0; k < N; ++k) acc += E[k];
+        const int un = unit0 + tid;
+        S.scal[un / S.nlat].E[un % S.nlat] = acc;
+        if (out) out[un] = acc;
+    }
+}
+
 }  // namespace v2
 }  // namespace mw

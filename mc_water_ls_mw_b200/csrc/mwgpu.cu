@@ -719,6 +719,17 @@ extern "C" int mwgpu_compute_model_energy_all(mwgpu_ctx* c, double* energies)
         const size_t smem1 = walker_smem_bytes(c->N, 1);
         CUDA_TRY(cudaFuncSetAttribute(k_model_energy_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
         k_model_energy_all<<<c->W * c->nlat, 32, smem1, c->stream>>>(c->S, c->out);
+    } else if (c->N <= v2::E3_THREADS && c->energy_kernel == 0) {
+        // one lane per molecule, tensor-form three-body sum (mw2_energy.cuh)
+        const v2::E3Lay Y3(c->N);
+        const int nunits = c->W * c->nlat, grid = (nunits + Y3.upc() - 1) / Y3.upc();
+        if (c->N == 48) {
+            CUDA_TRY(cudaFuncSetAttribute(v2::k_model_energy3<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, Y3.bytes()));
+            v2::k_model_energy3<48><<<grid, v2::E3_THREADS, Y3.bytes(), c->stream>>>(c->S, c->out);
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(v2::k_model_energy3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Y3.bytes()));
+            v2::k_model_energy3<0><<<grid, v2::E3_THREADS, Y3.bytes(), c->stream>>>(c->S, c->out);
+        }
     } else if (c->N == 48) {
         CUDA_TRY(cudaFuncSetAttribute(v2::k_model_energy2<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         v2::k_model_energy2<48><<<c->W * c->nlat, 32, smem, c->stream>>>(c->S, c->out);
