@@ -152,9 +152,11 @@ __global__ void __launch_bounds__(32, 24) k_model_energy2(const __grid_constant_
 // -- exact for compute_model_energy, which has no cos < 0.99 filter (molint.F90:470-483) -- so a centre needs 11
 // running sums instead of a table of bond records and a pairing loop.  A CTA of 3 warps holds TWO units (2 x 48
 // molecules = 96 lanes, every lane busy).  Phase 1: every lane walks its own Verlet row (stored transposed in shared
-// memory, [slot][molecule], so that the lanes of a warp read consecutive addresses) and keeps the in-range slots as
-// a bit mask in a register.  Phase 2: every lane walks its mask: geometry, radial functions, one exponential, pair
-// energy, 11 FMAs.  Nothing is compacted and nothing is paired.  The molecules' energies are summed per unit in
+// memory, [slot][molecule], so that the lanes of a warp read consecutive addresses) and keeps the slots that may be
+// in range as a bit mask in a register; this SCREEN runs in fp32 on float4 copies of the positions (relative to the
+// unit's first molecule) and of the image vectors -- two 16-byte loads per entry instead of six 8-byte ones, no fp64
+// pipe -- against a radius widened by 1e-5, so it has no false negatives.  Phase 2: every lane walks its mask in fp64:
+// geometry, the exact r < RCC test, radial functions, one exponential, pair energy, 11 FMAs.  Nothing is compacted and nothing is paired.  The molecules' energies are summed per unit in
 // molecule order by one thread (fixed order; parity tolerance 1e-11).
 // ================================================================================================================
 constexpr int E3_THREADS = 96;
@@ -166,7 +168,9 @@ struct E3Lay {                    // byte offsets of one unit's image; units fol
     __host__ __device__ int oV()  const { return 24 * N; }                          // [3][IVC]
     __host__ __device__ int oL()  const { return oV() + 24 * IVC; }                 // [LC][N] uint16, TRANSPOSED rows
     __host__ __device__ int oE()  const { return oL() + 2 * LC * N; }               // [N] fp64 energies of the molecules
-    __host__ __device__ int unit() const { return (oE() + 8 * N + 15) & ~15; }
+    __host__ __device__ int oPF() const { return (oE() + 8 * N + 15) & ~15; }       // [N] float4 positions - origin (screen)
+    __host__ __device__ int oVF() const { return oPF() + 16 * N; }                  // [IVC] float4 image vectors (screen)
+    __host__ __device__ int unit() const { return oVF() + 16 * IVC; }
     __host__ __device__ int upc() const { return E3_THREADS / N; }                  // units per CTA
     __host__ __device__ int bytes() const { return upc() * unit(); }
 };
@@ -195,6 +199,12 @@ __global__ void __launch_bounds__(E3_THREADS, 7) k_model_energy3(const __grid_co
         for (int t = tid; t < 3 * N; t += E3_THREADS) P[t] = gp[t];
         const double* gi = S.iv + (size_t)unit * 3 * IVC;
         for (int t = tid; t < 3 * IVC; t += E3_THREADS) V[t] = gi[t];
+        float4* PF = (float4*)(ub + Y.oPF());
+        float4* VF = (float4*)(ub + Y.oVF());
+        const double ox = gp[0], oy = gp[N], oz = gp[2 * N];          // origin of the fp32 screen: the unit's first molecule
+        for (int t = tid; t < N; t += E3_THREADS)
+            PF[t] = make_float4((float)(gp[t] - ox), (float)(gp[N + t] - oy), (float)(gp[2 * N + t] - oz), 0.f);
+        for (int t = tid; t < IVC; t += E3_THREADS) VF[t] = make_float4((float)gi[t], (float)gi[IVC + t], (float)gi[2 * IVC + t], 0.f);
         const uint4* gl = (const uint4*)(S.list + (size_t)unit * N * LC);
         for (int t = tid; t < N * LC / 8; t += E3_THREADS) {
             const uint4 v = gl[t];                       // entries 8*(t % (LC/8)) .. +7 of row t / (LC/8)
@@ -220,14 +230,20 @@ __global__ void __launch_bounds__(E3_THREADS, 7) k_model_energy3(const __grid_co
     if (live) {
         const int nni = S.nn[(size_t)unit * N + i];
         const double px = P[i], py = P[N + i], pz = P[2 * N + i];
-        // ---- phase 1: in-range slots of my row
+        // ---- phase 1: fp32 screen of my row (no false negatives: radius widened by 1e-5; positions relative to
+        // the unit's first molecule keep the fp32 error of a separation below 1e-6 of the cut-off)
+        const float4* PF = (const float4*)(ub + Y.oPF());
+        const float4* VF = (const float4*)(ub + Y.oVF());
+        const float4 pf = PF[i];
+        const float rscreen = (float)(RCC * RCC * (1.0 + 1e-5));
         uint32_t mask = 0;
-#pragma unroll 1
+#pragma unroll 2
         for (int s = 0; s < nni; ++s) {
             const uint32_t e = LT[s * N + i];
-            const int j = e & F.jmask, img = e >> F.ishift;
-            const double r2 = dist2((P[j] + V[img]) - px, (P[N + j] + V[IVC + img]) - py, (P[2 * N + j] + V[2 * IVC + img]) - pz);
-            if (r2 < CK.rcc2) mask |= 1u << s;            // beyond RCC every term of the bond is an exact 0.0
+            const float4 a = PF[e & F.jmask], b = VF[e >> F.ishift];
+            const float dx = (a.x + b.x) - pf.x, dy = (a.y + b.y) - pf.y, dz = (a.z + b.z) - pf.z;
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (r2 < rscreen) mask |= 1u << s;
         }
         // ---- phase 2: my bonds: pair energy and the 11 running sums of the tensor form
         double txx = 0.0, tyy = 0.0, tzz = 0.0, txy = 0.0, txz = 0.0, tyz = 0.0, vx = 0.0, vy = 0.0, vz = 0.0, sg = 0.0, sg2 = 0.0;
@@ -239,18 +255,20 @@ __global__ void __launch_bounds__(E3_THREADS, 7) k_model_energy3(const __grid_co
             const int j = e & F.jmask, img = e >> F.ishift;
             const double tx = (P[j] + V[img]) - px, ty = (P[N + j] + V[IVC + img]) - py, tz = (P[2 * N + j] + V[2 * IVC + img]) - pz;
             const double r2 = dist2(tx, ty, tz);
-            double ir, isr;
-            bond_radial(r2, ir, isr);
-            const double e1 = exp_nc(CK.sig02 * isr);
-            const double e_2 = e1 * e1, e_4 = e_2 * e_2;
-            const double g = e_4 * e_2;
-            const double s2 = CK.ss * ir * ir;
-            pair += CK.aeps * (CK.bigb * (s2 * s2) - 1.0) * (e_4 * e1);
-            const double ux = tx * ir, uy = ty * ir, uz = tz * ir;
-            const double gx = g * ux, gy = g * uy, gz = g * uz;
-            txx = fma(gx, ux, txx); tyy = fma(gy, uy, tyy); tzz = fma(gz, uz, tzz);
-            txy = fma(gx, uy, txy); txz = fma(gx, uz, txz); tyz = fma(gy, uz, tyz);
-            vx += gx; vy += gy; vz += gz; sg += g; sg2 = fma(g, g, sg2);
+            if (r2 < CK.rcc2) {                               // the exact test; beyond RCC every term of the bond is an exact 0.0
+                double ir, isr;
+                bond_radial(r2, ir, isr);
+                const double e1 = exp_nc(CK.sig02 * isr);
+                const double e_2 = e1 * e1, e_4 = e_2 * e_2;
+                const double g = e_4 * e_2;
+                const double s2 = CK.ss * ir * ir;
+                pair += CK.aeps * (CK.bigb * (s2 * s2) - 1.0) * (e_4 * e1);
+                const double ux = tx * ir, uy = ty * ir, uz = tz * ir;
+                const double gx = g * ux, gy = g * uy, gz = g * uz;
+                txx = fma(gx, ux, txx); tyy = fma(gy, uy, tyy); tzz = fma(gz, uz, tzz);
+                txy = fma(gx, uy, txy); txz = fma(gx, uz, txz); tyz = fma(gy, uz, tyz);
+                vx += gx; vy += gy; vz += gz; sg += g; sg2 = fma(g, g, sg2);
+            }
         }
         const double tt = txx * txx + tyy * tyy + tzz * tzz + 2.0 * (txy * txy + txz * txz + tyz * tyz);
         const double vv = vx * vx + vy * vy + vz * vz;
