@@ -13,6 +13,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <dlfcn.h>
 
 using namespace mw;
@@ -723,7 +724,15 @@ extern "C" int mwgpu_compute_model_energy_all(mwgpu_ctx* c, double* energies)
         // one lane per molecule, tensor-form three-body sum (mw2_energy.cuh)
         const v2::E3Lay Y3(c->N);
         const int nunits = c->W * c->nlat, grid = (nunits + Y3.upc() - 1) / Y3.upc();
-        if (c->N == 48) {
+        if (c->N == 48 && !getenv("MWGPU_ENERGY_NO_TMA")) {
+            // persistent, TMA double-buffered form: one CTA per resident slot, looping over pairs of units
+            const v2::E4Lay Y4(c->N);
+            int per_sm = 0;
+            CUDA_TRY(cudaFuncSetAttribute(v2::k_model_energy4<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, Y4.bytes()));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v2::k_model_energy4<48>, v2::E3_THREADS, Y4.bytes()));
+            const int g4 = std::min(grid, std::max(1, per_sm) * c->num_sms);
+            v2::k_model_energy4<48><<<g4, v2::E3_THREADS, Y4.bytes(), c->stream>>>(c->S, c->out);
+        } else if (c->N == 48) {
             CUDA_TRY(cudaFuncSetAttribute(v2::k_model_energy3<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, Y3.bytes()));
             v2::k_model_energy3<48><<<grid, v2::E3_THREADS, Y3.bytes(), c->stream>>>(c->S, c->out);
         } else {

@@ -3,7 +3,7 @@
 set -e
 tag=$1
 cd /root/repo
-timeout 3000 gpurun --timeout 1200 -- "python bench.py --steps 3 --warmup 3 --no-cpu --cycles 10 > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_mc_run -s 8 -c 1 -f -o gpurun_out/prof_$tag python bench.py --steps 3 --warmup 3 --no-cpu --cycles 10 > gpurun_out/ncu.log 2>&1; tail -c 3000 gpurun_out/plain.log | grep -o '\"value\": [0-9.e+]*' | head -1" 2>&1 | tail -4
+bash scripts/gpurun_retry.sh --timeout 1200 -- "python bench.py --steps 3 --warmup 3 --no-cpu --cycles 10 > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_mc_run -s 8 -c 1 -f -o gpurun_out/prof_$tag python bench.py --steps 3 --warmup 3 --no-cpu --cycles 10 > gpurun_out/ncu.log 2>&1; tail -c 3000 gpurun_out/plain.log | grep -o '\"value\": [0-9.e+]*' | head -1" 2>&1 | tail -4
 ncu -i gpurun_out/prof_$tag.ncu-rep --page source --csv > gpurun_out/src_$tag.csv 2>/dev/null
 ncu -i gpurun_out/prof_$tag.ncu-rep --page raw --csv > gpurun_out/raw_$tag.csv 2>/dev/null
 (cd /tmp && cuobjdump -xelf all /root/repo/mc_water_ls_mw_b200/libmwgpu.so >/dev/null 2>&1 && nvdisasm -g -c /tmp/mwgpu.sm_100a.cubin > /tmp/dis_$tag.txt 2>/dev/null)
