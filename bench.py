@@ -529,7 +529,7 @@ def run_ours(args):
                              "evals_per_launch": n_evals, "ms_per_batch": e_ms, "hbm_gbs_algorithmic": hbm_gbs,
                              "hbm_frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "hbm_peak": peak_kind,
                              "fp64_tflops_algorithmic": n_evals * FLOP_PER_EVAL / (e_ms * 1e-3) / 1e12,
-                             "kernel": "k_model_energy2<48>",
+                             "kernel": "v2::k_model_energy4<48>",
                              "inputs": f"the {nw} decorrelated walkers x {rep} replicas"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": tb,

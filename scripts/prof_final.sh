@@ -5,11 +5,11 @@
 set -e
 tag=$1
 cd /root/repo
-K2=_ZN2mw2v29k_mc_run2ILi2ELi48EEEvNS_11DeviceStateENS_8McParamsEi
+K2=_ZN2mw2v29k_mc_run2ILi2ELi48ELi14EEEvNS_11DeviceStateENS_8McParamsEi
 bash scripts/gpurun_retry.sh --timeout 2400 -- "python bench.py --steps 10 --warmup 3 > gpurun_out/final_bench_$tag.json 2> gpurun_out/final_bench_$tag.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/final_launches_$tag.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/final_ncu1.log 2>&1; \
 ncu --set full --clock-control none --import-source on -k regex:k_mc_run2 -s 6 -c 1 -f -o gpurun_out/final_mc_$tag python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/final_ncu2.log 2>&1; \
-ncu --set full --clock-control none --import-source on -k regex:k_model_energy2 -s 2 -c 1 -f -o gpurun_out/final_en_$tag python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/final_ncu3.log 2>&1; \
+ncu --set full --clock-control none --import-source on -k regex:k_model_energy4 -s 2 -c 1 -f -o gpurun_out/final_en_$tag python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/final_ncu3.log 2>&1; \
 tail -c 400 gpurun_out/final_bench_$tag.json" 2>&1 | tail -5
 for k in mc en; do
   ncu -i gpurun_out/final_${k}_$tag.ncu-rep --page raw --csv > profiles/${tag}_${k}_raw.csv 2>/dev/null
@@ -43,7 +43,7 @@ for k,name in (('mc','k_mc_run'),('en','k_model_energy')):
     t[name]['dram_bytes']=t[name]['dram_bytes_read']+t[name]['dram_bytes_write']
     t[name]['warp_instructions']=float(d['smsp__inst_executed.sum'][0])
     t[name]['ipc_per_sm_under_ncu']=float(d['sm__inst_executed.sum.per_cycle_active'][0])/148.0
-t['source']='ncu --set full --clock-control none, one launch of the default bench.py command (k_mc_run = v2::k_mc_run2<2,48>, 4096 walkers, 250 cycles per launch; k_model_energy = v2::k_model_energy2<48>, 65536 evaluations per launch); profiles/${tag}_*_raw.csv'
+t['source']='ncu --set full --clock-control none, one launch of the default bench.py command (k_mc_run = v2::k_mc_run2<2,48>, 4096 walkers, 250 cycles per launch; k_model_energy = v2::k_model_energy4<48>, 65536 evaluations per launch); profiles/${tag}_*_raw.csv'
 import sys; sys.path.insert(0,'/root/repo')
 import bench
 t['csrc_sha256']=bench.csrc_sha256()
