@@ -71,6 +71,7 @@ struct Lay {
     static constexpr int sXCH = sCTL + 32;                           // [8] fp64 energies exchanged between the warps
     static constexpr int sLV = sXCH + 64;                            // [2] log(V1/V2), log(V2/V1)
     static constexpr int sKV = sLV + 16;                             // [4] volume terms of the switch / of ls_mu (refresh_kv)
+    static constexpr int sSWAP = sKV + 24;                           // int: warp 0 takes lattice 2 (the 4th kv slot is free)
     static constexpr int SB = sKV + 32;
     __host__ __device__ __forceinline__ size_t bytes(int nlat) const { return (size_t)nlat * LB() + SB; }
 };
@@ -837,12 +838,21 @@ __global__ void __launch_bounds__(32 * NLAT, BL * (3 - NLAT)) k_mc_run2(const __
     const int wi = blockIdx.x;
     if (wi >= S.W) return;
     const Lay<NT> Y(S.N);
-    const int tid = threadIdx.x, lane = tid & 31, lat = (NLAT == 2) ? (tid >> 5) : 0;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int N = Y.N();
-    unsigned char* lb = smem + lat * Y.LB();
     unsigned char* sb = smem + NLAT * Y.LB();
     load_walker<NT>(Y, S, wi, smem, tid, 32 * NLAT);
+    // Which warp takes lattice 1 -- and with it the serial acceptance -- alternates with the hardware warp slot:
+    // the two warps of a walker sit on neighbouring schedulers (slot % 4), and with a fixed assignment every
+    // scheduler pair would carry all its acceptance warps on one side (measured: 77 % / 46 % issue-active).
+    if (NLAT == 2 && tid == 0) {
+        unsigned wslot;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wslot));
+        *at<int>(sb, Lay<NT>::sSWAP) = (int)((wslot >> 2) & 1u);
+    }
     __syncthreads();
+    const int lat = (NLAT == 2) ? ((tid >> 5) ^ *at<int>(sb, Lay<NT>::sSWAP)) : 0;
+    unsigned char* lb = smem + lat * Y.LB();
     WalkerScalars* sc = at<WalkerScalars>(sb, Lay<NT>::sSC);
     uint64_t* rngbase = at<uint64_t>(sb, Lay<NT>::sRB);
     double* rngbuf = at<double>(sb, Lay<NT>::sRNG);
