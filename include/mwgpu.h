@@ -280,6 +280,16 @@ int  mwgpu_timer_stop(mwgpu_ctx *ctx, float *ms);
 /* dependent-free DFMA throughput of the device in TFLOP/s (roofline denominator) */
 int  mwgpu_measure_fp64_peak(int device, double *tflops);
 int  mwgpu_kernel_launches(mwgpu_ctx *ctx, int64_t *count);   /* kernels launched by this context */
+/* Scheduling of one mwgpu_mc_run launch (warp-per-lattice kernel).  The walkers of a batch are independent
+ * (mc_cycle, mc_moves.F90:160-260, advances one walker's state; the reference runs one walker per MPI rank), so a
+ * batch larger than the GPU holds at once is cut into units of chunk_cycles MC cycles per walker that max_blocks
+ * persistent blocks take from a queue; a result never depends on either.  0 = automatic (the default): as many
+ * blocks as are resident at once, one unit per walker if the batch fits them, else units of 8 cycles.  A
+ * non-zero chunk_cycles cuts every launch into such units. */
+int  mwgpu_mc_set_schedule(mwgpu_ctx *ctx, int chunk_cycles, int max_blocks);
+/* %globaltimer (ns) at the start and the end of every walker's part of the last mwgpu_mc_run launch:
+ * start_end_ns[2*w], start_end_ns[2*w+1] (warp-per-lattice kernel only) */
+int  mwgpu_mc_get_walker_times(mwgpu_ctx *ctx, uint64_t *start_end_ns);
 
 #ifdef __cplusplus
 }

@@ -134,6 +134,8 @@ SYMBOLS = {
     "mwgpu_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),
     "mwgpu_measure_fp64_peak": (_i, [_i, _dp]),
     "mwgpu_kernel_launches": (_i, [_vp, C.POINTER(C.c_int64)]),
+    "mwgpu_mc_set_schedule": (_i, [_vp, _i, _i]),
+    "mwgpu_mc_get_walker_times": (_i, [_vp, C.POINTER(C.c_uint64)]),
 }
 
 

@@ -27,6 +27,10 @@
 #define MW2_BLOCKS 14        // resident walkers (CTAs) per SM the register allocation is bounded for
 #endif
 
+#ifndef MW2_CHUNK
+#define MW2_CHUNK 8          // cycles per unit of work when a batch is larger than the resident blocks of the GPU
+#endif
+
 namespace mw {
 namespace v2 {
 
@@ -72,6 +76,7 @@ struct Lay {
     static constexpr int sLV = sXCH + 64;                            // [2] log(V1/V2), log(V2/V1)
     static constexpr int sKV = sLV + 16;                             // [4] volume terms of the switch / of ls_mu (refresh_kv)
     static constexpr int sSWAP = sKV + 24;                           // int: warp 0 takes lattice 2 (the 4th kv slot is free)
+    static constexpr int sUNIT = sKV + 28;                           // int: the unit of work the block took from the queue
     static constexpr int SB = sKV + 32;
     __host__ __device__ __forceinline__ size_t bytes(int nlat) const { return (size_t)nlat * LB() + SB; }
 };
@@ -82,6 +87,12 @@ constexpr int CTL_STOP = 6, CTL_DEC = 7;
 __host__ inline size_t walker_bytes(int N, int nlat) { return Lay<0>(N).bytes(nlat); }
 
 template <typename T> __device__ __forceinline__ T* at(unsigned char* b, int off) { return (T*)(b + off); }
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ---------------------------------------------------------------- staging: global memory <-> the walker's image
 template <int NT>
@@ -826,17 +837,17 @@ __device__ __forceinline__ int generate_moves(const Lay<NT> Y, unsigned char* sm
     return rare ? ((__ffs(rare) - 1) >> 2) : nb;
 }
 
-// ---------------------------------------------------------------- the kernel: NLAT warps per walker
-// BL = resident walkers per SM the register allocation is bounded for: MW2_BLOCKS (72 registers) when the batch
-// fills the GPU, MW2_BLOCKS / 2 (no spills, 122 registers) for small ensembles, where a step lasts as long as one
-// walker's chain and more registers shorten it by 8 % (profiles/README.md).  Same PTX, same results.
-template <int NLAT, int NT, int BL>
-__global__ void __launch_bounds__(32 * NLAT, BL * (3 - NLAT)) k_mc_run2(const __grid_constant__ DeviceState S,
-                                                                         const __grid_constant__ McParams p, int ncycles)
+// ---------------------------------------------------------------- one turn of a walker on a block
+// NLAT warps; loads the walker's image, runs the move loop of mc_cycle (mc_moves.F90:160-260) and stores the image
+// back.  `first` = the walker's first turn of this launch (fixes the cycle at which its part of the launch ends).
+// With chunk > 0 the walker may give up the block every `chunk` cycles: it does when it is not behind the average
+// progress of the batch (qctr[4..5] = cycles completed by all walkers), so that slow walkers -- more bonds per
+// molecule -- hold their blocks longer and all walkers reach the end of the launch together.
+// Returns (uniform over the block) whether the walker has cycles left in this launch.
+template <int NLAT, int NT>
+__device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams& p, unsigned char* smem, int wi, int ncycles_launch,
+                                           int chunk, bool first)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int wi = blockIdx.x;
-    if (wi >= S.W) return;
     const Lay<NT> Y(S.N);
     const int tid = threadIdx.x, lane = tid & 31;
     const int N = Y.N();
@@ -867,6 +878,9 @@ __global__ void __launch_bounds__(32 * NLAT, BL * (3 - NLAT)) k_mc_run2(const __
     double* T = at<double>(lb, Y.oT());
     int err = 0;
     const int cycle0 = sc->cycle;
+    const int cyc_end = first ? cycle0 + ncycles_launch : S.cyc_end[wi];
+    if (tid == 0 && first) { S.cyc_end[wi] = cyc_end; S.wtime[2 * wi] = globaltimer_ns(); }
+    const int ncycles = cyc_end - cycle0;
     int rng_pos = 0;
 
     compute_bond_masks<NT>(Y, lb);
@@ -1132,6 +1146,17 @@ __global__ void __launch_bounds__(32 * NLAT, BL * (3 - NLAT)) k_mc_run2(const __
                 if (lane == 0) S.therm_n[wi] = n + 1;
             }
         }
+        if (chunk > 0 && (cyc + 1) % chunk == 0 && cyc + 1 < ncycles) {
+            // end of a unit: keep the block while this walker is behind the average progress of the batch
+            __syncthreads();
+            if (tid == 0) {
+                const long long tot = (long long)atomicAdd((unsigned long long*)(S.qctr + 4), (unsigned long long)chunk) + chunk;
+                const long long mine = cycle - (cyc_end - ncycles_launch);
+                ctl[CTL_DEC] = (mine * S.W >= tot) ? 1 : 0;
+            }
+            __syncthreads();
+            if (ctl[CTL_DEC]) break;
+        }
     }
     __syncthreads();
     if (lat == 0 && lane == 0) {
@@ -1142,7 +1167,70 @@ __global__ void __launch_bounds__(32 * NLAT, BL * (3 - NLAT)) k_mc_run2(const __
     err = (int)__reduce_or_sync(FULL, (unsigned)err);
     if (lane == 0 && err) atomicOr(&sc->error, err);
     __syncthreads();
+    const bool more = !ctl[CTL_STOP] && sc->cycle < cyc_end;
     store_walker<NT>(Y, S, wi, smem, tid, 32 * NLAT);
+    if (tid == 0 && !more) S.wtime[2 * wi + 1] = globaltimer_ns();
+    return more;
+}
+
+// ---------------------------------------------------------------- the kernel: persistent blocks of NLAT warps
+// A batch larger than the resident blocks of the GPU would run in waves of whole walkers and end on its slowest
+// one: measured on 4096 walkers, 2072 resident, a 250-cycle launch spends 40 of 191 ms below 90 % residency (walkers
+// differ by +-10 % in bonds per molecule, a few by 50 %; scripts/diag/tail_probe.py).  Walkers are independent
+// (the reference runs one per MPI rank), so the launch is cut into units of `chunk` cycles and the resident blocks
+// take walkers from a queue: entry q < W is walker q's first turn; at the end of a unit a walker that is not behind
+// the average progress of the batch gives up its block: the block publishes it at the tail of the queue (release)
+// and the block that takes that entry acquires it.  All walkers advance at the same rate in cycles -- the slow
+// ones simply hold a block for a larger share of the time -- and the tail of the launch is about one unit long.
+// A launch cut into turns is the same computation as consecutive launches (the state of a walker between cycles is
+// its stored image), so the results do not depend on chunk or on the number of blocks.
+// BL = resident walkers per SM the register allocation is bounded for: MW2_BLOCKS (72 registers) when the batch
+// fills the GPU, MW2_BLOCKS / 2 (no spills, 122 registers) for small ensembles, where a step lasts as long as one
+// walker's chain and more registers shorten it by 8 % (profiles/README.md).  Same PTX, same results.
+template <int NLAT, int NT, int BL>
+__global__ void __launch_bounds__(32 * NLAT, BL * (3 - NLAT)) k_mc_run2(const __grid_constant__ DeviceState S,
+                                                                         const __grid_constant__ McParams p, int ncycles, int chunk)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, W = S.W;
+    int* s_unit = at<int>(smem + NLAT * Lay<NT>(S.N).LB(), Lay<NT>::sUNIT);
+    const bool single = chunk >= ncycles;                   // one unit per walker: nothing is ever published
+    for (;;) {
+        if (tid == 0) {
+            int q = atomicAdd(S.qctr, 1), wi = -1;
+            if (q < W) wi = q;
+            else if (!single) {
+                const int* slot = S.queue + (q - W);
+                for (;;) {
+                    int v;
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
+                    if (v) { wi = v - 1; break; }
+                    int done;
+                    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(S.qctr + 2) : "memory");
+                    if (done >= W) break;                   // every walker finished: no entry will follow
+                    __nanosleep(500);
+                }
+            }
+            *s_unit = (wi < 0) ? -1 : (wi | (q < W ? (1 << 30) : 0));
+        }
+        __syncthreads();
+        const int u = *s_unit;
+        if (u < 0) return;
+        const int wi = u & ((1 << 30) - 1);
+        const bool more = run_walker<NLAT, NT>(S, p, smem, wi, ncycles, single ? 0 : chunk, (u >> 30) != 0);
+        __threadfence();
+        __syncthreads();                                    // the image is stored; s_unit and smem may be reused
+        if (tid == 0) {
+            if (more) {
+                const int t = atomicAdd(S.qctr + 1, 1);
+                __threadfence();
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(S.queue + t), "r"(wi + 1) : "memory");
+            } else {
+                __threadfence();
+                atomicAdd(S.qctr + 2, 1);
+            }
+        }
+    }
 }
 
 }  // namespace v2

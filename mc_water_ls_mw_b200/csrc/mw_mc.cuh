@@ -65,6 +65,13 @@ struct DeviceState {
     double* therm;      // [W][therm_cap][THERM_ROW]
     int*    therm_n;    // [W] rows recorded since the last drain (may exceed therm_cap: the excess was dropped)
     int     therm_int, therm_cap;
+    // scheduling of the warp-per-lattice walker kernel (mw2.cuh: persistent blocks take (walker, chunk of cycles)
+    // units from a queue in global memory)
+    int*    queue;      // [units of the launch] 0 = not yet published, else walker + 1
+    int*    qctr;       // [0] entries taken, [1] entries published after the initial W, [2] walkers finished,
+                        // [4..5] (64 bit) cycles completed by all walkers at unit boundaries
+    int*    cyc_end;    // [W] cycle number at which the walker's part of the launch ends
+    unsigned long long* wtime;   // [W][2] %globaltimer at the start of the walker's first / the end of its last unit
 };
 constexpr int THERM_ROW = 16;   // icyc, ls, E(1:2), ls_mu, volume(1:2), hmatrix(:,:,1)
 

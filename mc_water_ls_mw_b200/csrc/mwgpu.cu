@@ -67,6 +67,9 @@ struct mwgpu_ctx {
     int* skip = nullptr;           // [W] guard flags of mc_check_flatness
     double* gather = nullptr;      // [size][NB] windows of all ranks (dd joins over several GPUs)
     size_t gather_doubles = 0;
+    size_t queue_ints = 0;         // capacity of S.queue
+    int chunk_cycles = 0;          // cycles per unit of work of the walker kernel; 0: automatic
+    int max_blocks = 0;            // blocks of the walker kernel; 0: as many as the GPU holds at once
     int64_t launches = 0;
     float last_ms = 0.f;
     std::vector<double> h_mubin, h_binwidth;
@@ -130,6 +133,9 @@ extern "C" int mwgpu_create(int nwater, int nlat, int nwalkers, int device, mwgp
     rc |= dalloc(&S.nn, W * L * N);
     rc |= dalloc(&S.scal, W);
     rc |= dalloc(&S.transcount, W * N);
+    rc |= dalloc(&S.qctr, 8);
+    rc |= dalloc(&S.cyc_end, W);
+    rc |= dalloc(&S.wtime, W * 2);
     c->stage_doubles = W * L * (2 * 3 * N + 9);
     rc |= dalloc(&c->stage, c->stage_doubles);
     c->out_doubles = W * 2 > N ? W * 2 : N;
@@ -158,7 +164,7 @@ extern "C" void mwgpu_destroy(mwgpu_ctx* c)
     void* ptrs[] = {S.pos, S.ref, S.cell, S.recip, S.refcell, S.iv, S.niv, S.list, S.nn, S.scal,
                     S.weight, S.hist, S.uhist, S.wbase, S.hbase, S.ubase, S.transcount, S.mubin,
                     S.binwidth, S.ginv, S.hinc, S.edge, c->stage, c->out, c->iout, c->delta, c->fifo,
-                    c->book, c->skip, c->gather, S.therm, S.therm_n};
+                    c->book, c->skip, c->gather, S.therm, S.therm_n, S.queue, S.qctr, S.cyc_end, S.wtime};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1039,10 +1045,31 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
         CUDA_TRY(cudaFuncSetAttribute(k_mc_run<NLAT_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_mc_run<NLAT_, NT_><<<c->W, 32, smem, c->stream>>>(c->S, c->P, ncycles);                                 \
     } while (0)
+    // The warp-per-lattice kernel is persistent: as many blocks as the GPU holds at once (never more than walkers)
+    // take (walker, chunk of cycles) units from a queue.  A batch that fits the GPU at once runs one unit per walker;
+    // a larger one is cut into units of MW2_CHUNK cycles so that it does not end on its slowest walkers (mw2.cuh).
 #define MW_LAUNCH_MC2(NLAT_, NT_, BL_)                                                                            \
     do {                                                                                                          \
-        CUDA_TRY(cudaFuncSetAttribute(v2::k_mc_run2<NLAT_, NT_, BL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
-        v2::k_mc_run2<NLAT_, NT_, BL_><<<c->W, 32 * NLAT_, smem2, c->stream>>>(c->S, c->P, ncycles);              \
+        auto kern = v2::k_mc_run2<NLAT_, NT_, BL_>;                                                               \
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));            \
+        int per_sm = 0;                                                                                           \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * NLAT_, smem2));                \
+        if (per_sm < 1) return fail("mwgpu_mc_run: the walker kernel does not fit on an SM");                     \
+        long long slots = (long long)per_sm * c->num_sms;                                                         \
+        if (c->max_blocks > 0) slots = std::min<long long>(slots, c->max_blocks);                                 \
+        const int grid = (int)std::min<long long>(c->W, slots);                                                   \
+        int chunk = ncycles > 0 ? ncycles : 1;                                                                    \
+        if (c->chunk_cycles > 0) chunk = std::min(chunk, c->chunk_cycles);                                        \
+        else if (c->W > slots) chunk = std::min(chunk, MW2_CHUNK);                                                \
+        const size_t units = (size_t)c->W * ((size_t)(ncycles + chunk - 1) / chunk + 1);                          \
+        if (units > c->queue_ints) {                                                                              \
+            if (c->S.queue) { CUDA_TRY(cudaStreamSynchronize(c->stream)); cudaFree(c->S.queue); c->S.queue = nullptr; } \
+            if (int rc = dalloc(&c->S.queue, units)) return rc;                                                   \
+            c->queue_ints = units;                                                                                \
+        }                                                                                                         \
+        if (chunk < ncycles) CUDA_TRY(cudaMemsetAsync(c->S.queue, 0, sizeof(int) * units, c->stream));            \
+        CUDA_TRY(cudaMemsetAsync(c->S.qctr, 0, sizeof(int) * 8, c->stream));                                      \
+        kern<<<grid, 32 * NLAT_, smem2, c->stream>>>(c->S, c->P, ncycles, chunk);                                 \
     } while (0)
     // boxes of up to 64 molecules: one warp per lattice on a per-lattice shared-memory block (mw2.cuh); larger
     // boxes (and walker_kernel == 1): the first-generation kernel, one warp per walker
@@ -1075,6 +1102,23 @@ extern "C" int mwgpu_mc_set_kernel(mwgpu_ctx* c, int warps_per_walker)
         return fail("mwgpu_mc_set_kernel: the warp-per-lattice kernel needs boxes of up to 64 molecules");
     c->walker_kernel = warps_per_walker;
     c->energy_kernel = (warps_per_walker == 1) ? 1 : 0;       // generation 1 keeps its own batched energy kernel
+    return 0;
+}
+
+extern "C" int mwgpu_mc_set_schedule(mwgpu_ctx* c, int chunk_cycles, int max_blocks)
+{
+    if (!c) return fail("mwgpu_mc_set_schedule: NULL context");
+    if (chunk_cycles < 0 || max_blocks < 0) return fail("mwgpu_mc_set_schedule: chunk_cycles and max_blocks must be >= 0 (0 = automatic)");
+    c->chunk_cycles = chunk_cycles; c->max_blocks = max_blocks;
+    return 0;
+}
+
+extern "C" int mwgpu_mc_get_walker_times(mwgpu_ctx* c, uint64_t* start_end_ns)
+{
+    if (int rc = check_ctx(c, 0, false)) return rc;
+    if (!start_end_ns) return fail("mwgpu_mc_get_walker_times: NULL");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(start_end_ns, c->S.wtime, sizeof(uint64_t) * 2 * (size_t)c->W, cudaMemcpyDeviceToHost));
     return 0;
 }
 

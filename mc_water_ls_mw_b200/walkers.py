@@ -323,6 +323,17 @@ class WalkerBatch:
         check(self.L.mwgpu_kernel_launches(self.h, C.byref(n)))
         return n.value
 
+    def set_schedule(self, chunk_cycles: int = 0, max_blocks: int = 0) -> None:
+        """Cycles per unit of work and number of persistent blocks of the walker kernel (0 = automatic);
+        never changes a result."""
+        check(self.L.mwgpu_mc_set_schedule(self.h, int(chunk_cycles), int(max_blocks)))
+
+    def walker_times(self) -> np.ndarray:
+        """[W, 2] uint64: %globaltimer ns at the start / end of every walker's part of the last mc_run launch."""
+        t = np.zeros((self.nwalkers, 2), dtype=np.uint64)
+        check(self.L.mwgpu_mc_get_walker_times(self.h, t.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return t
+
 
 def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(128)

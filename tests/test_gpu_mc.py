@@ -145,6 +145,40 @@ def test_batch_walkers_equal_independent_single_walkers():
     assert len(set(mus)) == nw                                        # the walkers really are independent
 
 
+@pytest.mark.parametrize("ex,chunk,blocks", [
+    ("ice1_gen_weights", 3, 5),      # 12 walkers through 5 persistent blocks in units of 3 cycles (Wang-Landau updates)
+    ("ice1_sample", 1, 3),           # every cycle a unit: the queue turns over 12 x 20 times
+    ("ice1_sample", 7, 0),           # units, but a block per walker
+    ("single_box", 2, 4),            # one-lattice instantiation
+])
+def test_unit_scheduler_never_changes_a_result(ex, chunk, blocks):
+    """A launch cut into (walker, chunk of cycles) units taken from the device queue by a few persistent blocks
+    (the form every batch larger than the GPU runs in, mw2.cuh) == the serial chains of the oracle, bit for bit,
+    including a walker that stops early and the volume moves of the deck."""
+    nw, ncyc = 12, 20
+    ov = {"eq_mc_cycles": 4, "mc_vol_prob": 0.02}
+    g, up = make_gpu_walkers(ex, nwalkers=nw, overrides=ov)
+    os_ = make_oracle_walkers(ex, nw, overrides=ov)
+    g.set_schedule(chunk, blocks)
+    g.set_rng_philox(SEED, 7, 1000000)
+    for w, o in enumerate(os_):
+        o.set_rng_philox(SEED, 7 + w, 1000000)
+        assert o.mc_run(ncyc) == 0
+    g.mc_run(9); g.mc_run(ncyc - 9)                                  # two launches, the second one starts mid-chain
+    for w, o in enumerate(os_):
+        _compare(g, o, up, walker=w)
+    t = g.walker_times()
+    assert (t[:, 1] > t[:, 0]).all()
+    # the automatic schedule gives the same chains
+    g2, _ = make_gpu_walkers(ex, nwalkers=nw, overrides=ov)
+    g2.set_rng_philox(SEED, 7, 1000000)
+    g2.mc_run(ncyc)
+    for w in range(nw):
+        np.testing.assert_array_equal(g2.download(w)[0], g.download(w)[0])
+        assert list(g2.state(w).accepted) == list(g.state(w).accepted)
+        assert g2.state(w).model_energy[0] == g.state(w).model_energy[0]
+
+
 def test_delta_allreduce_of_bins_matches_reference_semantics():
     """comms_allreduce_eta/hist (comms_mpi.f90:244-277,461-493) over the walkers of one context."""
     from oracle import orc
