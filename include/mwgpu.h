@@ -177,7 +177,9 @@ int  mwgpu_mc_set_rng_fifo(mwgpu_ctx *ctx, const double *u, int64_t n);
 int  mwgpu_mc_run(mwgpu_ctx *ctx, int ncycles);
 /* Which walker kernel mwgpu_mc_run uses: 0 = automatic (default), 1 = one warp per walker, 2 = two warps per walker,
  * one per lattice -- the per-lattice loops of mc_moves.F90:1007-1018, :1076-1090 side by side (two lattices, up to 64
- * molecules).  Both produce the same chain: positions / lists / counters bit for bit, energies to 1e-11. */
+ * molecules), 4 = two warps per lattice, which also split the bond / triplet loops of compute_local_real_energy
+ * (molint.F90:276-404) of one lattice (at most four walkers per SM; never chosen automatically: it shortens a walker's
+ * step by ~1.5 %).  All produce the same chain: positions / lists / counters bit for bit, energies to 1e-11. */
 int  mwgpu_mc_set_kernel(mwgpu_ctx *ctx, int warps_per_walker);
 int  mwgpu_mc_run_async(mwgpu_ctx *ctx, int ncycles);     /* no host synchronisation */
 int  mwgpu_synchronize(mwgpu_ctx *ctx);

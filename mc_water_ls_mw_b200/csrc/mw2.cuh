@@ -596,8 +596,19 @@ __device__ __forceinline__ void reduce2(double& a0, double& a1)
 // compute_local_real_energy(imol) at the old position and -- when with_new -- at the trial position T[0..2] of the
 // block (molint.F90:220-404; mc_moves.F90:1010,1083).  Returns the energies (uniform), the in-range slot masks of
 // imol's row for both positions, and error bits.
-template <int NT>
-__device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb, int imol, bool with_new,
+// WPL = warps per lattice.  WPL == 2 (small ensembles, where a step lasts as long as one walker's serial chain):
+// the two warps of a lattice run stage 1 and the item table redundantly (same values, no exchange), then split
+// the work: warp `sub` takes the item passes sub, sub + 2, ... (the bond records of pass 0 cross through the
+// lattice's named barrier `bar`) and the i-centred pairs of variant `sub` (0 old, 1 new).  The energies returned
+// are this warp's PARTIAL sums; the caller adds the two warps' parts.
+__device__ __forceinline__ void lat_bar(int bar)
+{
+    if (bar == 1) asm volatile("bar.sync 1, 64;" ::: "memory");         // immediates: the block reserves 3 barriers, not 16
+    else asm volatile("bar.sync 2, 64;" ::: "memory");
+}
+
+template <int NT, int WPL>
+__device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb, int imol, bool with_new, int sub, int bar,
                                               double& eo, double& en, uint32_t& mo, uint32_t& mn)
 {
     const int N = Y.N(), lane = lane_id();
@@ -702,8 +713,9 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
             __syncwarp();
             // ---- items: geometry, radial functions, one exponential; own bonds leave their record and pair
             // energy, candidates close the j-centred triplets of both variants
+            bool synced = (WPL == 1);
 #pragma unroll 1
-            for (int t0 = first; t0 < nitems; t0 += 32) {
+            for (int t0 = first + 32 * sub; t0 < nitems; t0 += 32 * WPL) {
                 const int t = t0 + lane;
                 const bool in = t < nitems;
                 const uint32_t d = items[in ? t : first];
@@ -735,6 +747,7 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
                     }
                     __syncwarp();
                 }
+                if (WPL == 2 && !synced) { lat_bar(bar); synced = true; }   // the records of pass 0 reach the other warp
                 {
                     const uint32_t ra = (d >> 11) & 31u, rb = (d >> 16) & 31u;
                     const bool cand = ok && ty == 0u;
@@ -752,13 +765,48 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
                 }
             }
             __syncwarp();
+            if (WPL == 2) {
+                if (!synced) lat_bar(bar);                               // a warp without a pass in this round
+                if (step != 32) lat_bar(bar);                            // the item table is rewritten by the next round
+            }
             if (step == 32) break;
         }
 
         // ---- triplets centred on imol: all unordered pairs of bond records of one variant (rotation pairing:
         // record at position pos of a segment of n pairs with (pos + d) mod n, d = 1 .. n/2).  Up to 16 records
         // (nearly always) take two lanes each: lanes 0-15 the odd steps d, lanes 16-31 the even ones.
-        {
+        if (WPL == 2) {
+            // this warp: the records of variant `sub`; 4 / 2 / 1 lanes per record take the steps d = d0, d0 + 4 / 2 / 1, ...
+            const int nv = sub ? nw : no, base = sub ? no : 0;
+            const int sh = (nv <= 8) ? 3 : (nv <= 16) ? 4 : 5;
+            const int stride = 32 >> sh;
+            const int pos = lane & ((1 << sh) - 1);
+            const bool act = pos < nv;
+            const int n = act ? nv : 0;
+            const int r = base + pos;
+            const int half = n >> 1, send = base + n;
+            const bool even = !(n & 1);
+            const int rr = act ? r : 0;
+            const double ux = q[rr], uy = q[RC2 + rr], uz = q[2 * RC2 + rr];
+            const double g = act ? q[3 * RC2 + rr] : 0.0;
+            const uint32_t jr = recj[rr];
+            const int maxd = nv >> 1;
+            double tb = 0.0;
+#pragma unroll 1
+            for (int d = 1 + (lane >> sh); d <= maxd; d += stride) {
+                int c = r + d;
+                c = (c >= send) ? c - n : c;
+                const bool on = (d <= half) && !(even && d == half && pos >= half);
+                c = on ? c : rr;
+                const double ct = ux * q[c] + uy * q[RC2 + c] + uz * q[2 * RC2 + c];
+                const double mult = (recj[c] == jr) ? 3.0 : 1.0;
+                const double dd = ct - CK.cos0;
+                if (on && ct < CK.c099) tb += q[3 * RC2 + c] * (dd * dd) * mult;
+            }
+            tb *= CK.leps * g;
+            if (sub) an += tb; else ao += tb;
+            if (npass == 2) lat_bar(bar);                                // the records are rewritten by the second pass
+        } else {
             const int stride = (nown <= 16) ? 2 : 1;
             const int r = (stride == 2) ? (lane & 15) : lane;
             const bool act = r < nown;
@@ -844,15 +892,17 @@ __device__ __forceinline__ int generate_moves(const Lay<NT> Y, unsigned char* sm
 // progress of the batch (qctr[4..5] = cycles completed by all walkers), so that slow walkers -- more bonds per
 // molecule -- hold their blocks longer and all walkers reach the end of the launch together.
 // Returns (uniform over the block) whether the walker has cycles left in this launch.
-template <int NLAT, int NT>
+template <int NLAT, int NT, int WPL>
 __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams& p, unsigned char* smem, int wi, int ncycles_launch,
                                            int chunk, bool first)
 {
+    static_assert(WPL == 1 || (WPL == 2 && NLAT == 2), "two warps per lattice: lattice-switch boxes only");
+    constexpr int NTHR = 32 * NLAT * WPL;
     const Lay<NT> Y(S.N);
     const int tid = threadIdx.x, lane = tid & 31;
     const int N = Y.N();
     unsigned char* sb = smem + NLAT * Y.LB();
-    load_walker<NT>(Y, S, wi, smem, tid, 32 * NLAT);
+    load_walker<NT>(Y, S, wi, smem, tid, NTHR);
     // Which warp takes lattice 1 -- and with it the serial acceptance -- alternates with the hardware warp slot:
     // the two warps of a walker sit on neighbouring schedulers (slot % 4), and with a fixed assignment every
     // scheduler pair would carry all its acceptance warps on one side (measured: 77 % / 46 % issue-active).
@@ -862,7 +912,11 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
         *at<int>(sb, Lay<NT>::sSWAP) = (int)((wslot >> 2) & 1u);
     }
     __syncthreads();
-    const int lat = (NLAT == 2) ? ((tid >> 5) ^ *at<int>(sb, Lay<NT>::sSWAP)) : 0;
+    const int sub = (WPL == 2) ? ((tid >> 5) & 1) : 0;                 // WPL == 2: warps 2L, 2L+1 share lattice L
+    const int lat = (NLAT == 2) ? ((tid >> (WPL == 2 ? 6 : 5)) ^ *at<int>(sb, Lay<NT>::sSWAP)) : 0;
+    const bool prim = (sub == 0);                                       // the lattice's warp that commits and rebuilds
+    const bool accw = (lat == 0) && prim;                               // the warp that carries the serial acceptance
+    const int lbar = 1 + lat;                                           // named barrier of the lattice's two warps
     unsigned char* lb = smem + lat * Y.LB();
     WalkerScalars* sc = at<WalkerScalars>(sb, Lay<NT>::sSC);
     uint64_t* rngbase = at<uint64_t>(sb, Lay<NT>::sRB);
@@ -883,8 +937,8 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
     const int ncycles = cyc_end - cycle0;
     int rng_pos = 0;
 
-    compute_bond_masks<NT>(Y, lb);
-    if (lat == 0) {
+    if (prim) compute_bond_masks<NT>(Y, lb);
+    if (accw) {
         if (p.prob_error) err |= ERR_PROB;
         const uint64_t idx = sc->rng_index;
         __syncwarp();
@@ -906,7 +960,7 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
     int klast = p.nbins / 2 + 1;                                        // bin of the previous move's order parameter
     for (int cyc = 0; cyc < ncycles && !stop; ++cyc) {
         const int cycle = cycle0 + cyc + 1;
-        if (lat == 0) {
+        if (accw) {
             __syncwarp();
             if (lane == 0) {
                 sc->cycle = cycle;
@@ -919,9 +973,12 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
             __syncwarp();
             if (ctl[CTL_STOP]) err |= ERR_WINDOW;
         }
-        if (cycle % p.list_update_int == 0) {                          // :218-222, each warp its lattice
-            err |= compute_neighbours<NT>(Y, lb);
-            compute_bond_masks<NT>(Y, lb);
+        if (cycle % p.list_update_int == 0) {                          // :218-222, each lattice by its (first) warp
+            if (prim) {
+                err |= compute_neighbours<NT>(Y, lb);
+                compute_bond_masks<NT>(Y, lb);
+            }
+            if (WPL == 2) lat_bar(lbar);
         }
         const bool dd_eq = p.dd && (cycle < p.eq_mc_cycles);
         const bool bins_on = !(cycle < p.eq_mc_cycles);                // mc_update_wl_bins: :1615
@@ -931,7 +988,7 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
 
         int imove = 0;
         while (imove < N) {                                            // :224-250, GB moves per batch
-            if (lat == 0) {
+            if (accw) {
                 // every batch starts with a refill at the current draw index (the buffer starts at an even index)
                 const uint64_t next = *rngbase + (uint64_t)rng_pos;
                 __syncwarp();
@@ -964,13 +1021,14 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
                 }
                 double eo, en;
                 uint32_t mo, mn;
-                err |= local_energies<NT>(Y, lb, imol, true, eo, en, mo, mn);
+                err |= local_energies<NT, WPL>(Y, lb, imol, true, sub, lbar, eo, en, mo, mn);
                 double* xch = at<double>(sb, Lay<NT>::sXCH);
                 if (NLAT == 2) {
-                    if (lane == 0) { xch[lat * 2] = eo; xch[lat * 2 + 1] = en; }
+                    if (lane == 0) { xch[(lat * WPL + sub) * 2] = eo; xch[(lat * WPL + sub) * 2 + 1] = en; }
                     __syncthreads();                                    // A: both lattices' energies
                 }
-                if (lat == 0) {
+                if (accw) {
+                    if (WPL == 2) { eo = xch[0] + xch[2]; en = xch[1] + xch[3]; }     // the two warps' parts
                     if (lane == 0) atomicAdd(S.transcount + (size_t)wi * N + imol, 1);
                     const double* u = rngbuf + rng_pos + m * D;
                     // model_energy bookkeeping exactly as :1013-1016, :1087-1090
@@ -986,7 +1044,7 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
                             eta_acc = eta_rej = eb.eta; k_acc = k_rej = eb.k;
                         }
                     } else {
-                        const double eo1 = xch[2], en1 = xch[3];
+                        const double eo1 = (WPL == 2) ? xch[4] + xch[6] : xch[2], en1 = (WPL == 2) ? xch[5] + xch[7] : xch[3];
                         Eb1 = sc->E[1]; Ea1 = (Eb1 - eo1) + en1; dE1 = en1 - eo1;
                         const double dm = (dE0 - dE1) * p.beta;
                         mu_acc = mu_old + dm;                           // :1113
@@ -1062,7 +1120,9 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
                 if (NLAT == 2) __syncthreads();                         // B: the decision
                 const int dec = ctl[CTL_DEC];
                 one = (dec & 2) != 0;
-                if (dec & 1) {
+                if (!prim) {
+                    // the lattice's first warp commits / restores
+                } else if (dec & 1) {
                     // commit: new position, own bond mask, and the reverse bits of the bonds that formed / broke
                     uint32_t* BM = at<uint32_t>(lb, Y.oBM());
                     if (lane < 3) P[lane * N + imol] = T[lane];
@@ -1078,14 +1138,15 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
                     P[lane * N + imol] = xs(T[lane], T[3 + lane]);
                 }
                 __syncwarp();
+                if (WPL == 2) lat_bar(lbar);
             }
             imove += nr;
-            if (lat == 0) rng_pos += nr * D;
+            if (accw) rng_pos += nr * D;
             if (nr < nb) {
                 // ---------------- rare move types (warp 0; warp 1 waits at the next batch barrier) ----------------
                 // a volume move works on both lattice blocks: warp 1 must be through with its commit / restore
                 if (NLAT == 2) __syncthreads();
-                if (lat == 0) {
+                if (accw) {
                     const double xi = rngbuf[rng_pos];
                     rng_pos += 1;
                     if (xi < p.volP) {
@@ -1114,7 +1175,7 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
             }
         }
         if (stop) break;
-        if (lat == 0) {
+        if (accw) {
             __syncwarp();
             if (lane == 0) {
 #pragma unroll
@@ -1159,7 +1220,7 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
         }
     }
     __syncthreads();
-    if (lat == 0 && lane == 0) {
+    if (accw && lane == 0) {
         const uint64_t idx = *rngbase + (uint64_t)rng_pos;
         if (p.rng_mode == 1 && idx > S.fifo_len) err |= ERR_RNG_UNDERRUN;
         sc->rng_index = idx;
@@ -1168,7 +1229,7 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
     if (lane == 0 && err) atomicOr(&sc->error, err);
     __syncthreads();
     const bool more = !ctl[CTL_STOP] && sc->cycle < cyc_end;
-    store_walker<NT>(Y, S, wi, smem, tid, 32 * NLAT);
+    store_walker<NT>(Y, S, wi, smem, tid, NTHR);
     if (tid == 0 && !more) S.wtime[2 * wi + 1] = globaltimer_ns();
     return more;
 }
@@ -1187,8 +1248,8 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
 // BL = resident walkers per SM the register allocation is bounded for: MW2_BLOCKS (72 registers) when the batch
 // fills the GPU, MW2_BLOCKS / 2 (no spills, 122 registers) for small ensembles, where a step lasts as long as one
 // walker's chain and more registers shorten it by 8 % (profiles/README.md).  Same PTX, same results.
-template <int NLAT, int NT, int BL>
-__global__ void __launch_bounds__(32 * NLAT, BL * (3 - NLAT)) k_mc_run2(const __grid_constant__ DeviceState S,
+template <int NLAT, int NT, int BL, int WPL>
+__global__ void __launch_bounds__(32 * NLAT * WPL, BL * (3 - NLAT)) k_mc_run2(const __grid_constant__ DeviceState S,
                                                                          const __grid_constant__ McParams p, int ncycles, int chunk)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -1217,7 +1278,7 @@ __global__ void __launch_bounds__(32 * NLAT, BL * (3 - NLAT)) k_mc_run2(const __
         const int u = *s_unit;
         if (u < 0) return;
         const int wi = u & ((1 << 30) - 1);
-        const bool more = run_walker<NLAT, NT>(S, p, smem, wi, ncycles, single ? 0 : chunk, (u >> 30) != 0);
+        const bool more = run_walker<NLAT, NT, WPL>(S, p, smem, wi, ncycles, single ? 0 : chunk, (u >> 30) != 0);
         __threadfence();
         __syncthreads();                                    // the image is stored; s_unit and smem may be reused
         if (tid == 0) {

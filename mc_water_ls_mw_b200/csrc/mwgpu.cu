@@ -51,7 +51,7 @@ struct mwgpu_ctx {
     McParams P{};
     mwgpu_mc_params user{};
     bool mc_ready = false, energy_ready = false;
-    int walker_kernel = 0;         // 0: automatic, 1: one warp per walker, 2: two warps per walker (one per lattice)
+    int walker_kernel = 0;         // 0: automatic, 1: one warp per walker, 2: one warp per lattice, 4: two warps per lattice
     int energy_kernel = 0;         // batched full energy: 0 flattened-entry kernel (mw2_energy.cuh), 1 first generation
     int first_rank = 0, size = 1;
     int num_sms = 148;
@@ -1048,12 +1048,13 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
     // The warp-per-lattice kernel is persistent: as many blocks as the GPU holds at once (never more than walkers)
     // take (walker, chunk of cycles) units from a queue.  A batch that fits the GPU at once runs one unit per walker;
     // a larger one is cut into units of MW2_CHUNK cycles so that it does not end on its slowest walkers (mw2.cuh).
-#define MW_LAUNCH_MC2(NLAT_, NT_, BL_)                                                                            \
+#define MW_LAUNCH_MC2(NLAT_, NT_, BL_, WPL_)                                                                          \
     do {                                                                                                          \
-        auto kern = v2::k_mc_run2<NLAT_, NT_, BL_>;                                                               \
+        auto kern = v2::k_mc_run2<NLAT_, NT_, BL_, WPL_>;                                                         \
+        constexpr int nthr = 32 * NLAT_ * WPL_;                                                                   \
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));            \
         int per_sm = 0;                                                                                           \
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * NLAT_, smem2));                \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthr, smem2));                      \
         if (per_sm < 1) return fail("mwgpu_mc_run: the walker kernel does not fit on an SM");                     \
         long long slots = (long long)per_sm * c->num_sms;                                                         \
         if (c->max_blocks > 0) slots = std::min<long long>(slots, c->max_blocks);                                 \
@@ -1069,7 +1070,7 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
         }                                                                                                         \
         if (chunk < ncycles) CUDA_TRY(cudaMemsetAsync(c->S.queue, 0, sizeof(int) * units, c->stream));            \
         CUDA_TRY(cudaMemsetAsync(c->S.qctr, 0, sizeof(int) * 8, c->stream));                                      \
-        kern<<<grid, 32 * NLAT_, smem2, c->stream>>>(c->S, c->P, ncycles, chunk);                                 \
+        kern<<<grid, nthr, smem2, c->stream>>>(c->S, c->P, ncycles, chunk);                                       \
     } while (0)
     // boxes of up to 64 molecules: one warp per lattice on a per-lattice shared-memory block (mw2.cuh); larger
     // boxes (and walker_kernel == 1): the first-generation kernel, one warp per walker
@@ -1077,11 +1078,17 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
     const size_t smem2 = v2::walker_bytes(c->N, c->nlat);
     // small ensembles (at most MW2_BLOCKS / 2 walkers per SM): the instantiation with the larger register budget
     const bool small = (long long)c->W * 2 <= (long long)c->num_sms * MW2_BLOCKS;
-    if (gen2 && c->nlat == 2) {
-        if (c->N == 48) { if (small) MW_LAUNCH_MC2(2, 48, MW2_BLOCKS / 2); else MW_LAUNCH_MC2(2, 48, MW2_BLOCKS); }
-        else MW_LAUNCH_MC2(2, 0, MW2_BLOCKS);
+    // Two warps per lattice (four per walker) on request only: measured on 512 walkers per GPU the split of the item
+    // passes and pair sums of one lattice shortens a walker's step by 1.5 % -- the serial acceptance (35 % of a move)
+    // and the dependent chains inside one pass bound it, not the number of passes (profiles/README.md).
+    const bool quad = c->nlat == 2 && c->walker_kernel == 4;
+    if (gen2 && quad) {
+        if (c->N == 48) MW_LAUNCH_MC2(2, 48, 4, 2); else MW_LAUNCH_MC2(2, 0, 4, 2);
+    } else if (gen2 && c->nlat == 2) {
+        if (c->N == 48) { if (small) MW_LAUNCH_MC2(2, 48, MW2_BLOCKS / 2, 1); else MW_LAUNCH_MC2(2, 48, MW2_BLOCKS, 1); }
+        else MW_LAUNCH_MC2(2, 0, MW2_BLOCKS, 1);
     } else if (gen2) {
-        if (c->N == 48) MW_LAUNCH_MC2(1, 48, MW2_BLOCKS); else MW_LAUNCH_MC2(1, 0, MW2_BLOCKS);
+        if (c->N == 48) MW_LAUNCH_MC2(1, 48, MW2_BLOCKS, 1); else MW_LAUNCH_MC2(1, 0, MW2_BLOCKS, 1);
     }
     else if (c->nlat == 2)    { if (c->N == 48) MW_LAUNCH_MC(2, 48); else MW_LAUNCH_MC(2, 0); }
     else                      { if (c->N == 48) MW_LAUNCH_MC(1, 48); else MW_LAUNCH_MC(1, 0); }
@@ -1097,9 +1104,12 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
 extern "C" int mwgpu_mc_set_kernel(mwgpu_ctx* c, int warps_per_walker)
 {
     if (!c) return fail("mwgpu_mc_set_kernel: NULL context");
-    if (warps_per_walker < 0 || warps_per_walker > 2) return fail("mwgpu_mc_set_kernel: 0 (automatic), 1 or 2 warps per walker");
-    if (warps_per_walker == 2 && !ent_has_rev(c->N))
-        return fail("mwgpu_mc_set_kernel: the warp-per-lattice kernel needs boxes of up to 64 molecules");
+    if (warps_per_walker != 0 && warps_per_walker != 1 && warps_per_walker != 2 && warps_per_walker != 4)
+        return fail("mwgpu_mc_set_kernel: 0 (automatic), 1, 2 or 4 warps per walker");
+    if (warps_per_walker >= 2 && !ent_has_rev(c->N))
+        return fail("mwgpu_mc_set_kernel: the warp-per-lattice kernels need boxes of up to 64 molecules");
+    if (warps_per_walker == 4 && c->nlat != 2)
+        return fail("mwgpu_mc_set_kernel: four warps per walker = two per lattice of a lattice-switch box");
     c->walker_kernel = warps_per_walker;
     c->energy_kernel = (warps_per_walker == 1) ? 1 : 0;       // generation 1 keeps its own batched energy kernel
     return 0;

@@ -172,7 +172,7 @@ class WalkerBatch:
         self.mc_run(1)
 
     def set_kernel(self, warps_per_walker: int) -> None:
-        """0 = automatic, 1 = one warp per walker, 2 = one warp per lattice (mwgpu_mc_set_kernel)."""
+        """0 = automatic, 1 = one warp per walker, 2 = one warp per lattice, 4 = two warps per lattice (mwgpu_mc_set_kernel)."""
         check(self.L.mwgpu_mc_set_kernel(self.h, int(warps_per_walker)))
 
     def mc_run_async(self, ncycles: int) -> None:

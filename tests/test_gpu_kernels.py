@@ -1,9 +1,11 @@
-"""Both walker kernels against the oracle and against each other.
+"""The walker kernels against the oracle and against each other.
 
 mwgpu_mc_set_kernel(1): one warp per walker (first generation, mw_mc.cuh -- what boxes of more than 64 molecules
 run); (2): one warp per LATTICE on a per-lattice shared-memory block (mw2.cuh, the default for the reference's
-48-molecule boxes; mc_moves.F90:1007-1018, :1076-1090 are the per-lattice loops it runs side by side).  Same bar for
-both: positions / cell / lists / counters / random-number consumption bit-exact, energies 1e-11 relative."""
+48-molecule boxes; mc_moves.F90:1007-1018, :1076-1090 are the per-lattice loops it runs side by side); (4): two warps
+per lattice (the two warps of a lattice split the item passes and the old / new pair sums of
+compute_local_real_energy, molint.F90:276-404; on request only).  Same bar for
+all: positions / cell / lists / counters / random-number consumption bit-exact, energies 1e-11 relative."""
 import numpy as np
 import pytest
 
@@ -35,7 +37,7 @@ def _same_state(g, o, up, w=0):
     np.testing.assert_allclose(ug, o.unbiased_hist, rtol=1e-9, atol=1e-300)
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 4])
 @pytest.mark.parametrize("ex,ncyc,ov", [
     ("ice1_sample", 45, {"eq_mc_cycles": 5}),
     ("ice1_gen_weights", 45, {"eq_mc_cycles": 5}),
@@ -49,6 +51,8 @@ def _same_state(g, o, up, w=0):
 def test_chain_bit_exact_on_both_kernels(kernel, ex, ncyc, ov):
     o, up = make_oracle_walker(ex, overrides=ov)
     g, _ = make_gpu_walkers(ex, overrides=ov)
+    if kernel == 4 and up.num_lattices == 1:
+        pytest.skip("four warps per walker = two per lattice of a lattice-switch box")
     g.set_kernel(kernel)
     o.set_rng_philox(SEED, 7, 1000000); g.set_rng_philox(SEED, 7, 1000000)
     done = 0
@@ -68,7 +72,7 @@ def test_kernels_agree_on_a_batch_and_are_deterministic():
     nw, ncyc = 256, 40
     ov = {"eq_mc_cycles": 2, "mc_vol_prob": 0.03}
     out = []
-    for kernel in (1, 2, 2):
+    for kernel in (1, 2, 2, 4, 4):
         g, up = make_gpu_walkers("ice1_sample", nwalkers=nw, overrides=ov)
         g.set_kernel(kernel)
         g.set_rng_philox(SEED, 0, 1000000)
@@ -78,11 +82,13 @@ def test_kernels_agree_on_a_batch_and_are_deterministic():
         assert not any(s.error for s in st)
         out.append((g.download_all(), np.array([[s.accepted[0], s.accepted[1], s.accepted[2], s.rng_index, s.ls] for s in st]),
                     np.array([list(s.model_energy) for s in st])))
-    for a, b in ((out[0], out[1]), (out[1], out[2])):
+    for a, b in ((out[0], out[1]), (out[1], out[2]), (out[2], out[3]), (out[3], out[4])):
         for x, y in zip(a[0], b[0]):
             np.testing.assert_array_equal(x, y)
         np.testing.assert_array_equal(a[1], b[1])
     assert rel_err(out[0][2], out[1][2]) < TOL
+    assert rel_err(out[2][2], out[3][2]) < TOL
+    np.testing.assert_array_equal(out[3][2], out[4][2])
     np.testing.assert_array_equal(out[1][2], out[2][2])                     # same kernel: same bits in the energies too
 
 
@@ -91,7 +97,11 @@ def test_kernel_selection_errors():
     g, _ = make_gpu_walkers("ice1_sample")
     with pytest.raises(MwgpuError):
         g.set_kernel(3)
+    g.set_kernel(4)
     g.set_kernel(0)
+    g1, _ = make_gpu_walkers("single_box")
+    with pytest.raises(MwgpuError):
+        g1.set_kernel(4)
 
 
 def test_crowded_cells_split_the_variants():
@@ -110,7 +120,7 @@ def test_crowded_cells_split_the_variants():
     from mc_water_ls_mw_b200._lib import MwgpuError
     o.set_rng_philox(SEED, 0, 1000000)
     assert o.mc_run(6) == 0
-    for kernel in (2, 1):
+    for kernel in (2, 4, 1):
         g = W.WalkerBatch(up.nwater, up.num_lattices, 1)
         g.upload(ljr, hm); g.energy_init()
         g.mc_init(W.params_from_user(up), 0, 1, w, wl)
