@@ -1037,11 +1037,13 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
                     const double mu_old = sc->mu;
                     double diffkT, mu_acc = mu_old, mu_rej = mu_old, eta_acc = 0.0, eta_rej = 0.0;
                     int k_acc = 0, k_rej = 0;
+                    double cinc = 0.0;       // histogram increment of the lane's bin, requested as soon as the bin is known
                     if (NLAT == 1) {
                         diffkT = p.beta * dE0;
                         if (bins_on) {       // single box: ls_mu is never assigned (0) but the bins are still updated
                             const EtaBin eb = eta_bin(p, S.mubin, S.ginv, sc, wgt, mu_old);
                             eta_acc = eta_rej = eb.eta; k_acc = k_rej = eb.k;
+                            if (eb.k >= 1 && eb.k <= p.nbins) cinc = __ldg(S.hinc + eb.k - 1);
                         }
                     } else {
                         const double eo1 = (WPL == 2) ? xch[4] + xch[6] : xch[2], en1 = (WPL == 2) ? xch[5] + xch[7] : xch[3];
@@ -1052,7 +1054,10 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
                         // three weight look-ups in parallel lanes: eta(mu), eta(mu_acc), eta(mu_rej)
                         const double mine = (lane == 0) ? mu_old : (lane == 1) ? mu_acc : mu_rej;
                         EtaBin eb; eb.eta = 0.0; eb.k = 0;
-                        if (lane < 3) eb = eta_bin_near(p, S, sc, wgt, mine, klast);
+                        if (lane < 3) {
+                            eb = eta_bin_near(p, S, sc, wgt, mine, klast);
+                            if (bins_on && eb.k >= 1 && eb.k <= p.nbins) cinc = __ldg(S.hinc + eb.k - 1);
+                        }
                         const double eta_old = __shfl_sync(FULL, eb.eta, 0);
                         eta_acc = __shfl_sync(FULL, eb.eta, 1); eta_rej = __shfl_sync(FULL, eb.eta, 2);
                         k_acc = __shfl_sync(FULL, eb.k, 1); k_rej = __shfl_sync(FULL, eb.k, 2);
@@ -1100,8 +1105,8 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
                     // (the bin of the order parameter BEFORE the switch of this move, as in the reference's order)
                     const int kb = accepted ? k_acc : k_rej;
                     klast = kb;
+                    const double c = (NLAT == 1) ? cinc : __shfl_sync(FULL, cinc, accepted ? 1 : 2);
                     if (bins_on && kb >= 1 && kb <= p.nbins) {
-                        const double c = __ldg(S.hinc + kb - 1);
                         if (lane == 0) atomicAdd(hist + kb - 1, c);
                         if (p.samplerun) {
                             const double uf = __shfl_sync(FULL, ex, accepted ? 3 : 4);

@@ -247,6 +247,30 @@ __device__ __forceinline__ EtaBin eta_bin_near(const McParams& p, const DeviceSt
 {
     EtaBin r;
     const int nb = p.nbins;
+    // Fast path: mu is still in the bin of the guess (the usual case) and that bin is an inner bin of the window.
+    // Everything eta_weight needs around the guess is requested at once -- bin edges, mid-bin values, weights and
+    // gradient factors of the bins g-1, g, g+1 -- so the look-up waits for ONE round trip to the L1 / L2 instead
+    // of three dependent ones (edge -> mid-bin value -> weights); the arithmetic is eta_of_bin's, term for term.
+    if (nb >= 3 && p.eta_interp) {
+        const int g = min(max(kguess, 2), nb - 1);
+        const bool ro = p.samplerun != 0;
+        const double* w = wgt - 1;
+        const double* mb = S.mubin - 1;
+        const double e0 = __ldg(S.edge + g - 1), e1 = __ldg(S.edge + g);
+        const double m_m = __ldg(mb + g - 1), m_0 = __ldg(mb + g);
+        const double w_m = ro ? __ldg(w + g - 1) : __ldcg(w + g - 1), w_0 = ro ? __ldg(w + g) : __ldcg(w + g),
+                     w_p = ro ? __ldg(w + g + 1) : __ldcg(w + g + 1);
+        const double g_m = __ldg(S.ginv + g - 2), g_0 = __ldg(S.ginv + g - 1);
+        if (sc->in_window && !(mu < sc->mu_lo || mu > sc->mu_hi) && (mu > e0 + 1e-9) && (mu < e1 - 1e-9) &&
+            g != sc->start_bin && g != sc->end_bin) {
+            const bool up = mu > m_0;                        // gradient between bins g, g+1 anchored at g; else g-1, g at g-1
+            const double wa = up ? w_0 : w_m, wb = up ? w_p : w_0;
+            const double gg = (wb - wa) * (up ? g_0 : g_m);
+            r.k = g;
+            r.eta = wa + (mu - (up ? m_0 : m_m)) * gg;
+            return r;
+        }
+    }
     int k = min(max(kguess, 1), nb);
     double lo = __ldg(S.edge + k - 1), hi = __ldg(S.edge + k);
     if (mu >= hi && k < nb) { ++k; lo = hi; hi = __ldg(S.edge + k); }
