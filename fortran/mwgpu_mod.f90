@@ -203,12 +203,27 @@ module mwgpu
        integer(c_int64_t),value  :: index
      end function mwgpu_mc_set_rng_index
 
-     ! which walker kernel mwgpu_mc_run uses: 0 automatic, 1 one warp per walker, 2 one warp per lattice
+     ! which walker kernel mwgpu_mc_run uses: 0 automatic, 1 one warp per walker, 2 one warp per lattice,
+     ! 4 two warps per lattice
      integer(c_int) function mwgpu_mc_set_kernel(ctx,warps_per_walker) bind(C,name='mwgpu_mc_set_kernel')
        import :: c_int,c_ptr
        type(c_ptr),value    :: ctx
        integer(c_int),value :: warps_per_walker
      end function mwgpu_mc_set_kernel
+
+     ! scheduling of a launch: MC cycles per unit of work, persistent blocks (0 = automatic); never changes a result
+     integer(c_int) function mwgpu_mc_set_schedule(ctx,chunk_cycles,max_blocks) bind(C,name='mwgpu_mc_set_schedule')
+       import :: c_int,c_ptr
+       type(c_ptr),value    :: ctx
+       integer(c_int),value :: chunk_cycles,max_blocks
+     end function mwgpu_mc_set_schedule
+
+     ! %globaltimer (ns) at the start / end of every walker's part of the last mwgpu_mc_run: start_end_ns(2,nwalkers)
+     integer(c_int) function mwgpu_mc_get_walker_times(ctx,start_end_ns) bind(C,name='mwgpu_mc_get_walker_times')
+       import :: c_int,c_ptr,c_int64_t
+       type(c_ptr),value  :: ctx
+       integer(c_int64_t) :: start_end_ns(*)
+     end function mwgpu_mc_get_walker_times
 
      integer(c_int) function mwgpu_mc_set_rng_fifo(ctx,u,n) bind(C,name='mwgpu_mc_set_rng_fifo')
        import :: c_int,c_ptr,c_int64_t,c_double
