@@ -1062,6 +1062,7 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
         int chunk = ncycles > 0 ? ncycles : 1;                                                                    \
         if (c->chunk_cycles > 0) chunk = std::min(chunk, c->chunk_cycles);                                        \
         else if (c->W > slots) chunk = std::min(chunk, MW2_CHUNK);                                                \
+        chunk = std::max(chunk, (ncycles + 511) / 512);       /* at most 512 turns per walker: bounds the queue */        \
         const size_t units = (size_t)c->W * ((size_t)(ncycles + chunk - 1) / chunk + 1);                          \
         if (units > c->queue_ints) {                                                                              \
             if (c->S.queue) { CUDA_TRY(cudaStreamSynchronize(c->stream)); cudaFree(c->S.queue); c->S.queue = nullptr; } \
