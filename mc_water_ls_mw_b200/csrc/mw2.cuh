@@ -678,36 +678,41 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
         const uint32_t bmj0 = (go || gn) ? (BM[j] & ~excl) : 0u;
         const uint32_t dbase = ((uint32_t)j << 5) | ((go ? ro : IT_NONE) << 11) | ((gn ? rn : IT_NONE) << 16);
 
-        // ---- rounds: all centres at once when their candidates fit the table (always, at physical densities),
-        // else two centre lanes per round
+        // ---- rounds: one, when the candidates fit the table beside the own bonds (nearly always); a dense walker
+        // (ten bonds per molecule: > 96 items) takes its candidates in windows of the table's free part, two or
+        // three rounds (windows of the candidate enumeration, not of the centres: a centre's candidates may straddle
+        // two rounds)
         int incl0 = __popc(bmj0);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int t = __shfl_up_sync(FULL, incl0, d);
             if (lane >= d) incl0 += t;
         }
-        const int step = (nown + __shfl_sync(FULL, incl0, 31) <= IT2) ? 32 : 2;
+        const int ncand = __shfl_sync(FULL, incl0, 31);
+        const int cap = IT2 - nown;                            // nown < RC2: at least 65 entries
+        const int nrounds = (ncand <= cap) ? 1 : (ncand + cap - 1) / cap;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 32; c0 += step) {
-            uint32_t bmj = bmj0;
-            int incl = incl0;
-            if (step != 32) {
-                bmj = (lane >= c0 && lane < c0 + step) ? bmj0 : 0u;
-                incl = __popc(bmj);
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(FULL, incl, d);
-                    if (lane >= d) incl += t;
-                }
-            }
-            const int first = (c0 == 0) ? 0 : nown;           // own bonds are evaluated in the first round only
-            const int nitems = nown + __shfl_sync(FULL, incl, 31);
-            {
-                uint32_t* it = items + (nown + incl - __popc(bmj));
+        for (int rd = 0; rd < nrounds; ++rd) {
+            const int first = (rd == 0) ? 0 : nown;            // own bonds are evaluated in the first round only
+            int nitems = nown + ncand;
+            if (nrounds == 1) {
+                uint32_t bmj = bmj0;
+                uint32_t* it = items + (nown + incl0 - __popc(bmj0));
 #pragma unroll 1
                 while (bmj) {
                     const int s2 = __ffs(bmj) - 1; bmj &= bmj - 1;
                     *it++ = dbase | (uint32_t)s2;
+                }
+            } else {
+                const int lo = rd * cap, hi = min(ncand, lo + cap);
+                nitems = nown + (hi - lo);
+                uint32_t bmj = bmj0;
+                int gi = incl0 - __popc(bmj0);
+#pragma unroll 1
+                while (bmj) {
+                    const int s2 = __ffs(bmj) - 1; bmj &= bmj - 1;
+                    if (gi >= lo && gi < hi) items[nown + gi - lo] = dbase | (uint32_t)s2;
+                    ++gi;
                 }
             }
             __syncwarp();
@@ -767,9 +772,8 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
             __syncwarp();
             if (WPL == 2) {
                 if (!synced) lat_bar(bar);                               // a warp without a pass in this round
-                if (step != 32) lat_bar(bar);                            // the item table is rewritten by the next round
+                if (nrounds > 1) lat_bar(bar);                           // the item table is rewritten by the next round
             }
-            if (step == 32) break;
         }
 
         // ---- triplets centred on imol: all unordered pairs of bond records of one variant (rotation pairing:
