@@ -607,7 +607,9 @@ __device__ __forceinline__ void lat_bar(int bar)
     else asm volatile("bar.sync 2, 64;" ::: "memory");
 }
 
-template <int NT, int WPL>
+// ILP == 2 (one warp per lattice, at most four walkers per SM: registers to spare and nothing else to issue): two
+// item passes in flight per loop turn, their dependent chains (geometry -> 1/r -> exponential) interleaved.
+template <int NT, int WPL, int ILP>
 __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb, int imol, bool with_new, int sub, int bar,
                                               double& eo, double& en, uint32_t& mo, uint32_t& mn)
 {
@@ -719,54 +721,76 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
             // ---- items: geometry, radial functions, one exponential; own bonds leave their record and pair
             // energy, candidates close the j-centred triplets of both variants
             bool synced = (WPL == 1);
-#pragma unroll 1
-            for (int t0 = first + 32 * sub; t0 < nitems; t0 += 32 * WPL) {
-                const int t = t0 + lane;
+            // one item: the geometry of "list slot of a row, seen from a centre", 1/r, the exponential
+            struct Item { uint32_t d; double ux, uy, uz, g, ir, e1, e_4; bool ok; };
+            auto item_at = [&](int t0_) -> Item {
+                Item a;
+                const int t = t0_ + lane;
                 const bool in = t < nitems;
-                const uint32_t d = items[in ? t : first];
-                const uint32_t ty = d >> 21;
-                const uint32_t e2 = L[((d >> 5) & 63u) * LC + (d & 31u)];
+                a.d = items[in ? t : first];
+                const uint32_t ty = a.d >> 21;
+                const uint32_t e2 = L[((a.d >> 5) & 63u) * LC + (a.d & 31u)];
                 const int k = e2 & 63, im2 = e2 >> 11;
                 // centre: a molecule of the block, or the trial position
-                const double* cp = (ty == 2u) ? T : P + ((d >> 5) & 63u);
+                const double* cp = (ty == 2u) ? T : P + ((a.d >> 5) & 63u);
                 const int cs = (ty == 2u) ? 1 : N;
                 const double tx = (P[k] + V[im2]) - cp[0];
                 const double ty_ = (P[N + k] + V[IVC + im2]) - cp[cs];
                 const double tz = (P[2 * N + k] + V[2 * IVC + im2]) - cp[2 * cs];
                 const double sq0 = dist2(tx, ty_, tz);
-                const bool ok = in && (sq0 < CK.rcc2);
-                const double sq = ok ? sq0 : CK.ss;                    // any length inside the cut-off
-                double ir, isr;
-                bond_radial(sq, ir, isr);
-                const double e1 = exp_nc(CK.sig02 * isr);              // exp(sigma*isr) = e1^5, exp(gamma*sigma*isr) = e1^6
-                const double e_2 = e1 * e1, e_4 = e_2 * e_2;
-                const double g = e_4 * e_2;
-                const double ux = tx * ir, uy = ty_ * ir, uz = tz * ir;
-                if (t0 == 0) {                                          // all own bonds sit in the first 32 items
-                    if (ok && ty != 0u) {
-                        const int r = (d >> 11) & 31;
-                        q[r] = ux; q[RC2 + r] = uy; q[2 * RC2 + r] = uz; q[3 * RC2 + r] = g;
-                        const double s2 = CK.ss * ir * ir;
-                        const double pe = CK.aeps * (CK.bigb * (s2 * s2) - 1.0) * (e_4 * e1);
-                        if (ty == 1u) ao += pe; else an += pe;
-                    }
-                    __syncwarp();
+                a.ok = in && (sq0 < CK.rcc2);
+                const double sq = a.ok ? sq0 : CK.ss;                  // any length inside the cut-off
+                double isr;
+                bond_radial(sq, a.ir, isr);
+                a.e1 = exp_nc(CK.sig02 * isr);                         // exp(sigma*isr) = e1^5, exp(gamma*sigma*isr) = e1^6
+                const double e_2 = a.e1 * a.e1;
+                a.e_4 = e_2 * e_2;
+                a.g = a.e_4 * e_2;
+                a.ux = tx * a.ir; a.uy = ty_ * a.ir; a.uz = tz * a.ir;
+                return a;
+            };
+            // own bonds (all in the first 32 items) leave their record and pair energy
+            auto own_bond = [&](const Item& a) {
+                const uint32_t ty = a.d >> 21;
+                if (a.ok && ty != 0u) {
+                    const int r = (a.d >> 11) & 31;
+                    q[r] = a.ux; q[RC2 + r] = a.uy; q[2 * RC2 + r] = a.uz; q[3 * RC2 + r] = a.g;
+                    const double s2 = CK.ss * a.ir * a.ir;
+                    const double pe = CK.aeps * (CK.bigb * (s2 * s2) - 1.0) * (a.e_4 * a.e1);
+                    if (ty == 1u) ao += pe; else an += pe;
                 }
-                if (WPL == 2 && !synced) { lat_bar(bar); synced = true; }   // the records of pass 0 reach the other warp
-                {
-                    const uint32_t ra = (d >> 11) & 31u, rb = (d >> 16) & 31u;
-                    const bool cand = ok && ty == 0u;
-                    const bool ho = cand && ra != IT_NONE, hn = cand && rb != IT_NONE;
-                    const int io = ho ? (int)ra : 0, in_ = hn ? (int)rb : 0;
-                    const double ex = CK.leps * g;
-                    const double cto = -(q[io] * ux + q[RC2 + io] * uy + q[2 * RC2 + io] * uz);
-                    const double d_o = cto - CK.cos0;
-                    const double vo = q[3 * RC2 + io] * ex * (d_o * d_o);
-                    if (ho && cto < CK.c099) ao += vo;                  // the cos < 0.99 filter of molint.F90:367-371
-                    const double ctn = -(q[in_] * ux + q[RC2 + in_] * uy + q[2 * RC2 + in_] * uz);
-                    const double dn = ctn - CK.cos0;
-                    const double vn = q[3 * RC2 + in_] * ex * (dn * dn);
-                    if (hn && ctn < CK.c099) an += vn;
+            };
+            // candidates close the j-centred triplets of both variants
+            auto candidate = [&](const Item& a) {
+                const uint32_t ra = (a.d >> 11) & 31u, rb = (a.d >> 16) & 31u;
+                const bool cand = a.ok && (a.d >> 21) == 0u;
+                const bool ho = cand && ra != IT_NONE, hn = cand && rb != IT_NONE;
+                const int io = ho ? (int)ra : 0, in_ = hn ? (int)rb : 0;
+                const double ex = CK.leps * a.g;
+                const double cto = -(q[io] * a.ux + q[RC2 + io] * a.uy + q[2 * RC2 + io] * a.uz);
+                const double d_o = cto - CK.cos0;
+                const double vo = q[3 * RC2 + io] * ex * (d_o * d_o);
+                if (ho && cto < CK.c099) ao += vo;                      // the cos < 0.99 filter of molint.F90:367-371
+                const double ctn = -(q[in_] * a.ux + q[RC2 + in_] * a.uy + q[2 * RC2 + in_] * a.uz);
+                const double dn = ctn - CK.cos0;
+                const double vn = q[3 * RC2 + in_] * ex * (dn * dn);
+                if (hn && ctn < CK.c099) an += vn;
+            };
+            if (ILP == 2) {
+#pragma unroll 1
+                for (int t0 = first; t0 < nitems; t0 += 64) {
+                    const Item a = item_at(t0), b = item_at(t0 + 32);
+                    if (t0 == 0) { own_bond(a); __syncwarp(); }
+                    candidate(a);
+                    candidate(b);
+                }
+            } else {
+#pragma unroll 1
+                for (int t0 = first + 32 * sub; t0 < nitems; t0 += 32 * WPL) {
+                    const Item a = item_at(t0);
+                    if (t0 == 0) { own_bond(a); __syncwarp(); }
+                    if (WPL == 2 && !synced) { lat_bar(bar); synced = true; }   // the records of pass 0 reach the other warp
+                    candidate(a);
                 }
             }
             __syncwarp();
@@ -896,11 +920,12 @@ __device__ __forceinline__ int generate_moves(const Lay<NT> Y, unsigned char* sm
 // progress of the batch (qctr[4..5] = cycles completed by all walkers), so that slow walkers -- more bonds per
 // molecule -- hold their blocks longer and all walkers reach the end of the launch together.
 // Returns (uniform over the block) whether the walker has cycles left in this launch.
-template <int NLAT, int NT, int WPL>
+template <int NLAT, int NT, int WPL, int ILP>
 __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams& p, unsigned char* smem, int wi, int ncycles_launch,
                                            int chunk, bool first)
 {
     static_assert(WPL == 1 || (WPL == 2 && NLAT == 2), "two warps per lattice: lattice-switch boxes only");
+    static_assert(ILP == 1 || WPL == 1, "two passes in flight: one warp per lattice");
     constexpr int NTHR = 32 * NLAT * WPL;
     const Lay<NT> Y(S.N);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -1025,7 +1050,7 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
                 }
                 double eo, en;
                 uint32_t mo, mn;
-                err |= local_energies<NT, WPL>(Y, lb, imol, true, sub, lbar, eo, en, mo, mn);
+                err |= local_energies<NT, WPL, ILP>(Y, lb, imol, true, sub, lbar, eo, en, mo, mn);
                 double* xch = at<double>(sb, Lay<NT>::sXCH);
                 if (NLAT == 2) {
                     if (lane == 0) { xch[(lat * WPL + sub) * 2] = eo; xch[(lat * WPL + sub) * 2 + 1] = en; }
@@ -1257,7 +1282,7 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
 // BL = resident walkers per SM the register allocation is bounded for: MW2_BLOCKS (72 registers) when the batch
 // fills the GPU, MW2_BLOCKS / 2 (no spills, 122 registers) for small ensembles, where a step lasts as long as one
 // walker's chain and more registers shorten it by 8 % (profiles/README.md).  Same PTX, same results.
-template <int NLAT, int NT, int BL, int WPL>
+template <int NLAT, int NT, int BL, int WPL, int ILP>
 __global__ void __launch_bounds__(32 * NLAT * WPL, BL * (3 - NLAT)) k_mc_run2(const __grid_constant__ DeviceState S,
                                                                          const __grid_constant__ McParams p, int ncycles, int chunk)
 {
@@ -1287,7 +1312,7 @@ __global__ void __launch_bounds__(32 * NLAT * WPL, BL * (3 - NLAT)) k_mc_run2(co
         const int u = *s_unit;
         if (u < 0) return;
         const int wi = u & ((1 << 30) - 1);
-        const bool more = run_walker<NLAT, NT, WPL>(S, p, smem, wi, ncycles, single ? 0 : chunk, (u >> 30) != 0);
+        const bool more = run_walker<NLAT, NT, WPL, ILP>(S, p, smem, wi, ncycles, single ? 0 : chunk, (u >> 30) != 0);
         __threadfence();
         __syncthreads();                                    // the image is stored; s_unit and smem may be reused
         if (tid == 0) {

@@ -1048,9 +1048,9 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
     // The warp-per-lattice kernel is persistent: as many blocks as the GPU holds at once (never more than walkers)
     // take (walker, chunk of cycles) units from a queue.  A batch that fits the GPU at once runs one unit per walker;
     // a larger one is cut into units of MW2_CHUNK cycles so that it does not end on its slowest walkers (mw2.cuh).
-#define MW_LAUNCH_MC2(NLAT_, NT_, BL_, WPL_)                                                                          \
+#define MW_LAUNCH_MC2(NLAT_, NT_, BL_, WPL_, ILP_)                                                                    \
     do {                                                                                                          \
-        auto kern = v2::k_mc_run2<NLAT_, NT_, BL_, WPL_>;                                                         \
+        auto kern = v2::k_mc_run2<NLAT_, NT_, BL_, WPL_, ILP_>;                                                   \
         constexpr int nthr = 32 * NLAT_ * WPL_;                                                                   \
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));            \
         int per_sm = 0;                                                                                           \
@@ -1084,12 +1084,18 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
     // and the dependent chains inside one pass bound it, not the number of passes (profiles/README.md).
     const bool quad = c->nlat == 2 && c->walker_kernel == 4;
     if (gen2 && quad) {
-        if (c->N == 48) MW_LAUNCH_MC2(2, 48, 4, 2); else MW_LAUNCH_MC2(2, 0, 4, 2);
+        if (c->N == 48) MW_LAUNCH_MC2(2, 48, 4, 2, 1); else MW_LAUNCH_MC2(2, 0, 4, 2, 1);
     } else if (gen2 && c->nlat == 2) {
-        if (c->N == 48) { if (small) MW_LAUNCH_MC2(2, 48, MW2_BLOCKS / 2, 1); else MW_LAUNCH_MC2(2, 48, MW2_BLOCKS, 1); }
-        else MW_LAUNCH_MC2(2, 0, MW2_BLOCKS, 1);
+        // at most four walkers per SM: two item passes in flight per warp (registers to spare, idle issue slots)
+        const bool tiny = (long long)c->W <= 4ll * c->num_sms;
+        if (c->N == 48) {
+            if (tiny) MW_LAUNCH_MC2(2, 48, 4, 1, 2);
+            else if (small) MW_LAUNCH_MC2(2, 48, MW2_BLOCKS / 2, 1, 1);
+            else MW_LAUNCH_MC2(2, 48, MW2_BLOCKS, 1, 1);
+        }
+        else MW_LAUNCH_MC2(2, 0, MW2_BLOCKS, 1, 1);
     } else if (gen2) {
-        if (c->N == 48) MW_LAUNCH_MC2(1, 48, MW2_BLOCKS, 1); else MW_LAUNCH_MC2(1, 0, MW2_BLOCKS, 1);
+        if (c->N == 48) MW_LAUNCH_MC2(1, 48, MW2_BLOCKS, 1, 1); else MW_LAUNCH_MC2(1, 0, MW2_BLOCKS, 1, 1);
     }
     else if (c->nlat == 2)    { if (c->N == 48) MW_LAUNCH_MC(2, 48); else MW_LAUNCH_MC(2, 0); }
     else                      { if (c->N == 48) MW_LAUNCH_MC(1, 48); else MW_LAUNCH_MC(1, 0); }

@@ -13,7 +13,7 @@ g.mc_init(W.params_from_user(up), 0, nw, w, wl)
 g.set_rng_philox(20141211, 0, 1000000)
 for _ in range(2):
     g.mc_run(500); g.mc_monitor()
-for mode in (250, 16, 8, 4, 2, 1, 8, 4):
+for mode in (250, 32, 16, 8, 4, 16, 8, 32):
     g.set_schedule(mode, 0)
     ts = []
     for i in range(6):
