@@ -133,8 +133,10 @@ def _config(nw: int, total: int, C: int, nwater: int = 48, cpu: bool = False):
                     f"{EXAMPLE} deck (48 mW molecules per lattice, cubic<->hexagonal ice, 200 K, 1 atm, fixed weights), "
                     f"production phase after {PREP_CYCLES} equilibration cycles",
         **work, "cycles_per_step": C,
-        "l2_policy": "walker state (~75 MB for 4096 walkers) is read from and written back to global memory once per step; "
-                     "the hot loop runs out of shared memory, so cache state between steps does not matter",
+        "l2_policy": "walker state (~75 MB for 4096 walkers) lives in global memory; a walker's 15 KB image is loaded into shared "
+                     "memory for every turn on a persistent block (every 8 cycles unless the walker is behind the batch's average "
+                     "progress, when the batch exceeds the resident blocks) and stored back; the hot loop runs out of shared "
+                     "memory, so cache state between steps does not matter",
         "rng": "Philox-4x32-10, one stream per walker",
     }
 

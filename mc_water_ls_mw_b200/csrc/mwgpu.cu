@@ -1086,8 +1086,10 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
     if (gen2 && quad) {
         if (c->N == 48) MW_LAUNCH_MC2(2, 48, 4, 2, 1); else MW_LAUNCH_MC2(2, 0, 4, 2, 1);
     } else if (gen2 && c->nlat == 2) {
-        // at most four walkers per SM: two item passes in flight per warp (registers to spare, idle issue slots)
-        const bool tiny = (long long)c->W <= 4ll * c->num_sms;
+        // at most four walkers per SM: two item passes in flight per warp (registers to spare, idle issue slots);
+        // automatic selection only -- an explicit mwgpu_mc_set_kernel(2) keeps one pass per turn, the code the full
+        // GPU runs, so the parity tests hold both forms to the oracle
+        const bool tiny = c->walker_kernel == 0 && (long long)c->W <= 4ll * c->num_sms;
         if (c->N == 48) {
             if (tiny) MW_LAUNCH_MC2(2, 48, 4, 1, 2);
             else if (small) MW_LAUNCH_MC2(2, 48, MW2_BLOCKS / 2, 1, 1);
