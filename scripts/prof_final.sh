@@ -5,7 +5,7 @@
 set -e
 tag=$1
 cd /root/repo
-K2=_ZN2mw2v29k_mc_run2ILi2ELi48ELi14ELi1EEEvNS_11DeviceStateENS_8McParamsEii
+K2=_ZN2mw2v29k_mc_run2ILi2ELi48ELi14ELi1ELi1EEEvNS_11DeviceStateENS_8McParamsEii
 bash scripts/gpurun_retry.sh --timeout 2400 -- "python bench.py --steps 10 --warmup 3 > gpurun_out/final_bench_$tag.json 2> gpurun_out/final_bench_$tag.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/final_launches_$tag.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/final_ncu1.log 2>&1; \
 ncu --set full --clock-control none --import-source on -k regex:k_mc_run2 -s 6 -c 1 -f -o gpurun_out/final_mc_$tag python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/final_ncu2.log 2>&1; \
