@@ -489,13 +489,16 @@ def run_ours(args):
     import ctypes as Ct
     states = (W.WalkerState * nw)()
 
+    bufs = [(hl, hr, hh), (out_l.numpy(), out_r.numpy(), out_h.numpy())]
+
     def e2e_step():
-        g.upload_all(hl, hh, hr)                        # H2D: positions, reference positions, cells
+        (il, ir, ih), (ol, or_, oh) = bufs
+        g.upload_all(il, ih, ir)                        # H2D: positions, reference positions, cells
         g.energy_init()                                 # lists + energies + mu, as after a checkpoint load
         g.mc_run(C)
-        W.check(g.L.mwgpu_download_all(g.h, W._dp(out_l.numpy()), W._dp(out_r.numpy()), W._dp(out_h.numpy())))
+        W.check(g.L.mwgpu_download_all(g.h, W._dp(ol), W._dp(or_), W._dp(oh)))
         W.check(g.L.mwgpu_mc_get_states(g.h, states))   # D2H: energies, mu, volumes, counters
-        hl[...] = out_l.numpy(); hr[...] = out_r.numpy(); hh[...] = out_h.numpy()
+        bufs.reverse()                                  # this step's result is the next step's input (no host copy)
 
     for _ in range(max(1, min(args.warmup, 3))):
         e2e_step()
