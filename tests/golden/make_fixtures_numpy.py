@@ -1,6 +1,7 @@
 """Generates tests/golden/numpy_vectors.npz from the independent numpy restatement (ref_numpy.py): lists, full and
 local energies of both lattices, and the state after 3 MC cycles (accept / reject sequence, positions, counters,
-bins) of ice1_sample and single_box under a host FIFO of random numbers.  tests/test_oracle_numpy.py holds the C
+bins) of ice1_sample, single_box, ice1_gen_weights and of single windows of the two domain-decomposed decks
+under a host FIFO of random numbers.  tests/test_oracle_numpy.py holds the C
 oracle to these vectors.
 
     python tests/golden/make_fixtures_numpy.py
@@ -18,16 +19,23 @@ from mc_water_ls_mw_b200 import decks          # input readers only (namelists, 
 from tests.golden import ref_numpy as R
 
 CASES = {
-    # deck: (overrides, cycles, rng seed)
-    "ice1_sample": ({"eq_mc_cycles": 1, "mc_vol_prob": 0.04, "list_update_int": 2}, 3, 101),
-    "single_box": ({"eq_mc_cycles": 1, "mc_vol_prob": 0.04, "list_update_int": 2}, 3, 202),
-    "ice1_gen_weights": ({"eq_mc_cycles": 1, "list_update_int": 2}, 2, 303),
+    # key: (deck, overrides, cycles, rng seed, rank, size)
+    "ice1_sample": ("ice1_sample", {"eq_mc_cycles": 1, "mc_vol_prob": 0.04, "list_update_int": 2}, 3, 101, 0, 1),
+    "single_box": ("single_box", {"eq_mc_cycles": 1, "mc_vol_prob": 0.04, "list_update_int": 2}, 3, 202, 0, 1),
+    "ice1_gen_weights": ("ice1_gen_weights", {"eq_mc_cycles": 1, "list_update_int": 2}, 2, 303, 0, 1),
+    # domain decomposition over the order parameter (mc_moves.F90:660-703): window 1 of 4 never holds the walker
+    # (equilibration phase: no weights, no switches, no bins); window 3 of 4 holds it from the start (production
+    # phase from cycle 2: in-window weights, out-of-window rejections, switches, unbiased histogram); the weight
+    # generation deck updates the window's weights only (:1682-1685)
+    "ice1_sample_dd@0of4": ("ice1_sample_dd", {"eq_mc_cycles": 100, "mc_vol_prob": 0.04, "list_update_int": 2}, 3, 404, 0, 4),
+    "ice1_sample_dd@2of4": ("ice1_sample_dd", {"eq_mc_cycles": 2, "mc_vol_prob": 0.04, "list_update_int": 2}, 3, 505, 2, 4),
+    "ice1_gen_weights_dd@2of4": ("ice1_gen_weights_dd", {"eq_mc_cycles": 2, "list_update_int": 2}, 3, 606, 2, 4),
 }
 
 
-def load(name, ov):
+def load(name, ov, size=1):
     d = os.path.join(HERE, "examples", name)
-    up = decks.read_input(os.path.join(d, "ice.input"))
+    up = decks.read_input(os.path.join(d, "ice.input"), size=size)        # io.f90:249: one rank = no overlap
     for k, v in ov.items():
         setattr(up, k, v)
     h, r = decks.read_config(d, up)
@@ -40,9 +48,9 @@ def load(name, ov):
 
 def main():
     out = {}
-    for name, (ov, ncyc, seed) in CASES.items():
-        up, h, r, w, wl = load(name, ov)
-        b = R.Box(up, h, r, weights=w, file_wl_factor=wl)
+    for name, (deck, ov, ncyc, seed, rank, size) in CASES.items():
+        up, h, r, w, wl = load(deck, ov, size)
+        b = R.Box(up, h, r, weights=w, file_wl_factor=wl, rank=rank, size=size)
         nl, N = b.nlat, b.N
         out[f"{name}/nn"] = np.array(b.nn, dtype=np.int32)
         out[f"{name}/jn"] = np.array(b.jn, dtype=np.int32)
@@ -53,6 +61,8 @@ def main():
         out[f"{name}/mu_bin"] = np.array(b.mu_bin)
         out[f"{name}/binwidth"] = np.array(b.binwidth)
         out[f"{name}/scalars"] = np.array([b.r_pos, b.r_neg, b.av_binwidth, b.log_unbiased_norm])
+        out[f"{name}/window"] = np.array([b.my_start_bin, b.my_end_bin, b.my_mu_min, b.my_mu_max, b.ls])
+        out[f"{name}/weight0"] = np.array(b.weight)
         u = np.random.default_rng(seed).random(8 * N * ncyc + 16)
         out[f"{name}/fifo"] = u
         b.set_fifo(u)

@@ -12,7 +12,8 @@ keb721/mc_water_ls_mw, not from oracle/mw_oracle.c -- used to pin the C oracle (
     mc_volume                   mc_moves.F90:1216-1534
     mc_lattice_switch           mc_moves.F90:1536-1594
     mc_update_wl_bins           mc_moves.F90:1597-1689
-    move loop of mc_cycle       mc_moves.F90:145-255
+    move loop of mc_cycle       mc_moves.F90:145-255 (incl. the 'dd' window check :181-208 and the switch ban :237,:244)
+    'dd' windows of mc_init     mc_moves.F90:660-703, :808-812
 
 Everything is IEEE double arithmetic in the reference's operation order (Python floats never contract into FMAs);
 1-based indices are kept in the list arrays (jn, vn) as the reference stores them.  Random numbers come from a
@@ -296,11 +297,45 @@ class Box:
                 else:
                     lun = math.log(incr) + self.weight[k] + math.log(1.0 + math.exp(lun - self.weight[k]) / incr)
             self.log_unbiased_norm = lun
-        # 'mw' strategy: the whole range is this rank's window
-        self.my_start_bin, self.my_end_bin = 1, nb
-        self.my_mu_min, self.my_mu_max = up.mu_min, up.mu_max
-        self.walker_in_window = True
         self.ls = up.ls
+        self.dd = (getattr(up, "parallel_strategy", "mw") == "dd")
+        if self.dd:                                               # :660-703 (1-based bins, sums left to right)
+            def bsum(n):
+                t = 0.0
+                for i in range(n):
+                    t = t + bw[i]
+                return t
+            ov = up.window_overlap
+            bpw = nb // size
+            if rank == 0:
+                self.my_start_bin = 1
+                self.my_end_bin = bpw + ov
+                self.my_mu_min = up.mu_min
+                self.my_mu_max = up.mu_min + bsum(self.my_end_bin)
+            if size > 1:
+                if 1 <= rank <= size - 2:
+                    self.my_start_bin = rank * bpw - ov
+                    self.my_end_bin = (rank + 1) * bpw + ov
+                    self.my_mu_min = up.mu_min + bsum(self.my_start_bin - 1)
+                    self.my_mu_max = up.mu_min + bsum(self.my_end_bin)
+                if rank == size - 1:
+                    self.my_start_bin = rank * bpw - ov
+                    self.my_end_bin = nb
+                    self.my_mu_min = up.mu_min + bsum(self.my_start_bin - 1)
+                    self.my_mu_max = up.mu_max
+            if self.my_mu_max < 0.0: self.ls = 1
+            if self.my_mu_min > 0.0: self.ls = 2
+            if self.nlat == 2:                                    # :808-812
+                for i in range(0, self.my_start_bin - 1):
+                    self.weight[i] = 0.0
+                for i in range(self.my_end_bin, nb):
+                    self.weight[i] = 0.0
+            self.walker_in_window = False                         # :112, set by the first cycles (:181-208)
+        else:
+            # 'mw' strategy: the whole range is this rank's window (:712-718, :872)
+            self.my_start_bin, self.my_end_bin = 1, nb
+            self.my_mu_min, self.my_mu_max = up.mu_min, up.mu_max
+            self.walker_in_window = True
         beta = 1.0 / (KB * up.temperature)
         self.ref_enthalpy = [self.model_energy[l] + (up.pressure * self.volume[l] if up.mc_ensemble == "npt" else 0.0)
                              for l in range(self.nlat)]            # main.f90:146-150
@@ -552,9 +587,18 @@ class Box:
         for i in range(self.my_start_bin - 1, self.my_end_bin):
             self.weight[i] = self.weight[i] - minbin
 
-    def mc_cycle(self):                                           # :145-255 ('mw' strategy)
+    def mc_cycle(self):                                           # :145-255
         up = self.up
         self.mc_cycle_num += 1
+        if self.dd:                                               # :181-208
+            if self.mc_cycle_num < up.eq_mc_cycles:
+                self.walker_in_window = (self.ls_mu > self.my_mu_min) and (self.ls_mu < self.my_mu_max)
+            elif self.mc_cycle_num == up.eq_mc_cycles:
+                if not self.walker_in_window:
+                    raise RuntimeError("Error : Not all walkers have reached their designated window")
+            else:
+                self.walker_in_window = True
+        no_switch = self.dd and self.mc_cycle_num < up.eq_mc_cycles   # :237, :244
         if self.mc_cycle_num % up.list_update_int == 0:
             for l in range(self.nlat):
                 self.compute_neighbours(l)
@@ -571,13 +615,15 @@ class Box:
                 self.att[1] += 1
                 self.trace.append((1, int(ok)))
             elif xi < self.swP:
-                ok = self.mc_lattice_switch()
-                self.att[2] += 1
-                self.trace.append((2, int(ok)))
+                if not no_switch:
+                    ok = self.mc_lattice_switch()
+                    self.att[2] += 1
+                    self.trace.append((2, int(ok)))
             if up.mc_always_switch and self.nlat == 2:
-                ok = self.mc_lattice_switch()
-                self.att[2] += 1
-                self.trace.append((3, int(ok)))
+                if not no_switch:
+                    ok = self.mc_lattice_switch()
+                    self.att[2] += 1
+                    self.trace.append((3, int(ok)))
         for l in range(self.nlat):
             self.average_energy[l] = self.average_energy[l] + self.model_energy[l]
         if up.mc_ensemble == "npt":

@@ -14,22 +14,28 @@ from tests.helpers import GOLDEN, load_example, used_lists
 
 V = np.load(os.path.join(GOLDEN, "numpy_vectors.npz"))
 CASES = {
-    "ice1_sample": {"eq_mc_cycles": 1, "mc_vol_prob": 0.04, "list_update_int": 2},
-    "single_box": {"eq_mc_cycles": 1, "mc_vol_prob": 0.04, "list_update_int": 2},
-    "ice1_gen_weights": {"eq_mc_cycles": 1, "list_update_int": 2},
+    # key: (deck, overrides, rank, size) -- tests/golden/make_fixtures_numpy.py
+    "ice1_sample": ("ice1_sample", {"eq_mc_cycles": 1, "mc_vol_prob": 0.04, "list_update_int": 2}, 0, 1),
+    "single_box": ("single_box", {"eq_mc_cycles": 1, "mc_vol_prob": 0.04, "list_update_int": 2}, 0, 1),
+    "ice1_gen_weights": ("ice1_gen_weights", {"eq_mc_cycles": 1, "list_update_int": 2}, 0, 1),
+    # single windows of the domain-decomposed decks (mc_moves.F90:660-703, :181-208, :237, :244, :808-812, :1682-1685)
+    "ice1_sample_dd@0of4": ("ice1_sample_dd", {"eq_mc_cycles": 100, "mc_vol_prob": 0.04, "list_update_int": 2}, 0, 4),
+    "ice1_sample_dd@2of4": ("ice1_sample_dd", {"eq_mc_cycles": 2, "mc_vol_prob": 0.04, "list_update_int": 2}, 2, 4),
+    "ice1_gen_weights_dd@2of4": ("ice1_gen_weights_dd", {"eq_mc_cycles": 2, "list_update_int": 2}, 2, 4),
 }
 
 
 def _oracle(name):
-    up, h, r, w, wl = load_example(name)
-    for k, v in CASES[name].items():
+    deck, ov, rank, size = CASES[name]
+    up, h, r, w, wl = load_example(deck, size=size)
+    for k, v in ov.items():
         setattr(up, k, v)
     s = orc.System(up.nwater, up.num_lattices)
     s.set_config(r, h)
     s.energy_init()
     for ils in range(1, up.num_lattices + 1):
         s.compute_model_energy(ils)
-    assert s.mc_init(orc.params_from_user(up), rank=0, size=1, weights=w, file_wl_factor=wl) == 0
+    assert s.mc_init(orc.params_from_user(up), rank=rank, size=size, weights=w, file_wl_factor=wl) == 0
     return s, up
 
 
@@ -54,6 +60,11 @@ def test_lists_and_energies_of_the_input_configuration(name):
     if nl == 2:
         assert abs(s.getd("log_unbiased_norm") - sc[3]) < 1e-10
         assert abs(s.getd("ls_mu") - V[f"{name}/mu0"][0]) < 1e-9
+        # the rank's window of the order parameter, the lattice it forces, the weights it keeps
+        win = V[f"{name}/window"]
+        assert (s.geti("my_start_bin"), s.geti("my_end_bin"), s.geti("ls")) == (int(win[0]), int(win[1]), int(win[4]))
+        assert abs(s.getd("my_mu_min") - win[2]) < 1e-11 and abs(s.getd("my_mu_max") - win[3]) < 1e-11
+        np.testing.assert_array_equal(np.array(s.weight), V[f"{name}/weight0"])
 
 
 @pytest.mark.parametrize("name", list(CASES))
