@@ -777,12 +777,29 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
                 if (hn && ctn < CK.c099) an += vn;
             };
             if (ILP == 2) {
+                // as many passes in flight as the items left need, up to three (a dense walker: 65-96 items)
 #pragma unroll 1
-                for (int t0 = first; t0 < nitems; t0 += 64) {
-                    const Item a = item_at(t0), b = item_at(t0 + 32);
-                    if (t0 == 0) { own_bond(a); __syncwarp(); }
-                    candidate(a);
-                    candidate(b);
+                for (int t0 = first; t0 < nitems;) {
+                    const int left = nitems - t0;
+                    if (left > 64) {
+                        const Item a = item_at(t0), b = item_at(t0 + 32), c = item_at(t0 + 64);
+                        if (t0 == 0) { own_bond(a); __syncwarp(); }
+                        candidate(a);
+                        candidate(b);
+                        candidate(c);
+                        t0 += 96;
+                    } else if (left > 32) {
+                        const Item a = item_at(t0), b = item_at(t0 + 32);
+                        if (t0 == 0) { own_bond(a); __syncwarp(); }
+                        candidate(a);
+                        candidate(b);
+                        t0 += 64;
+                    } else {
+                        const Item a = item_at(t0);
+                        if (t0 == 0) { own_bond(a); __syncwarp(); }
+                        candidate(a);
+                        t0 += 32;
+                    }
                 }
             } else {
 #pragma unroll 1
