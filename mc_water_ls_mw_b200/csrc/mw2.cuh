@@ -607,8 +607,9 @@ __device__ __forceinline__ void lat_bar(int bar)
     else asm volatile("bar.sync 2, 64;" ::: "memory");
 }
 
-// ILP == 2 (one warp per lattice, at most four walkers per SM: registers to spare and nothing else to issue): two
-// item passes in flight per loop turn, their dependent chains (geometry -> 1/r -> exponential) interleaved.
+// ILP = item passes in flight per loop turn (one warp per lattice; registers to spare and nothing else to issue when
+// the GPU holds few walkers): 3 in the instantiation for at most four walkers per SM, 1 everywhere else;
+// the dependent chains of the passes (geometry -> 1/r -> exponential) interleave.
 template <int NT, int WPL, int ILP>
 __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb, int imol, bool with_new, int sub, int bar,
                                               double& eo, double& en, uint32_t& mo, uint32_t& mn)
@@ -776,12 +777,12 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
                 const double vn = q[3 * RC2 + in_] * ex * (dn * dn);
                 if (hn && ctn < CK.c099) an += vn;
             };
-            if (ILP == 2) {
-                // as many passes in flight as the items left need, up to three (a dense walker: 65-96 items)
+            if (ILP >= 2) {
+                // as many passes in flight as the items left need, up to ILP (three: a dense walker's 65-96 items)
 #pragma unroll 1
                 for (int t0 = first; t0 < nitems;) {
                     const int left = nitems - t0;
-                    if (left > 64) {
+                    if (ILP >= 3 && left > 64) {
                         const Item a = item_at(t0), b = item_at(t0 + 32), c = item_at(t0 + 64);
                         if (t0 == 0) { own_bond(a); __syncwarp(); }
                         candidate(a);
@@ -942,7 +943,7 @@ __device__ __forceinline__ bool run_walker(const DeviceState& S, const McParams&
                                            int chunk, bool first)
 {
     static_assert(WPL == 1 || (WPL == 2 && NLAT == 2), "two warps per lattice: lattice-switch boxes only");
-    static_assert(ILP == 1 || WPL == 1, "two passes in flight: one warp per lattice");
+    static_assert(ILP == 1 || WPL == 1, "several passes in flight: one warp per lattice");
     constexpr int NTHR = 32 * NLAT * WPL;
     const Lay<NT> Y(S.N);
     const int tid = threadIdx.x, lane = tid & 31;

@@ -1086,12 +1086,13 @@ static int mc_run_impl(mwgpu_ctx* c, int ncycles, bool sync)
     if (gen2 && quad) {
         if (c->N == 48) MW_LAUNCH_MC2(2, 48, 4, 2, 1); else MW_LAUNCH_MC2(2, 0, 4, 2, 1);
     } else if (gen2 && c->nlat == 2) {
-        // at most four walkers per SM: two item passes in flight per warp (registers to spare, idle issue slots);
+        // at most four walkers per SM: up to three item passes in flight per warp (registers to spare, idle issue
+        // slots; at up to seven per SM two in flight measured no gain: 64-67 ms per step at 1024 walkers either way);
         // automatic selection only -- an explicit mwgpu_mc_set_kernel(2) keeps one pass per turn, the code the full
         // GPU runs, so the parity tests hold both forms to the oracle
         const bool tiny = c->walker_kernel == 0 && (long long)c->W <= 4ll * c->num_sms;
         if (c->N == 48) {
-            if (tiny) MW_LAUNCH_MC2(2, 48, 4, 1, 2);
+            if (tiny) MW_LAUNCH_MC2(2, 48, 4, 1, 3);
             else if (small) MW_LAUNCH_MC2(2, 48, MW2_BLOCKS / 2, 1, 1);
             else MW_LAUNCH_MC2(2, 48, MW2_BLOCKS, 1, 1);
         }
