@@ -701,10 +701,24 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
             if (nrounds == 1) {
                 uint32_t bmj = bmj0;
                 uint32_t* it = items + (nown + incl0 - __popc(bmj0));
+                if (ILP >= 2) {
+                    // few walkers per SM (latency, not issue slots): lowest slot from the front and highest from the
+                    // back in one turn -- half the dependent turns, the same table (an odd one out is written twice)
+                    uint32_t* ie = it + __popc(bmj0) - 1;
 #pragma unroll 1
-                while (bmj) {
-                    const int s2 = __ffs(bmj) - 1; bmj &= bmj - 1;
-                    *it++ = dbase | (uint32_t)s2;
+                    while (bmj) {
+                        const int lo = __ffs(bmj) - 1, hi = 31 - __clz(bmj);
+                        *it++ = dbase | (uint32_t)lo;
+                        *ie-- = dbase | (uint32_t)hi;
+                        bmj &= bmj - 1;
+                        bmj &= ~(1u << hi);
+                    }
+                } else {
+#pragma unroll 1
+                    while (bmj) {
+                        const int s2 = __ffs(bmj) - 1; bmj &= bmj - 1;
+                        *it++ = dbase | (uint32_t)s2;
+                    }
                 }
             } else {
                 const int lo = rd * cap, hi = min(ncand, lo + cap);
@@ -866,16 +880,40 @@ __device__ __forceinline__ int local_energies(const Lay<NT> Y, unsigned char* lb
             const uint32_t jr = recj[rr];
             const int maxd = max(no, nw) >> 1;
             double tb = 0.0;
+            if (ILP >= 2) {
+                // few walkers per SM: two steps d per turn, their loads and dot products independent; the terms are
+                // added in the same order (a masked term adds +0.0: same bits)
+                auto term = [&](int d) -> double {
+                    int c = r + d;
+                    c = (c >= send) ? c - n : c;
+                    const bool on = (d <= half) && !(even && d == half && pos >= half);
+                    c = on ? c : rr;
+                    const double ct = ux * q[c] + uy * q[RC2 + c] + uz * q[2 * RC2 + c];
+                    const double mult = (recj[c] == jr) ? 3.0 : 1.0;
+                    const double dd = ct - CK.cos0;
+                    const double v = q[3 * RC2 + c] * (dd * dd) * mult;
+                    return (on && ct < CK.c099) ? v : 0.0;
+                };
+                int d = (stride == 2) ? 1 + (lane >> 4) : 1;
 #pragma unroll 1
-            for (int d = (stride == 2) ? 1 + (lane >> 4) : 1; d <= maxd; d += stride) {
-                int c = r + d;
-                c = (c >= send) ? c - n : c;
-                const bool on = (d <= half) && !(even && d == half && pos >= half);
-                c = on ? c : rr;
-                const double ct = ux * q[c] + uy * q[RC2 + c] + uz * q[2 * RC2 + c];
-                const double mult = (recj[c] == jr) ? 3.0 : 1.0;
-                const double dd = ct - CK.cos0;
-                if (on && ct < CK.c099) tb += q[3 * RC2 + c] * (dd * dd) * mult;
+                for (; d + stride <= maxd; d += 2 * stride) {
+                    const double t1 = term(d), t2 = term(d + stride);
+                    tb += t1;
+                    tb += t2;
+                }
+                if (d <= maxd) tb += term(d);
+            } else {
+#pragma unroll 1
+                for (int d = (stride == 2) ? 1 + (lane >> 4) : 1; d <= maxd; d += stride) {
+                    int c = r + d;
+                    c = (c >= send) ? c - n : c;
+                    const bool on = (d <= half) && !(even && d == half && pos >= half);
+                    c = on ? c : rr;
+                    const double ct = ux * q[c] + uy * q[RC2 + c] + uz * q[2 * RC2 + c];
+                    const double mult = (recj[c] == jr) ? 3.0 : 1.0;
+                    const double dd = ct - CK.cos0;
+                    if (on && ct < CK.c099) tb += q[3 * RC2 + c] * (dd * dd) * mult;
+                }
             }
             tb *= CK.leps * g;
             if (sg) an += tb; else ao += tb;
