@@ -31,6 +31,16 @@ CASES = {
     "ice1_sample_dd@2of4": ("ice1_sample_dd", {"eq_mc_cycles": 2, "mc_vol_prob": 0.04, "list_update_int": 2}, 3, 505, 2, 4),
     "ice1_gen_weights_dd@2of4": ("ice1_gen_weights_dd", {"eq_mc_cycles": 2, "list_update_int": 2}, 3, 606, 2, 4),
 }
+# periodic bookkeeping that changes the walker's state, between two stretches of cycles:
+# key: (deck, overrides, cycles before, event, cycles after, rng seed)
+EVENT_CASES = {
+    # mc_monitor_stats (mc_moves.F90:1722-1732, :1786-1810) in the equilibration phase: step sizes re-tuned, stored
+    # energies replaced by fresh ones, counters reset -- the second stretch runs on all of that
+    "ice1_sample+monitor": ("ice1_sample", {"eq_mc_cycles": 100, "mc_vol_prob": 0.06, "list_update_int": 2}, 2, "monitor", 2, 707),
+    "single_box+monitor": ("single_box", {"eq_mc_cycles": 100, "mc_vol_prob": 0.06, "list_update_int": 2}, 2, "monitor", 2, 808),
+    # mc_check_chain_synchronisation (:2217-2416) after volume moves have let the two cells drift apart
+    "ice1_sample+chain_sync": ("ice1_sample", {"eq_mc_cycles": 1, "mc_vol_prob": 0.06, "list_update_int": 2}, 2, "chain_sync", 2, 910),
+}
 
 
 def load(name, ov, size=1):
@@ -86,6 +96,40 @@ def main():
         tr = np.array(b.trace)
         print(f"{name}: E0 = {b.model_energy[:nl]}, accepted {b.acc}, attempted {b.att}, draws {b.fpos}, "
               f"volume moves {(tr[:, 0] == 1).sum()}")
+    for name, (deck, ov, n1, event, n2, seed) in EVENT_CASES.items():
+        up, h, r, w, wl = load(deck, ov)
+        b = R.Box(up, h, r, weights=w, file_wl_factor=wl)
+        nl, N = b.nlat, b.N
+        u = np.random.default_rng(seed).random(8 * N * (n1 + n2) + 16)
+        out[f"{name}/fifo"] = u
+        b.set_fifo(u)
+        for _ in range(n1):
+            b.mc_cycle()
+        out[f"{name}/pre_counters"] = np.array(b.acc + b.att, dtype=np.int64)
+        if event == "monitor":
+            b.mc_monitor_stats()
+        else:
+            b.mc_check_chain_synchronisation()
+        out[f"{name}/mid_ljr"] = np.array(b.r)
+        out[f"{name}/mid_hmatrix"] = b.hflat()
+        out[f"{name}/mid_energy"] = np.array(b.model_energy[:nl])
+        out[f"{name}/mid_mu"] = np.array([b.ls_mu])
+        out[f"{name}/mid_steps"] = np.array([b.mc_max_trans, b.mc_dv_max])
+        for _ in range(n2):
+            b.mc_cycle()
+        out[f"{name}/ncycles"] = np.array([n1, n2])
+        out[f"{name}/ljr"] = np.array(b.r)
+        out[f"{name}/ref_ljr"] = np.array(b.ref)
+        out[f"{name}/hmatrix"] = b.hflat()
+        out[f"{name}/counters"] = np.array(b.acc + b.att + [b.ls, b.fpos, b.mc_cycle_num], dtype=np.int64)
+        out[f"{name}/energy"] = np.array(b.model_energy[:nl])
+        out[f"{name}/mu"] = np.array([b.ls_mu])
+        out[f"{name}/volume"] = np.array(b.volume[:nl])
+        out[f"{name}/average_energy"] = np.array(b.average_energy[:nl])
+        out[f"{name}/mc_translations"] = np.array(b.mc_translations, dtype=np.int32)
+        tr = np.array(b.trace)
+        print(f"{name}: pre {out[f'{name}/pre_counters'].tolist()}, steps {b.mc_max_trans:.6f} {b.mc_dv_max:.6f}, accepted {b.acc}, "
+              f"attempted {b.att}, draws {b.fpos}, volume moves {(tr[:, 0] == 1).sum()}")
     np.savez_compressed(os.path.join(HERE, "numpy_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "numpy_vectors.npz"))
 

@@ -14,6 +14,8 @@ keb721/mc_water_ls_mw, not from oracle/mw_oracle.c -- used to pin the C oracle (
     mc_update_wl_bins           mc_moves.F90:1597-1689
     move loop of mc_cycle       mc_moves.F90:145-255 (incl. the 'dd' window check :181-208 and the switch ban :237,:244)
     'dd' windows of mc_init     mc_moves.F90:660-703, :808-812
+    mc_monitor_stats (state effects)        mc_moves.F90:1722-1732, :1786-1810
+    mc_check_chain_synchronisation          mc_moves.F90:2217-2416
 
 Everything is IEEE double arithmetic in the reference's operation order (Python floats never contract into FMAs);
 1-based indices are kept in the list arrays (jn, vn) as the reference stores them.  Random numbers come from a
@@ -77,6 +79,7 @@ class Box:
         self.h = [[[float(hflat[l][j * 3 + i]) for j in range(3)] for i in range(3)] for l in range(self.nlat)]
         self.r = [[[float(x) for x in ljr[l][i]] for i in range(self.N)] for l in range(self.nlat)]
         self.ref = [[list(p) for p in lat] for lat in self.r]                    # init.f90:103
+        self.ref_h = [[row[:] for row in self.h[l]] for l in range(self.nlat)]   # init.f90:90
         self.recip = [recipmatrix(self.h[l]) for l in range(self.nlat)]          # init.f90:90
         self.volume = [0.0] * self.nlat
         self.model_energy = [0.0] * self.nlat
@@ -629,6 +632,51 @@ class Box:
         if up.mc_ensemble == "npt":
             for l in range(self.nlat):
                 self.average_energy[l] = self.average_energy[l] + up.pressure * self.volume[l]
+
+    # ---- periodic bookkeeping that changes the walker's state -------------------------------------------------
+    def mc_monitor_stats(self):                                   # :1722-1732, :1786-1810 (state effects only)
+        up = self.up
+        if up.eq_adjust_mc and self.mc_cycle_num < up.eq_mc_cycles:
+            # a ratio of 0 / 0 attempts is NaN in the reference; max(NaN, x) is compiler-defined -- not exercised here
+            atr = float(self.acc[0]) / float(self.att[0])
+            avr = float(self.acc[1]) / float(self.att[1])
+            self.mc_max_trans = max(self.mc_max_trans * atr / up.mc_target_ratio, 0.1)
+            self.mc_dv_max = max(self.mc_dv_max * avr / up.mc_target_ratio, 0.0001)
+        for l in range(self.nlat):                                # :1786-1792: the stored energies are replaced
+            self.compute_model_energy(l)
+        self.acc = [0, 0, 0]; self.att = [0, 0, 0]
+        self.mc_translations = [0] * self.N
+        self.average_energy = [0.0, 0.0]
+        self.max_dmu = 0.0; self.min_dmu = sys.float_info.max
+
+    def mc_check_chain_synchronisation(self):                     # :2217-2416
+        up = self.up
+        beta = 1.0 / (KB * up.temperature)
+        self.compute_model_energy(0); self.compute_model_energy(1)
+        hd = [[self.h[0][i][j] - self.ref_h[0][i][j] for j in range(3)] for i in range(3)]       # :2262
+        self.h[1] = [[self.ref_h[1][i][j] + hd[i][j] for j in range(3)] for i in range(3)]       # :2277
+        self.recip[0] = recipmatrix(self.h[0]); self.recip[1] = recipmatrix(self.h[1])
+
+        def scaled(rm, v):                                        # :2294-2306
+            t = [rm[0][c] * v[0] + rm[1][c] * v[1] + rm[2][c] * v[2] for c in range(3)]
+            return [t[c] * 0.5 * INVPI for c in range(3)]
+
+        for i in range(self.N):
+            sv = [scaled(self.recip[l], self.r[l][i]) for l in range(2)]
+            rv = [scaled(self.recip[l], self.ref[l][i]) for l in range(2)]
+            d1 = [sv[0][c] - rv[0][c] for c in range(3)]
+            s2 = [rv[1][c] + d1[c] for c in range(3)]             # :2331
+            hm = self.h[1]
+            self.r[1][i] = [hm[d][0] * s2[0] + hm[d][1] * s2[1] + hm[d][2] * s2[2] for d in range(3)]   # matmul, :2332
+        for l in range(2):
+            self.volume[l] = abs(determinant(self.h[l]))
+            self.compute_ivects(l)
+        self.compute_model_energy(0); self.compute_model_energy(1)
+        # :2409-2411 -- written without the parentheses of :1370-1372: left to right
+        mu = self.model_energy[0] + up.pressure * self.volume[0] - self.model_energy[1] - up.pressure * self.volume[1]
+        if up.leshift:
+            mu = mu - self.ref_enthalpy[0] + self.ref_enthalpy[1]
+        self.ls_mu = mu * beta - float(self.N) * math.log(self.volume[0] / self.volume[1])
 
     # ---- views for the fixtures -------------------------------------------------------------------------------
     def hflat(self):

@@ -26,7 +26,10 @@ CASES = {
 
 
 def _oracle(name):
-    deck, ov, rank, size = CASES[name]
+    return _make(*CASES[name])
+
+
+def _make(deck, ov, rank=0, size=1):
     up, h, r, w, wl = load_example(deck, size=size)
     for k, v in ov.items():
         setattr(up, k, v)
@@ -95,6 +98,55 @@ def test_chain_under_the_same_fifo(name):
         np.testing.assert_allclose(np.array(s.unbiased_hist), V[f"{name}/unbiased_hist"], rtol=1e-9, atol=1e-300)
     tr = V[f"{name}/trace"]
     assert (tr[:, 0] == 1).sum() == c[4] and tr[tr[:, 0] == 0][:, 1].sum() == c[0]
+
+
+EVENT_CASES = {
+    # key: (deck, overrides, event) -- tests/golden/make_fixtures_numpy.py
+    "ice1_sample+monitor": ("ice1_sample", {"eq_mc_cycles": 100, "mc_vol_prob": 0.06, "list_update_int": 2}, "monitor"),
+    "single_box+monitor": ("single_box", {"eq_mc_cycles": 100, "mc_vol_prob": 0.06, "list_update_int": 2}, "monitor"),
+    "ice1_sample+chain_sync": ("ice1_sample", {"eq_mc_cycles": 1, "mc_vol_prob": 0.06, "list_update_int": 2}, "chain_sync"),
+}
+
+
+@pytest.mark.parametrize("name", list(EVENT_CASES))
+def test_monitor_and_chain_synchronisation_between_two_stretches(name):
+    """mc_monitor_stats (mc_moves.F90:1722-1732, :1786-1810: step sizes re-tuned, stored energies replaced, counters
+    reset) and mc_check_chain_synchronisation (:2217-2416: lattice 2 forced onto lattice 1's displacements) between
+    two stretches of cycles: the state right after the event and the chain that runs on it."""
+    deck, ov, event = EVENT_CASES[name]
+    s, up = _make(deck, ov)
+    nl = up.num_lattices
+    s.set_rng_fifo(V[f"{name}/fifo"])
+    n1, n2 = [int(x) for x in V[f"{name}/ncycles"]]
+    assert s.mc_run(n1) == 0
+    pre = V[f"{name}/pre_counters"]
+    assert [s.geti("acc_r"), s.geti("acc_v"), s.geti("acc_s"), s.geti("att_r"), s.geti("att_v"), s.geti("att_s")] == list(pre)
+    if event == "monitor":
+        s.mc_monitor()
+        st = V[f"{name}/mid_steps"]
+        assert s.getd("mc_max_trans") == st[0] and s.getd("mc_dv_max") == st[1]
+        assert [s.geti("acc_r"), s.geti("att_r"), s.geti("att_v")] == [0, 0, 0]
+    else:
+        s.mc_chain_sync()
+    np.testing.assert_array_equal(np.array(s.ljr), V[f"{name}/mid_ljr"])
+    np.testing.assert_array_equal(np.array(s.hmatrix), V[f"{name}/mid_hmatrix"])
+    np.testing.assert_allclose(np.array(s.model_energy), V[f"{name}/mid_energy"], rtol=1e-12)
+    if nl == 2:
+        assert abs(s.getd("ls_mu") - V[f"{name}/mid_mu"][0]) < 1e-9
+    assert s.mc_run(n2) == 0
+    c = V[f"{name}/counters"]
+    assert [s.geti("acc_r"), s.geti("acc_v"), s.geti("acc_s")] == list(c[0:3])
+    assert [s.geti("att_r"), s.geti("att_v"), s.geti("att_s")] == list(c[3:6])
+    assert s.geti("ls") == c[6] and s.geti("rng_fifo_pos") == c[7] and s.geti("mc_cycle_num") == c[8]
+    np.testing.assert_array_equal(np.array(s.ljr), V[f"{name}/ljr"])
+    np.testing.assert_array_equal(np.array(s.ref_ljr), V[f"{name}/ref_ljr"])
+    np.testing.assert_array_equal(np.array(s.hmatrix), V[f"{name}/hmatrix"])
+    np.testing.assert_array_equal(np.array(s.mc_translations), V[f"{name}/mc_translations"])
+    np.testing.assert_allclose(np.array(s.model_energy), V[f"{name}/energy"], rtol=1e-12)
+    np.testing.assert_allclose(np.array(s.volume), V[f"{name}/volume"], rtol=1e-15)
+    np.testing.assert_allclose(np.array(s.arr_d("average_energy", (2,)))[:nl], V[f"{name}/average_energy"], rtol=1e-12)
+    if nl == 2:
+        assert abs(s.getd("ls_mu") - V[f"{name}/mu"][0]) < 1e-9
 
 
 def test_restatement_is_independent_of_the_oracle():
