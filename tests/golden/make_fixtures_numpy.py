@@ -30,6 +30,13 @@ CASES = {
     "ice1_sample_dd@0of4": ("ice1_sample_dd", {"eq_mc_cycles": 100, "mc_vol_prob": 0.04, "list_update_int": 2}, 3, 404, 0, 4),
     "ice1_sample_dd@2of4": ("ice1_sample_dd", {"eq_mc_cycles": 2, "mc_vol_prob": 0.04, "list_update_int": 2}, 3, 505, 2, 4),
     "ice1_gen_weights_dd@2of4": ("ice1_gen_weights_dd", {"eq_mc_cycles": 2, "list_update_int": 2}, 3, 606, 2, 4),
+    # branches of the switch / the weights the decks do not take by default
+    "ice1_sample/nvt": ("ice1_sample", {"eq_mc_cycles": 1, "mc_ensemble": "nvt", "list_update_int": 2}, 2, 1101, 0, 1),
+    "ice1_sample/leshift": ("ice1_sample", {"eq_mc_cycles": 1, "leshift": True, "mc_vol_prob": 0.04}, 2, 1202, 0, 1),
+    "ice1_sample/no_interp": ("ice1_sample", {"eq_mc_cycles": 1, "eta_interp": False, "mc_vol_prob": 0.04}, 2, 1303, 0, 1),
+    "ice1_gen_weights/switch_prob": ("ice1_gen_weights", {"eq_mc_cycles": 1, "mc_always_switch": False, "mc_switch_prob": 0.3,
+                                                          "mc_vol_prob": 0.04}, 2, 1404, 0, 1),
+    "ice1_gen_weights/swetnam": ("ice1_gen_weights", {"eq_mc_cycles": 1, "wl_swetnam": True}, 2, 1505, 0, 1),
 }
 # periodic bookkeeping that changes the walker's state, between two stretches of cycles:
 # key: (deck, overrides, cycles before, event, cycles after, rng seed)

@@ -25,8 +25,21 @@ CASES = {
 }
 
 
+# branches the decks do not take by default; CPU side only (the CUDA path is held to the oracle on the same branches in
+# tests/test_gpu_mc.py::test_single_walker_chain_bit_exact and tests/test_gpu_kernels.py::test_chain_bit_exact_on_both_kernels)
+VARIANT_CASES = {
+    "ice1_sample/nvt": ("ice1_sample", {"eq_mc_cycles": 1, "mc_ensemble": "nvt", "list_update_int": 2}, 0, 1),
+    "ice1_sample/leshift": ("ice1_sample", {"eq_mc_cycles": 1, "leshift": True, "mc_vol_prob": 0.04}, 0, 1),
+    "ice1_sample/no_interp": ("ice1_sample", {"eq_mc_cycles": 1, "eta_interp": False, "mc_vol_prob": 0.04}, 0, 1),
+    "ice1_gen_weights/switch_prob": ("ice1_gen_weights", {"eq_mc_cycles": 1, "mc_always_switch": False, "mc_switch_prob": 0.3,
+                                                          "mc_vol_prob": 0.04}, 0, 1),
+    "ice1_gen_weights/swetnam": ("ice1_gen_weights", {"eq_mc_cycles": 1, "wl_swetnam": True}, 0, 1),
+}
+ALL_CASES = {**CASES, **VARIANT_CASES}
+
+
 def _oracle(name):
-    return _make(*CASES[name])
+    return _make(*ALL_CASES[name])
 
 
 def _make(deck, ov, rank=0, size=1):
@@ -42,7 +55,7 @@ def _make(deck, ov, rank=0, size=1):
     return s, up
 
 
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", list(ALL_CASES))
 def test_lists_and_energies_of_the_input_configuration(name):
     s, up = _oracle(name)
     nl = up.num_lattices
@@ -70,7 +83,7 @@ def test_lists_and_energies_of_the_input_configuration(name):
         np.testing.assert_array_equal(np.array(s.weight), V[f"{name}/weight0"])
 
 
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", list(ALL_CASES))
 def test_chain_under_the_same_fifo(name):
     """3 cycles (2 for weight generation) with volume moves and a list refresh inside: every accept / reject decision,
     every position and every counter of the C oracle equals the numpy restatement's."""
