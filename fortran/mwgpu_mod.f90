@@ -335,7 +335,105 @@ module mwgpu
        integer(c_int),intent(out)        :: nrows,ndropped
      end function mwgpu_mc_get_therm
 
+     !---------------- many walkers per context (one MPI rank drives a batch) ----------------!
+     integer(c_int) function mwgpu_num_walkers(ctx) bind(C,name='mwgpu_num_walkers')
+       import :: c_int,c_ptr
+       type(c_ptr),value :: ctx
+     end function mwgpu_num_walkers
+
+     ! arrays carry a trailing walker dimension: ljr(3,1,nwater,nlat,nwalkers), hmatrix(3,3,nlat,nwalkers)
+     integer(c_int) function mwgpu_upload_all(ctx,ljr,ref_ljr,hmatrix) bind(C,name='mwgpu_upload_all')
+       import :: c_int,c_ptr,c_double
+       type(c_ptr),value         :: ctx
+       real(c_double),intent(in) :: ljr(*),ref_ljr(*),hmatrix(*)
+     end function mwgpu_upload_all
+
+     integer(c_int) function mwgpu_download_all(ctx,ljr,ref_ljr,hmatrix) bind(C,name='mwgpu_download_all')
+       import :: c_int,c_ptr,c_double
+       type(c_ptr),value          :: ctx
+       real(c_double),intent(out) :: ljr(*),ref_ljr(*),hmatrix(*)
+     end function mwgpu_download_all
+
+     ! compute_local_real_energy for every molecule of a lattice in one launch: energy(nwater)
+     integer(c_int) function mwgpu_compute_local_real_energy_all(ctx,walker,ils,energy) &
+          bind(C,name='mwgpu_compute_local_real_energy_all')
+       import :: c_int,c_ptr,c_double
+       type(c_ptr),value          :: ctx
+       integer(c_int),value       :: walker,ils
+       real(c_double),intent(out) :: energy(*)
+     end function mwgpu_compute_local_real_energy_all
+
+     integer(c_int) function mwgpu_compute_neighbours_all(ctx) bind(C,name='mwgpu_compute_neighbours_all')
+       import :: c_int,c_ptr
+       type(c_ptr),value :: ctx
+     end function mwgpu_compute_neighbours_all
+
+     ! compute_model_energy for every lattice of every walker: energies(nlat,nwalkers)
+     integer(c_int) function mwgpu_compute_model_energy_all(ctx,energies) bind(C,name='mwgpu_compute_model_energy_all')
+       import :: c_int,c_ptr,c_double
+       type(c_ptr),value          :: ctx
+       real(c_double),intent(out) :: energies(*)
+     end function mwgpu_compute_model_energy_all
+
+     ! mwgpu_mc_run without the host synchronisation; mwgpu_synchronize waits and reports the walkers' error flags
+     integer(c_int) function mwgpu_mc_run_async(ctx,ncycles) bind(C,name='mwgpu_mc_run_async')
+       import :: c_int,c_ptr
+       type(c_ptr),value    :: ctx
+       integer(c_int),value :: ncycles
+     end function mwgpu_mc_run_async
+
+     integer(c_int) function mwgpu_synchronize(ctx) bind(C,name='mwgpu_synchronize')
+       import :: c_int,c_ptr
+       type(c_ptr),value :: ctx
+     end function mwgpu_synchronize
+
+     integer(c_int) function mwgpu_mc_get_states(ctx,states) bind(C,name='mwgpu_mc_get_states')
+       import :: c_int,c_ptr,mwgpu_walker_state
+       type(c_ptr),value                    :: ctx
+       type(mwgpu_walker_state),intent(out) :: states(*)
+     end function mwgpu_mc_get_states
+
+     ! the bin grid of mc_init (mc_moves.F90:557-656): mu_bin(nbins), binwidth(nbins),
+     ! scalars(4) = r_pos, r_neg, av_binwidth, log_unbiased_norm
+     integer(c_int) function mwgpu_mc_get_grid(ctx,mu_bin,binwidth,scalars) bind(C,name='mwgpu_mc_get_grid')
+       import :: c_int,c_ptr,c_double
+       type(c_ptr),value          :: ctx
+       real(c_double),intent(out) :: mu_bin(*),binwidth(*),scalars(*)
+     end function mwgpu_mc_get_grid
+
+     !---------------- measurement helpers ----------------!
+     integer(c_int) function mwgpu_last_kernel_ms(ctx,ms) bind(C,name='mwgpu_last_kernel_ms')
+       import :: c_int,c_ptr,c_float
+       type(c_ptr),value        :: ctx
+       real(c_float),intent(out) :: ms
+     end function mwgpu_last_kernel_ms
+
+     integer(c_int) function mwgpu_timer_start(ctx) bind(C,name='mwgpu_timer_start')
+       import :: c_int,c_ptr
+       type(c_ptr),value :: ctx
+     end function mwgpu_timer_start
+
+     integer(c_int) function mwgpu_timer_stop(ctx,ms) bind(C,name='mwgpu_timer_stop')
+       import :: c_int,c_ptr,c_float
+       type(c_ptr),value        :: ctx
+       real(c_float),intent(out) :: ms
+     end function mwgpu_timer_stop
+
+     integer(c_int) function mwgpu_measure_fp64_peak(device,tflops) bind(C,name='mwgpu_measure_fp64_peak')
+       import :: c_int,c_double
+       integer(c_int),value       :: device
+       real(c_double),intent(out) :: tflops
+     end function mwgpu_measure_fp64_peak
+
+     integer(c_int) function mwgpu_kernel_launches(ctx,count) bind(C,name='mwgpu_kernel_launches')
+       import :: c_int,c_ptr,c_int64_t
+       type(c_ptr),value              :: ctx
+       integer(c_int64_t),intent(out) :: count
+     end function mwgpu_kernel_launches
+
      !---------------- comms ----------------!
+     ! (mwgpu_comms_reduce_local / _apply -- the in-process merge over several contexts of one process -- are not
+     !  bound here: a Fortran host has one context per MPI rank and calls mwgpu_comms_allreduce_bins)
      ! comms_join_uhist / comms_join_eta (comms_mpi.f90:299-375, :377-459)
      integer(c_int) function mwgpu_comms_join_uhist(ctx,overlap,joined) bind(C,name='mwgpu_comms_join_uhist')
        import :: c_int,c_ptr,c_double
