@@ -120,7 +120,9 @@ def test_crowded_cells_split_the_variants():
     from mc_water_ls_mw_b200._lib import MwgpuError
     o.set_rng_philox(SEED, 0, 1000000)
     assert o.mc_run(6) == 0
-    for kernel in (2, 4, 1):
+    # 0 = automatic: one walker on the GPU runs the instantiation for at most four walkers per SM, whose item loop takes
+    # up to three passes per turn -- these 90-odd items per round are what drives it through the three-pass form
+    for kernel in (2, 4, 0, 1):
         g = W.WalkerBatch(up.nwater, up.num_lattices, 1)
         g.upload(ljr, hm); g.energy_init()
         g.mc_init(W.params_from_user(up), 0, 1, w, wl)
